@@ -1,0 +1,383 @@
+// d9d_b200 — torch bindings (TORCH_LIBRARY) for the native sm_100a kernels.
+// Compiled with the host compiler only; the kernels live in *.cu translation units that do not include torch.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/torch.h>
+
+#include <tuple>
+#include <vector>
+
+#include "d9d_ops.h"
+
+namespace {
+
+using at::Tensor;
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline int dtype_code(const Tensor& t) {
+  if (t.scalar_type() == at::kBFloat16) return 0;
+  if (t.scalar_type() == at::kFloat) return 1;
+  if (t.scalar_type() == at::kHalf) return 2;
+  TORCH_CHECK(false, "d9d_b200: unsupported dtype ", t.scalar_type());
+}
+
+#define CHECK_CUDA_CONTIG(t) TORCH_CHECK((t).is_cuda() && (t).is_contiguous(), #t " must be a contiguous CUDA tensor")
+
+// ------------------------------------------------------------------ GEMM ------------------------
+int epi_for(const Tensor& d, bool accumulate) {
+  if (d.scalar_type() == at::kBFloat16) return accumulate ? 3 : 0;
+  TORCH_CHECK(d.scalar_type() == at::kFloat, "gemm output must be bf16 or fp32");
+  return accumulate ? 2 : 1;
+}
+
+// d[M,N] (+)= op(a) · op(b)^T.  a: [M,K] or (a_mn) [K,M];  b: [N,K] or (b_mn) [K,N].  Row strides may be padded.
+void gemm(const Tensor& a, const Tensor& b, Tensor d, bool a_mn, bool b_mn, bool accumulate) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda(), "gemm: CUDA tensors required");
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm: bf16 operands required");
+  TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && d.dim() == 2, "gemm: 2-D tensors required");
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && d.stride(1) == 1, "gemm: innermost stride must be 1");
+  c10::cuda::CUDAGuard guard(a.device());
+  d9d::GemmArgs g;
+  g.mode = 0;
+  g.a_mn = a_mn; g.b_mn = b_mn;
+  g.M = static_cast<int>(a_mn ? a.size(1) : a.size(0));
+  g.K = static_cast<int>(a_mn ? a.size(0) : a.size(1));
+  g.N = static_cast<int>(b_mn ? b.size(1) : b.size(0));
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == g.K, "gemm: K mismatch");
+  TORCH_CHECK(d.size(0) == g.M && d.size(1) == g.N, "gemm: output shape mismatch");
+  g.A = a.data_ptr(); g.B = b.data_ptr(); g.D = d.data_ptr();
+  g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
+  g.epi = epi_for(d, accumulate);
+  d9d::gemm_dense(g, cur_stream());
+}
+
+// d[R,N] = a[R,K] · W[e(r)];  b: [E,N,K] (b_mn=false) or [E,K,N] (b_mn=true)
+void gemm_grouped_m(const Tensor& a, const Tensor& b, Tensor d, const Tensor& tile_group, bool b_mn) {
+  CHECK_CUDA_CONTIG(a); CHECK_CUDA_CONTIG(b); CHECK_CUDA_CONTIG(d); CHECK_CUDA_CONTIG(tile_group);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && d.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(tile_group.scalar_type() == at::kInt && a.size(0) % 128 == 0 && tile_group.numel() == a.size(0) / 128);
+  c10::cuda::CUDAGuard guard(a.device());
+  d9d::GemmArgs g;
+  g.mode = 1; g.epi = 0; g.a_mn = false; g.b_mn = b_mn;
+  g.M = static_cast<int>(a.size(0)); g.K = static_cast<int>(a.size(1));
+  g.N = static_cast<int>(b_mn ? b.size(2) : b.size(1));
+  TORCH_CHECK((b_mn ? b.size(1) : b.size(2)) == g.K, "gemm_grouped_m: K mismatch");
+  TORCH_CHECK(d.size(0) == g.M && d.size(1) == g.N);
+  g.num_groups = static_cast<int>(b.size(0));
+  g.A = a.data_ptr(); g.B = b.data_ptr(); g.D = d.data_ptr();
+  g.lda = a.stride(0); g.ldb = b.stride(1); g.ldd = d.stride(0);
+  g.b_group_stride = b.stride(0);
+  g.tile_group = tile_group.data_ptr<int>();
+  d9d::gemm_grouped(g, cur_stream());
+}
+
+// d[E,M,N] (+)= a[rows_e, M]^T · b[rows_e, N] over each expert's row range group_offsets[e]..[e+1]
+void gemm_grouped_k(const Tensor& a, const Tensor& b, Tensor d, const Tensor& group_offsets, bool accumulate) {
+  CHECK_CUDA_CONTIG(a); CHECK_CUDA_CONTIG(b); CHECK_CUDA_CONTIG(d); CHECK_CUDA_CONTIG(group_offsets);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(group_offsets.scalar_type() == at::kInt && a.size(0) == b.size(0));
+  c10::cuda::CUDAGuard guard(a.device());
+  d9d::GemmArgs g;
+  g.mode = 2; g.a_mn = true; g.b_mn = true;
+  g.M = static_cast<int>(a.size(1)); g.N = static_cast<int>(b.size(1)); g.K = 0;
+  g.k_total = a.size(0);
+  g.num_groups = static_cast<int>(d.size(0));
+  TORCH_CHECK(group_offsets.numel() == g.num_groups + 1 && d.size(1) == g.M && d.size(2) == g.N);
+  g.A = a.data_ptr(); g.B = b.data_ptr(); g.D = d.data_ptr();
+  g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(1); g.d_group_stride = d.stride(0);
+  g.group_offsets = group_offsets.data_ptr<int>();
+  g.epi = epi_for(d, accumulate);
+  d9d::gemm_grouped(g, cur_stream());
+}
+
+// fused linear-CE forward: returns (nll[T] fp32, lse[T] fp32)
+std::tuple<Tensor, Tensor> ce_forward(const Tensor& h, const Tensor& w, const Tensor& target, int64_t ignore_index) {
+  CHECK_CUDA_CONTIG(h); CHECK_CUDA_CONTIG(w); CHECK_CUDA_CONTIG(target);
+  TORCH_CHECK(h.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && target.scalar_type() == at::kLong);
+  c10::cuda::CUDAGuard guard(h.device());
+  const int T = static_cast<int>(h.size(0)), K = static_cast<int>(h.size(1)), V = static_cast<int>(w.size(0));
+  TORCH_CHECK(w.size(1) == K && target.numel() == T);
+  const int bn = d9d::gemm_ce_block_n();
+  const int n_tiles = (V + bn - 1) / bn;
+  auto fopt = h.options().dtype(at::kFloat);
+  Tensor part_max = at::empty({n_tiles, T}, fopt), part_sum = at::empty({n_tiles, T}, fopt);
+  Tensor tgt_logit = at::zeros({T}, fopt), lse = at::empty({T}, fopt), nll = at::empty({T}, fopt);
+  d9d::GemmArgs g;
+  g.mode = 0; g.epi = 4;
+  g.M = T; g.N = V; g.K = K;
+  g.A = h.data_ptr(); g.B = w.data_ptr(); g.lda = K; g.ldb = K; g.ldd = V;
+  g.ce_target = target.data_ptr<int64_t>() ? reinterpret_cast<const long long*>(target.data_ptr<int64_t>()) : nullptr;
+  g.ce_part_max = part_max.data_ptr<float>(); g.ce_part_sum = part_sum.data_ptr<float>();
+  g.ce_tgt_logit = tgt_logit.data_ptr<float>();
+  g.ce_ignore_index = ignore_index;
+  d9d::gemm_ce(g, cur_stream());
+  d9d::ce_finalize(part_max.data_ptr<float>(), part_sum.data_ptr<float>(), tgt_logit.data_ptr<float>(),
+                   reinterpret_cast<const long long*>(target.data_ptr<int64_t>()), ignore_index, n_tiles, T,
+                   lse.data_ptr<float>(), nll.data_ptr<float>(), cur_stream());
+  return {nll, lse};
+}
+
+// fused linear-CE backward, one token chunk: out[Tc, V] (bf16) = grad[t] * (softmax(h w^T) - onehot(target))
+void ce_dlogits(const Tensor& h, const Tensor& w, const Tensor& target, const Tensor& lse, const Tensor& grad,
+                Tensor out, int64_t ignore_index) {
+  CHECK_CUDA_CONTIG(h); CHECK_CUDA_CONTIG(w); CHECK_CUDA_CONTIG(target); CHECK_CUDA_CONTIG(lse);
+  CHECK_CUDA_CONTIG(grad); CHECK_CUDA_CONTIG(out);
+  TORCH_CHECK(out.scalar_type() == at::kBFloat16 && lse.scalar_type() == at::kFloat && grad.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(h.device());
+  const int T = static_cast<int>(h.size(0)), K = static_cast<int>(h.size(1)), V = static_cast<int>(w.size(0));
+  TORCH_CHECK(out.size(0) == T && out.size(1) == V);
+  d9d::GemmArgs g;
+  g.mode = 0; g.epi = 5;
+  g.M = T; g.N = V; g.K = K;
+  g.A = h.data_ptr(); g.B = w.data_ptr(); g.D = out.data_ptr(); g.lda = K; g.ldb = K; g.ldd = V;
+  g.ce_target = reinterpret_cast<const long long*>(target.data_ptr<int64_t>());
+  g.ce_lse = lse.data_ptr<float>(); g.ce_grad = grad.data_ptr<float>();
+  g.ce_ignore_index = ignore_index;
+  d9d::gemm_ce(g, cur_stream());
+}
+
+// ------------------------------------------------------------------ RMSNorm ---------------------
+std::tuple<Tensor, Tensor> rms_norm_fwd(const Tensor& x, const Tensor& w, double eps, bool zero_centered) {
+  CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(w);
+  TORCH_CHECK(x.scalar_type() == w.scalar_type(), "rms_norm: x and weight dtypes must match");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int N = static_cast<int>(x.size(-1));
+  const int64_t M = x.numel() / N;
+  Tensor out = at::empty_like(x);
+  Tensor inv = at::empty({M}, x.options().dtype(at::kFloat));
+  d9d::rms_norm_fwd(x.data_ptr(), w.data_ptr(), out.data_ptr(), inv.data_ptr<float>(), M, N, static_cast<float>(eps),
+                    zero_centered, dtype_code(x), cur_stream());
+  return {out, inv};
+}
+
+std::tuple<Tensor, Tensor> rms_norm_bwd(const Tensor& dout, const Tensor& x, const Tensor& w, const Tensor& inv_rms,
+                                        bool zero_centered) {
+  CHECK_CUDA_CONTIG(dout); CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(w); CHECK_CUDA_CONTIG(inv_rms);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int N = static_cast<int>(x.size(-1));
+  const int64_t M = x.numel() / N;
+  Tensor dx = at::empty_like(x);
+  Tensor dw = at::empty_like(w);
+  Tensor partial = at::empty({d9d::rms_norm_bwd_num_partials(), N}, x.options().dtype(at::kFloat));
+  d9d::rms_norm_bwd(dout.data_ptr(), x.data_ptr(), w.data_ptr(), inv_rms.data_ptr<float>(), dx.data_ptr(),
+                    dw.data_ptr(), partial.data_ptr<float>(), M, N, zero_centered, dtype_code(x), cur_stream());
+  return {dx, dw};
+}
+
+// ------------------------------------------------------------------ SiLU * mul -------------------
+Tensor silu_mul_fwd(const Tensor& x, const Tensor& y) {
+  CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(y);
+  TORCH_CHECK(x.scalar_type() == y.scalar_type() && x.numel() == y.numel());
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = at::empty_like(x);
+  d9d::silu_mul_fwd(x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(), dtype_code(x), cur_stream());
+  return out;
+}
+
+std::tuple<Tensor, Tensor> silu_mul_bwd(const Tensor& dout, const Tensor& x, const Tensor& y) {
+  CHECK_CUDA_CONTIG(dout); CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(y);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor dx = at::empty_like(x), dy = at::empty_like(y);
+  d9d::silu_mul_bwd(dout.data_ptr(), x.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.data_ptr(), x.numel(),
+                    dtype_code(x), cur_stream());
+  return {dx, dy};
+}
+
+Tensor silu_mul_probs_fwd(const Tensor& x, const Tensor& y, const Tensor& probs) {
+  CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(y); CHECK_CUDA_CONTIG(probs);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 && probs.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor out = at::empty_like(x);
+  d9d::silu_mul_probs_fwd(x.data_ptr(), y.data_ptr(), probs.data_ptr<float>(), out.data_ptr(), x.size(0),
+                          static_cast<int>(x.size(1)), cur_stream());
+  return out;
+}
+
+std::tuple<Tensor, Tensor, Tensor> silu_mul_probs_bwd(const Tensor& dout, const Tensor& x, const Tensor& y,
+                                                      const Tensor& probs) {
+  CHECK_CUDA_CONTIG(dout); CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(y); CHECK_CUDA_CONTIG(probs);
+  c10::cuda::CUDAGuard guard(x.device());
+  Tensor dx = at::empty_like(x), dy = at::empty_like(y), dp = at::empty_like(probs);
+  d9d::silu_mul_probs_bwd(dout.data_ptr(), x.data_ptr(), y.data_ptr(), probs.data_ptr<float>(), dx.data_ptr(),
+                          dy.data_ptr(), dp.data_ptr<float>(), x.size(0), static_cast<int>(x.size(1)), cur_stream());
+  return {dx, dy, dp};
+}
+
+// ------------------------------------------------------------------ stochastic rounding ----------
+void sr_copy_(Tensor dst, const Tensor& src, int64_t seed) {
+  CHECK_CUDA_CONTIG(dst); CHECK_CUDA_CONTIG(src);
+  TORCH_CHECK(dst.scalar_type() == at::kBFloat16 && src.scalar_type() == at::kFloat && dst.numel() == src.numel());
+  c10::cuda::CUDAGuard guard(src.device());
+  d9d::sr_copy_f32_to_bf16(src.data_ptr<float>(), dst.data_ptr(), src.numel(), static_cast<uint64_t>(seed), cur_stream());
+}
+
+// metas: int64 [n_tensors, 6] = (p, g, m, v, numel, rng_base) in device memory; block_map: int32 [n_blocks, 2]
+void adamw_sr_multi_(const Tensor& metas, const Tensor& block_map, double lr, double beta1, double beta2, double eps,
+                     double weight_decay, int64_t step, int64_t seed, const c10::optional<Tensor>& grad_scale,
+                     bool grad_bf16, bool state_bf16) {
+  CHECK_CUDA_CONTIG(metas); CHECK_CUDA_CONTIG(block_map);
+  TORCH_CHECK(metas.scalar_type() == at::kLong && metas.size(1) == 6 && block_map.scalar_type() == at::kInt);
+  static_assert(sizeof(d9d::AdamTensorMeta) == 6 * sizeof(int64_t), "meta layout");
+  c10::cuda::CUDAGuard guard(metas.device());
+  const double bc1 = 1.0 - std::exp(static_cast<double>(step) * std::log(beta1));
+  const double bc2 = 1.0 - std::exp(static_cast<double>(step) * std::log(beta2));
+  const float* gs = nullptr;
+  if (grad_scale.has_value()) {
+    TORCH_CHECK(grad_scale->is_cuda() && grad_scale->scalar_type() == at::kFloat && grad_scale->numel() == 1);
+    gs = grad_scale->data_ptr<float>();
+  }
+  d9d::adamw_sr_multi(reinterpret_cast<const d9d::AdamTensorMeta*>(metas.data_ptr<int64_t>()),
+                      reinterpret_cast<const int2*>(block_map.data_ptr<int>()), static_cast<int>(block_map.size(0)),
+                      static_cast<float>(lr), static_cast<float>(beta1), static_cast<float>(beta2),
+                      static_cast<float>(eps), static_cast<float>(weight_decay), static_cast<float>(bc1),
+                      static_cast<float>(bc2), static_cast<uint64_t>(seed), gs, grad_bf16, state_bf16, cur_stream());
+}
+
+// ------------------------------------------------------------------ RoPE -------------------------
+// x: [T, H, D] view (token stride arbitrary, head/dim contiguous); cos/sin: [max_pos, rope_dim] fp32; pos: [T] int64
+Tensor rope_apply(const Tensor& x, const Tensor& cos_cache, const Tensor& sin_cache, const Tensor& pos, int64_t style,
+                  bool inverse) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 3 && x.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(x.stride(2) == 1 && x.stride(1) == x.size(2), "rope: heads must be contiguous");
+  CHECK_CUDA_CONTIG(cos_cache); CHECK_CUDA_CONTIG(sin_cache); CHECK_CUDA_CONTIG(pos);
+  TORCH_CHECK(cos_cache.scalar_type() == at::kFloat && sin_cache.scalar_type() == at::kFloat && pos.scalar_type() == at::kLong);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t T = x.size(0);
+  const int H = static_cast<int>(x.size(1)), D = static_cast<int>(x.size(2));
+  Tensor out = at::empty({T, H, D}, x.options());
+  d9d::rope_apply(x.data_ptr(), out.data_ptr(), cos_cache.data_ptr<float>(), sin_cache.data_ptr<float>(),
+                  reinterpret_cast<const long long*>(pos.data_ptr<int64_t>()), T, H, D,
+                  static_cast<int>(cos_cache.size(1)), x.stride(0), static_cast<int64_t>(H) * D,
+                  static_cast<int>(style), inverse, cur_stream());
+  return out;
+}
+
+// ------------------------------------------------------------------ MoE --------------------------
+// -> (counts[E], seg_offsets[E+1], row_map[T*k], tile_group[capacity/128])   all int32, no host sync
+std::tuple<Tensor, Tensor, Tensor, Tensor> moe_build_layout(const Tensor& topk_ids, int64_t num_experts, int64_t align,
+                                                            int64_t capacity) {
+  CHECK_CUDA_CONTIG(topk_ids);
+  TORCH_CHECK(topk_ids.scalar_type() == at::kLong && topk_ids.dim() == 2);
+  c10::cuda::CUDAGuard guard(topk_ids.device());
+  const int64_t T = topk_ids.size(0), k = topk_ids.size(1);
+  auto iopt = topk_ids.options().dtype(at::kInt);
+  Tensor counts = at::empty({num_experts}, iopt), seg = at::empty({num_experts + 1}, iopt);
+  Tensor row_map = at::empty({T * k}, iopt), tile_group = at::empty({capacity / 128}, iopt);
+  Tensor scratch = at::empty({std::max<int64_t>(1, d9d::moe_layout_scratch_ints(T * k, static_cast<int>(num_experts)))}, iopt);
+  d9d::moe_build_layout(reinterpret_cast<const long long*>(topk_ids.data_ptr<int64_t>()), T, static_cast<int>(k),
+                        static_cast<int>(num_experts), static_cast<int>(align), capacity, counts.data_ptr<int>(),
+                        seg.data_ptr<int>(), row_map.data_ptr<int>(), tile_group.data_ptr<int>(),
+                        scratch.data_ptr<int>(), cur_stream());
+  return {counts, seg, row_map, tile_group};
+}
+
+// x[T,H] (+ probs[T,k]) -> xp[capacity,H] (+ pp[capacity]); pad rows zeroed, rows past the last segment untouched
+std::tuple<Tensor, Tensor> moe_permute(const Tensor& x, const c10::optional<Tensor>& probs, const Tensor& row_map,
+                                       const Tensor& counts, const Tensor& seg_offsets, int64_t capacity) {
+  CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(row_map);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.dim() == 2);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t T = x.size(0), H = x.size(1);
+  const int k = static_cast<int>(row_map.numel() / std::max<int64_t>(T, 1));
+  Tensor xp = at::empty({capacity, H}, x.options());
+  Tensor pp;
+  const float* pptr = nullptr;
+  float* ppout = nullptr;
+  if (probs.has_value()) {
+    TORCH_CHECK(probs->is_contiguous() && probs->scalar_type() == at::kFloat);
+    pp = at::empty({capacity}, x.options().dtype(at::kFloat));
+    pptr = probs->data_ptr<float>();
+    ppout = pp.data_ptr<float>();
+  } else {
+    pp = at::empty({0}, x.options().dtype(at::kFloat));
+  }
+  d9d::moe_permute(x.data_ptr(), pptr, row_map.data_ptr<int>(), xp.data_ptr(), ppout, T, k, static_cast<int>(H), cur_stream());
+  d9d::moe_zero_pad(xp.data_ptr(), ppout, counts.data_ptr<int>(), seg_offsets.data_ptr<int>(),
+                    static_cast<int>(counts.numel()), static_cast<int>(H), cur_stream());
+  return {xp, pp};
+}
+
+// y[T,H] = sum_j yp[row_map[t,j]];   with dpp: also dprobs[T,k] = dpp[row_map[t,j]]
+std::tuple<Tensor, Tensor> moe_gather(const Tensor& yp, const c10::optional<Tensor>& dpp, const Tensor& row_map,
+                                      int64_t T, int64_t k) {
+  CHECK_CUDA_CONTIG(yp); CHECK_CUDA_CONTIG(row_map);
+  TORCH_CHECK(yp.scalar_type() == at::kBFloat16 && row_map.numel() == T * k);
+  c10::cuda::CUDAGuard guard(yp.device());
+  const int H = static_cast<int>(yp.size(1));
+  Tensor y = at::empty({T, H}, yp.options());
+  Tensor dprobs;
+  if (dpp.has_value()) {
+    dprobs = at::empty({T, k}, yp.options().dtype(at::kFloat));
+    d9d::moe_permute_bwd(yp.data_ptr(), dpp->data_ptr<float>(), row_map.data_ptr<int>(), y.data_ptr(),
+                         dprobs.data_ptr<float>(), T, static_cast<int>(k), H, cur_stream());
+  } else {
+    dprobs = at::empty({0}, yp.options().dtype(at::kFloat));
+    d9d::moe_unpermute(yp.data_ptr(), row_map.data_ptr<int>(), y.data_ptr(), T, static_cast<int>(k), H, cur_stream());
+  }
+  return {y, dprobs};
+}
+
+// ------------------------------------------------------------------ grad utils -------------------
+void sumsq_accumulate_(const Tensor& x, Tensor out) {
+  CHECK_CUDA_CONTIG(x);
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kFloat && out.numel() == 1);
+  c10::cuda::CUDAGuard guard(x.device());
+  d9d::sumsq_accumulate(x.data_ptr(), x.numel(), dtype_code(x), out.data_ptr<float>(), cur_stream());
+}
+
+void scale_inplace_(Tensor x, const Tensor& scale) {
+  CHECK_CUDA_CONTIG(x);
+  TORCH_CHECK(scale.is_cuda() && scale.scalar_type() == at::kFloat && scale.numel() == 1);
+  c10::cuda::CUDAGuard guard(x.device());
+  d9d::scale_inplace(x.data_ptr(), x.numel(), dtype_code(x), scale.data_ptr<float>(), cur_stream());
+}
+
+}  // namespace
+
+TORCH_LIBRARY(d9d_b200, m) {
+  m.def("gemm(Tensor a, Tensor b, Tensor(a!) d, bool a_mn, bool b_mn, bool accumulate) -> ()");
+  m.def("gemm_grouped_m(Tensor a, Tensor b, Tensor(a!) d, Tensor tile_group, bool b_mn) -> ()");
+  m.def("gemm_grouped_k(Tensor a, Tensor b, Tensor(a!) d, Tensor group_offsets, bool accumulate) -> ()");
+  m.def("ce_forward(Tensor h, Tensor w, Tensor target, int ignore_index) -> (Tensor, Tensor)");
+  m.def("ce_dlogits(Tensor h, Tensor w, Tensor target, Tensor lse, Tensor grad, Tensor(a!) out, int ignore_index) -> ()");
+  m.def("rms_norm_fwd(Tensor x, Tensor w, float eps, bool zero_centered) -> (Tensor, Tensor)");
+  m.def("rms_norm_bwd(Tensor dout, Tensor x, Tensor w, Tensor inv_rms, bool zero_centered) -> (Tensor, Tensor)");
+  m.def("silu_mul_fwd(Tensor x, Tensor y) -> Tensor");
+  m.def("silu_mul_bwd(Tensor dout, Tensor x, Tensor y) -> (Tensor, Tensor)");
+  m.def("silu_mul_probs_fwd(Tensor x, Tensor y, Tensor probs) -> Tensor");
+  m.def("silu_mul_probs_bwd(Tensor dout, Tensor x, Tensor y, Tensor probs) -> (Tensor, Tensor, Tensor)");
+  m.def("sr_copy_(Tensor(a!) dst, Tensor src, int seed) -> ()");
+  m.def(
+      "adamw_sr_multi_(Tensor metas, Tensor block_map, float lr, float beta1, float beta2, float eps, float "
+      "weight_decay, int step, int seed, Tensor? grad_scale, bool grad_bf16, bool state_bf16) -> ()");
+  m.def("rope_apply(Tensor x, Tensor cos_cache, Tensor sin_cache, Tensor pos, int style, bool inverse) -> Tensor");
+  m.def("moe_build_layout(Tensor topk_ids, int num_experts, int align, int capacity) -> (Tensor, Tensor, Tensor, Tensor)");
+  m.def("moe_permute(Tensor x, Tensor? probs, Tensor row_map, Tensor counts, Tensor seg_offsets, int capacity) -> (Tensor, Tensor)");
+  m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
+  m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
+  m.def("scale_inplace_(Tensor(a!) x, Tensor scale) -> ()");
+}
+
+TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
+  m.impl("gemm", &gemm);
+  m.impl("gemm_grouped_m", &gemm_grouped_m);
+  m.impl("gemm_grouped_k", &gemm_grouped_k);
+  m.impl("ce_forward", &ce_forward);
+  m.impl("ce_dlogits", &ce_dlogits);
+  m.impl("rms_norm_fwd", &rms_norm_fwd);
+  m.impl("rms_norm_bwd", &rms_norm_bwd);
+  m.impl("silu_mul_fwd", &silu_mul_fwd);
+  m.impl("silu_mul_bwd", &silu_mul_bwd);
+  m.impl("silu_mul_probs_fwd", &silu_mul_probs_fwd);
+  m.impl("silu_mul_probs_bwd", &silu_mul_probs_bwd);
+  m.impl("sr_copy_", &sr_copy_);
+  m.impl("adamw_sr_multi_", &adamw_sr_multi_);
+  m.impl("rope_apply", &rope_apply);
+  m.impl("moe_build_layout", &moe_build_layout);
+  m.impl("moe_permute", &moe_permute);
+  m.impl("moe_gather", &moe_gather);
+  m.impl("sumsq_accumulate_", &sumsq_accumulate_);
+  m.impl("scale_inplace_", &scale_inplace_);
+}

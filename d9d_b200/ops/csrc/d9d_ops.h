@@ -1,0 +1,116 @@
+// d9d_b200 native op launchers (plain C++ API, no torch dependency).
+// Every launcher enqueues work on `stream` and returns immediately.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace d9d {
+
+// ------------------------------------------------------------------ GEMM (tcgen05) ---------------
+struct GemmArgs {
+  int mode = 0;        // gemm::Mode
+  int epi = 0;         // gemm::Epi
+  bool a_mn = false;   // A stored [K, M] (M contiguous) instead of [M, K]
+  bool b_mn = false;   // B stored [K, N] (N contiguous) instead of [N, K]
+  const void* A = nullptr;
+  const void* B = nullptr;
+  void* D = nullptr;
+  long long lda = 0, ldb = 0, ldd = 0;  // leading dims in elements
+  long long b_group_stride = 0;         // GROUPED_M: elements between experts in B (0 => dense packing)
+  long long d_group_stride = 0;         // GROUPED_K: elements between experts in D
+  int M = 0, N = 0, K = 0;
+  int num_groups = 1;
+  long long k_total = 0;               // GROUPED_K: total rows of the grouped reduction dim
+  const int* tile_group = nullptr;     // GROUPED_M
+  const int* group_offsets = nullptr;  // GROUPED_K
+  int block_n = 0;                     // 0 => heuristic
+  // fused linear cross entropy
+  const long long* ce_target = nullptr;
+  const float* ce_lse = nullptr;
+  const float* ce_grad = nullptr;
+  float* ce_part_max = nullptr;
+  float* ce_part_sum = nullptr;
+  float* ce_tgt_logit = nullptr;
+  long long ce_ignore_index = -100;
+};
+
+void gemm_dense(const GemmArgs& a, cudaStream_t stream);
+void gemm_grouped(const GemmArgs& a, cudaStream_t stream);
+void gemm_ce(const GemmArgs& a, cudaStream_t stream);
+int gemm_ce_block_n();
+// (part_max, part_sum)[n_tiles, M] + tgt_logit[M] -> lse[M], nll[M] (0 where target == ignore_index)
+void ce_finalize(const float* part_max, const float* part_sum, const float* tgt_logit, const long long* target,
+                 long long ignore_index, int n_tiles, int M, float* lse, float* nll, cudaStream_t stream);
+
+// ------------------------------------------------------------------ normalisation ----------------
+// dtype codes: 0 = bf16, 1 = fp32, 2 = fp16
+void rms_norm_fwd(const void* x, const void* w, void* out, float* inv_rms, long long M, int N, float eps,
+                  bool zero_centered, int dtype, cudaStream_t stream);
+// dw_partial: [rms_norm_bwd_num_partials(), N] fp32 scratch; dw: [N] in dtype
+int rms_norm_bwd_num_partials();
+void rms_norm_bwd(const void* dout, const void* x, const void* w, const float* inv_rms, void* dx, void* dw,
+                  float* dw_partial, long long M, int N, bool zero_centered, int dtype, cudaStream_t stream);
+
+// ------------------------------------------------------------------ activations ------------------
+void silu_mul_fwd(const void* x, const void* y, void* out, long long n, int dtype, cudaStream_t stream);
+void silu_mul_bwd(const void* dout, const void* x, const void* y, void* dx, void* dy, long long n, int dtype,
+                  cudaStream_t stream);
+// MoE variant: out[r, :] = silu(x) * y * probs[r];  bwd also yields dprobs[r]
+void silu_mul_probs_fwd(const void* x, const void* y, const float* probs, void* out, long long rows, int cols,
+                        cudaStream_t stream);
+void silu_mul_probs_bwd(const void* dout, const void* x, const void* y, const float* probs, void* dx, void* dy,
+                        float* dprobs, long long rows, int cols, cudaStream_t stream);
+
+// ------------------------------------------------------------------ stochastic rounding ----------
+void sr_copy_f32_to_bf16(const float* src, void* dst, long long n, uint64_t seed, cudaStream_t stream);
+
+struct AdamTensorMeta {
+  void* p;        // bf16
+  const void* g;  // bf16 or fp32
+  void* m;        // bf16 or fp32
+  void* v;        // bf16 or fp32
+  long long n;
+  long long rng_base;  // element offset into the launch-wide philox stream
+};
+// metas / block_map live in device memory. block_map[b] = {tensor index, chunk index}; chunk = ADAM_CHUNK elements.
+constexpr int ADAM_CHUNK = 8192;
+void adamw_sr_multi(const AdamTensorMeta* metas, const int2* block_map, int num_blocks, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2, uint64_t seed,
+                    const float* grad_scale /*device scalar or null*/, bool grad_bf16, bool state_bf16,
+                    cudaStream_t stream);
+
+// ------------------------------------------------------------------ RoPE (+ fused q/k RMSNorm) ---
+// x: [T, H, D] (row stride = ldx elements per token), cos/sin cache: [max_pos, rope_dim] fp32 or bf16 (as float here),
+// pos: [T] int64. style 0 = HALF, 1 = INTERLEAVED. inverse => apply the transposed rotation (backward).
+void rope_apply(const void* x, void* out, const float* cos_cache, const float* sin_cache, const long long* pos,
+                long long T, int H, int D, int rope_dim, long long ldx, long long ldo, int style, bool inverse,
+                cudaStream_t stream);
+
+// ------------------------------------------------------------------ MoE routing / permutation ----
+// Builds the 128-row-aligned expert-sorted layout fully on device (no host sync):
+//   topk_ids [T, k] int64 (ids outside [0, E) are dropped)
+//   -> counts[E], seg_offsets[E+1] (aligned to `align`), row_map[T*k] (dest row or -1),
+//      tile_group[cap/128] (expert per 128-row tile or -1), total_rows[1]
+long long moe_layout_scratch_ints(long long n_entries, int E);
+void moe_build_layout(const long long* topk_ids, long long T, int k, int E, int align, long long capacity_rows,
+                      int* counts, int* seg_offsets, int* row_map, int* tile_group, int* chunk_scratch,
+                      cudaStream_t stream);
+// zero the pad rows [seg_offsets[e] + counts[e], seg_offsets[e+1]) of xp (and pp if given)
+void moe_zero_pad(void* xp, float* pp, const int* counts, const int* seg_offsets, int E, int H, cudaStream_t stream);
+// x[T,H] -> xp[cap,H] (rows not written stay zero: caller zero-fills), probs[T,k] -> pp[cap]
+void moe_permute(const void* x, const float* probs, const int* row_map, void* xp, float* pp, long long T, int k,
+                 int H, cudaStream_t stream);
+// y[T,H] = sum_k yp[row_map[t,k], :]   (fp32 accumulate)
+void moe_unpermute(const void* yp, const int* row_map, void* y, long long T, int k, int H, cudaStream_t stream);
+// backward of permute: dx[T,H] = sum_k dxp[row_map[t,k]], dprobs[T,k] = dpp[row_map[t,k]]
+void moe_permute_bwd(const void* dxp, const float* dpp, const int* row_map, void* dx, float* dprobs, long long T,
+                     int k, int H, cudaStream_t stream);
+
+// ------------------------------------------------------------------ grad utilities ---------------
+// out[0] += sum(x^2) over a flat fp32/bf16 buffer (dtype code as above)
+void sumsq_accumulate(const void* x, long long n, int dtype, float* out, cudaStream_t stream);
+// x *= *scale (device scalar)
+void scale_inplace(void* x, long long n, int dtype, const float* scale, cudaStream_t stream);
+
+}  // namespace d9d

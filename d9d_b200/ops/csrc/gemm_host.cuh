@@ -1,0 +1,129 @@
+// Host-side launcher pieces for the tcgen05 GEMM: TMA descriptor encoding + dispatch helpers.
+#pragma once
+
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "d9d_ops.h"
+#include "gemm_sm100.cuh"
+
+namespace d9d {
+namespace gemm {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved at run time so the extension has no link-time dependency on libcuda (CPU-only build hosts)
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || p == nullptr) throw std::runtime_error("d9d: cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 3-D bf16 tensor map, 128B swizzle. dims/strides innermost-first; strides in elements for dims 1,2.
+inline CUtensorMap make_tmap_bf16_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                                     uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (strides[0] & 15) != 0 || (strides[1] & 15) != 0)
+    throw std::runtime_error("d9d gemm: operand base/strides must be 16-byte aligned for TMA");
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("d9d gemm: cuTensorMapEncodeTiled failed: " + std::to_string(r));
+  return m;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+void launch_one(const GemmArgs& a, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  auto kern = gemm_kernel<MODE, BLOCK_N, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    configured = true;
+  }
+  // ---- tensor maps ----
+  CUtensorMap ta, tb;
+  if (MODE == GROUPED_K) {
+    // A: [R, M] (M contiguous), B: [R, N] (N contiguous); reduction over grouped rows
+    ta = make_tmap_bf16_3d(a.A, a.M, a.k_total, 1, a.lda, a.lda * a.k_total, 64, BLOCK_K);
+    tb = make_tmap_bf16_3d(a.B, a.N, a.k_total, 1, a.ldb, a.ldb * a.k_total, 64, BLOCK_K);
+  } else {
+    if (!A_MN) ta = make_tmap_bf16_3d(a.A, a.K, a.M, 1, a.lda, a.lda * a.M, 64, BLOCK_M);
+    else       ta = make_tmap_bf16_3d(a.A, a.M, a.K, 1, a.lda, a.lda * a.K, 64, BLOCK_K);
+    const uint64_t g = (MODE == GROUPED_M) ? a.num_groups : 1;
+    if (!B_MN) tb = make_tmap_bf16_3d(a.B, a.K, a.N, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.N, 64, BLOCK_N);
+    else       tb = make_tmap_bf16_3d(a.B, a.N, a.K, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.K, 64, BLOCK_K);
+  }
+  Params p{};
+  p.M = a.M; p.N = a.N; p.K = a.K; p.num_groups = a.num_groups;
+  p.D = a.D; p.ldd = a.ldd; p.d_group_stride = a.d_group_stride;
+  p.tile_group = a.tile_group; p.group_offsets = a.group_offsets;
+  p.ce_target = a.ce_target; p.ce_lse = a.ce_lse; p.ce_grad = a.ce_grad;
+  p.ce_part_max = a.ce_part_max; p.ce_part_sum = a.ce_part_sum; p.ce_tgt_logit = a.ce_tgt_logit;
+  p.ce_ignore_index = a.ce_ignore_index; p.ce_softcap = 0.f;
+
+  const long long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+  long long tiles = m_tiles * n_tiles * (MODE == GROUPED_K ? a.num_groups : 1);
+  if (tiles <= 0) return;
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+}
+
+// pick BLOCK_N minimising (waves x tile cost); ties go to the wider tile
+inline int pick_block_n(long long m_tiles_x_groups, int N) {
+  const int cands[3] = {256, 192, 128};
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    const long long tiles = m_tiles_x_groups * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sm_count() - 1) / sm_count();
+    const double cost = static_cast<double>(waves) * (bn + 24 /*fixed per-tile overhead*/);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+#define D9D_DISPATCH_BN(MODE, AMN, BMN, EPI, bn, args, stream)                     \
+  do {                                                                             \
+    if ((bn) == 256) launch_one<MODE, 256, AMN, BMN, EPI>(args, stream);           \
+    else if ((bn) == 192) launch_one<MODE, 192, AMN, BMN, EPI>(args, stream);      \
+    else launch_one<MODE, 128, AMN, BMN, EPI>(args, stream);                       \
+  } while (0)
+
+#define D9D_DISPATCH_EPI4(MODE, AMN, BMN, epi, bn, args, stream)                                  \
+  do {                                                                                            \
+    switch (epi) {                                                                                \
+      case EPI_BF16: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_BF16, bn, args, stream); break;          \
+      case EPI_F32: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_F32, bn, args, stream); break;            \
+      case EPI_F32_ACC: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_F32_ACC, bn, args, stream); break;    \
+      case EPI_BF16_ACC: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_BF16_ACC, bn, args, stream); break;  \
+      default: throw std::runtime_error("d9d gemm: unsupported epilogue for this mode");          \
+    }                                                                                             \
+  } while (0)
+
+}  // namespace gemm
+}  // namespace d9d

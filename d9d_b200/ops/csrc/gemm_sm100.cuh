@@ -1,0 +1,393 @@
+// d9d_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] = A[M,K] · B[N,K]^T      bf16 operands, fp32 accumulation in TMEM.
+//
+// * operands are staged by TMA (128B swizzle) into a multi-stage smem ring,
+// * one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16),
+// * accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1,
+// * either operand may be K-major or MN-major (needed for dgrad / wgrad without transposes),
+// * three problem shapes share the mainloop:
+//     DENSE      plain GEMM
+//     GROUPED_M  rows of A/D are grouped by expert (128-row aligned segments, device-side tile->expert table),
+//                B is [E, ...]  -> MoE forward / dgrad without any host sync
+//     GROUPED_K  the reduction dim is grouped (per-expert weight gradients), D is [E, M, N]
+// * epilogues: bf16 store, fp32 store, fp32 accumulate, and the fused linear-cross-entropy epilogues.
+#pragma once
+
+#include "common.cuh"
+
+namespace d9d {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;  // warp0: TMA, warp1: MMA, warps2-5: epilogue
+constexpr int NUM_EPI_WARPS = 4;
+
+enum Mode : int { DENSE = 0, GROUPED_M = 1, GROUPED_K = 2 };
+enum Epi : int {
+  EPI_BF16 = 0,       // D(bf16) = acc
+  EPI_F32 = 1,        // D(f32) = acc
+  EPI_F32_ACC = 2,    // D(f32) += acc
+  EPI_BF16_ACC = 3,   // D(bf16) += acc   (fp32 add, rn)
+  EPI_CE_LSE = 4,     // fused linear-CE forward: per (row, n_tile) running max / sum-exp / target logit
+  EPI_CE_DLOGITS = 5  // fused linear-CE backward: D(bf16) = g[row] * (exp(acc - lse[row]) - [col == target[row]])
+};
+
+struct Params {
+  int M, N, K;            // DENSE: problem dims. GROUPED_M: M = padded row capacity. GROUPED_K: M,N = per-expert out dims
+  int num_groups;         // experts (1 for dense)
+  void* D;                // output
+  long long ldd;          // leading dim of D (elements)
+  long long d_group_stride;  // GROUPED_K: elements between per-expert outputs
+  const int* tile_group;  // GROUPED_M: [M/128] expert id per m-tile (-1 => unused tile)
+  const int* group_offsets;  // GROUPED_K: [E+1] row offsets (multiples of BLOCK_K) into the grouped K dimension
+  // fused CE
+  const long long* ce_target;  // [M] int64 targets (ignore_index allowed)
+  const float* ce_lse;         // [M]           (DLOGITS)
+  const float* ce_grad;        // [M]           (DLOGITS) upstream grad per row
+  float* ce_part_max;          // [n_tiles, M]  (LSE)
+  float* ce_part_sum;          // [n_tiles, M]  (LSE)
+  float* ce_tgt_logit;         // [M]           (LSE) written by the tile that owns the target column
+  long long ce_ignore_index;
+  float ce_softcap;  // unused (0)
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SMEM_BUDGET = 212 * 1024;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS_NEEDED = 2 * BLOCK_N;
+  static constexpr uint32_t TMEM_COLS = TMEM_COLS_NEEDED <= 32    ? 32
+                                        : TMEM_COLS_NEEDED <= 64  ? 64
+                                        : TMEM_COLS_NEEDED <= 128 ? 128
+                                        : TMEM_COLS_NEEDED <= 256 ? 256
+                                                                  : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int m_blk, n_blk, group;
+  int k_begin, k_blocks;  // k offset (elements) and number of BLOCK_K chunks
+  bool valid;
+};
+
+template <int MODE, int BLOCK_N>
+__device__ __forceinline__ int num_tiles(const Params& p) {
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  if (MODE == GROUPED_K) return p.num_groups * m_tiles * n_tiles;
+  return m_tiles * n_tiles;
+}
+
+template <int MODE, int BLOCK_N>
+__device__ __forceinline__ TileCoord get_tile(const Params& p, int tile) {
+  TileCoord t;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  t.valid = true;
+  if (MODE == GROUPED_K) {
+    const int per_group = m_tiles * n_tiles;
+    t.group = tile / per_group;
+    const int r = tile - t.group * per_group;
+    t.m_blk = r / n_tiles;
+    t.n_blk = r - t.m_blk * n_tiles;
+    const int k0 = p.group_offsets[t.group], k1 = p.group_offsets[t.group + 1];
+    t.k_begin = k0;
+    t.k_blocks = (k1 - k0 + BLOCK_K - 1) / BLOCK_K;
+    return t;
+  }
+  // L2-friendly rasterisation: walk GROUP_M m-blocks for each n-block before moving on.
+  constexpr int GROUP_M = 8;
+  const int group_span = GROUP_M * n_tiles;
+  const int gid = tile / group_span;
+  const int first_m = gid * GROUP_M;
+  const int gm = min(m_tiles - first_m, GROUP_M);
+  const int r = tile - gid * group_span;
+  t.m_blk = first_m + (r % gm);
+  t.n_blk = r / gm;
+  t.k_begin = 0;
+  t.k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  t.group = 0;
+  if (MODE == GROUPED_M) {
+    t.group = p.tile_group[t.m_blk];
+    t.valid = t.group >= 0;
+  }
+  return t;
+}
+
+template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * C::A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int total_tiles = num_tiles<MODE, BLOCK_N>(p);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
+        if (!t.valid) continue;
+        const int m_idx = t.m_blk * BLOCK_M, n_idx = t.n_blk * BLOCK_N;
+        for (int kb = 0; kb < t.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int k_idx = t.k_begin + kb * BLOCK_K;
+          uint8_t* sa = smem_a + stage * C::A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], k_idx, m_idx, 0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_3d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_idx + j * 64, k_idx, 0);
+          }
+          const int bg = (MODE == GROUPED_M) ? t.group : 0;
+          if (!B_MN) {
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], k_idx, n_idx, bg);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_idx + j * 64, k_idx, bg);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
+      if (!t.valid) continue;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < t.k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem_a + stage * C::A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * C::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
+            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================= epilogue (4 warps, one TMEM lane quadrant each) =================
+    const int quad = warp & 3;
+    const int lane = lane_id();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
+      if (!t.valid) continue;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = t.m_blk * BLOCK_M + quad * 32 + lane;
+      const int col0 = t.n_blk * BLOCK_N;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
+      const bool have_acc = t.k_blocks > 0;
+
+      if constexpr (EPI == EPI_CE_LSE) {
+        // online softmax statistics over this tile's columns
+        float run_max = -INFINITY, run_sum = 0.f;
+        const long long tgt = row_ok ? p.ce_target[row] : -1;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          __syncwarp();
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int cbase = col0 + c * 32;
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = (cbase + i < p.N) ? __uint_as_float(r[i]) : -INFINITY;
+            r[i] = __float_as_uint(v);
+            cmax = fmaxf(cmax, v);
+          }
+          if (cmax > -INFINITY) {
+            const float new_max = fmaxf(run_max, cmax);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s += __expf(__uint_as_float(r[i]) - new_max);
+            run_sum = run_sum * __expf(run_max - new_max) + s;
+            run_max = new_max;
+          }
+          if (row_ok && tgt >= cbase && tgt < cbase + 32 && tgt < p.N) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cbase + i == tgt) p.ce_tgt_logit[row] = __uint_as_float(r[i]);
+          }
+        }
+        if (row_ok) {
+          p.ce_part_max[static_cast<long long>(t.n_blk) * p.M + row] = run_max;
+          p.ce_part_sum[static_cast<long long>(t.n_blk) * p.M + row] = run_sum;
+        }
+      } else {
+        long long d_off = static_cast<long long>(row) * p.ldd;
+        if (MODE == GROUPED_K) d_off += static_cast<long long>(t.group) * p.d_group_stride;
+        float lse = 0.f, g = 0.f;
+        long long tgt = -1;
+        if constexpr (EPI == EPI_CE_DLOGITS) {
+          if (row_ok) {
+            tgt = p.ce_target[row];
+            lse = p.ce_lse[row];
+            g = (tgt == p.ce_ignore_index) ? 0.f : p.ce_grad[row];
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          __syncwarp();
+          if (have_acc) {
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0;
+          }
+          const int cbase = col0 + c * 32;
+          if (row_ok && cbase < p.N) {
+          if constexpr (EPI == EPI_CE_DLOGITS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float pr = __expf(__uint_as_float(r[i]) - lse);
+              if (cbase + i == tgt) pr -= 1.f;
+              r[i] = __float_as_uint(pr * g);
+            }
+          }
+          const bool full_chunk = (cbase + 32 <= p.N);
+          if constexpr (EPI == EPI_BF16 || EPI == EPI_CE_DLOGITS || EPI == EPI_BF16_ACC) {
+            __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + cbase;
+            const bool vec_ok = full_chunk && ((reinterpret_cast<uintptr_t>(dptr) & 15) == 0);
+            if (vec_ok) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                uint4 o;
+                if constexpr (EPI == EPI_BF16_ACC) {
+                  const uint4 old = *reinterpret_cast<const uint4*>(dptr + v * 8);
+                  const float2 o0 = unpack_bf16x2(old.x), o1 = unpack_bf16x2(old.y), o2 = unpack_bf16x2(old.z),
+                               o3 = unpack_bf16x2(old.w);
+                  o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]) + o0.x, __uint_as_float(r[v * 8 + 1]) + o0.y);
+                  o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]) + o1.x, __uint_as_float(r[v * 8 + 3]) + o1.y);
+                  o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]) + o2.x, __uint_as_float(r[v * 8 + 5]) + o2.y);
+                  o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]) + o3.x, __uint_as_float(r[v * 8 + 7]) + o3.y);
+                } else {
+                  o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
+                  o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
+                  o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
+                  o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
+                }
+                *reinterpret_cast<uint4*>(dptr + v * 8) = o;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (cbase + i < p.N) {
+                  float v = __uint_as_float(r[i]);
+                  if constexpr (EPI == EPI_BF16_ACC) v += __bfloat162float(dptr[i]);
+                  dptr[i] = __float2bfloat16_rn(v);
+                }
+            }
+          } else {
+            float* dptr = reinterpret_cast<float*>(p.D) + d_off + cbase;
+            const bool vec_ok = full_chunk && ((reinterpret_cast<uintptr_t>(dptr) & 15) == 0);
+            if (vec_ok) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                float4 o = make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
+                                       __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+                if constexpr (EPI == EPI_F32_ACC) {
+                  const float4 old = *reinterpret_cast<const float4*>(dptr + v * 4);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dptr + v * 4) = o;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (cbase + i < p.N) {
+                  float v = __uint_as_float(r[i]);
+                  if constexpr (EPI == EPI_F32_ACC) v += dptr[i];
+                  dptr[i] = v;
+                }
+            }
+          }
+          }  // row_ok
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+}  // namespace gemm
+}  // namespace d9d

@@ -1,0 +1,352 @@
+"""Numerics of every native sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from d9d_b200 import ops as _ops
+
+    return _ops.load()
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize(
+    "M,N,K",
+    [(128, 256, 64), (256, 512, 128), (1000, 776, 520), (4096, 2048, 768), (333, 129 * 8, 72), (8192, 576, 768)],
+)
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_nt(ops, M, N, K, out_dtype):
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    d = torch.empty(M, N, device="cuda", dtype=out_dtype)
+    ops.gemm(a, b, d, False, False, False)
+    ref = a.float() @ b.float().t()
+    assert _rel_err(d, ref) < (1e-2 if out_dtype == torch.bfloat16 else 1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 776, 520), (4096, 768, 2048)])
+def test_gemm_dgrad_layout(ops, M, N, K):
+    # d[M,N] = a[M,K] @ b[K,N]   (b is MN-major: N contiguous)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    d = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, d, False, True, False)
+    assert _rel_err(d, a.float() @ b.float()) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (776, 520, 1000), (768, 2048, 4096)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_wgrad_layout(ops, M, N, K, accumulate):
+    # d[M,N] (+)= a[K,M]^T @ b[K,N]   (both MN-major)
+    a = torch.randn(K, M, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    d0 = torch.randn(M, N, device="cuda", dtype=torch.float32)
+    d = d0.clone()
+    ops.gemm(a, b, d, True, True, accumulate)
+    ref = a.float().t() @ b.float() + (d0 if accumulate else 0)
+    assert _rel_err(d, ref) < 1e-4
+
+
+def test_gemm_mn_a_k_b(ops):
+    M, N, K = 384, 320, 192
+    a = torch.randn(K, M, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    d = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, d, True, False, False)
+    assert _rel_err(d, a.float().t() @ b.float().t()) < 1e-4
+
+
+def test_gemm_bf16_accumulate(ops):
+    M, N, K = 512, 384, 256
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    d0 = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    d = d0.clone()
+    ops.gemm(a, b, d, False, False, True)
+    assert _rel_err(d, a.float() @ b.float().t() + d0.float()) < 1e-2
+
+
+def _make_groups(counts, align=128):
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + (c + align - 1) // align * align)
+    return offs
+
+
+@pytest.mark.parametrize("b_mn", [False, True])
+def test_gemm_grouped_m(ops, b_mn):
+    E, K, N = 5, 192, 320
+    counts = [130, 0, 77, 256, 1]
+    offs = _make_groups(counts)
+    cap = offs[-1] + 256  # trailing unused tiles
+    a = torch.zeros(cap, K, device="cuda", dtype=torch.bfloat16)
+    tile_group = torch.full((cap // 128,), -1, dtype=torch.int32)
+    for e, c in enumerate(counts):
+        a[offs[e] : offs[e] + c] = torch.randn(c, K, device="cuda", dtype=torch.bfloat16)
+        tile_group[offs[e] // 128 : offs[e + 1] // 128] = e
+    tile_group = tile_group.cuda()
+    w = torch.randn(E, K, N, device="cuda", dtype=torch.bfloat16) if b_mn else torch.randn(E, N, K, device="cuda", dtype=torch.bfloat16)
+    d = torch.full((cap, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_grouped_m(a, w, d, tile_group, b_mn)
+    for e, c in enumerate(counts):
+        we = w[e].float() if b_mn else w[e].float().t()
+        ref = a[offs[e] : offs[e + 1]].float() @ we
+        assert _rel_err(d[offs[e] : offs[e + 1]], ref) < 1e-2 or ref.numel() == 0
+    assert (d[offs[-1] :] == 7.0).all()  # unused tiles untouched
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_grouped_k(ops, accumulate):
+    E, Md, Nd = 4, 192, 136
+    counts = [130, 0, 77, 256]
+    offs = _make_groups(counts)
+    R = offs[-1]
+    x = torch.zeros(R, Md, device="cuda", dtype=torch.bfloat16)
+    dy = torch.zeros(R, Nd, device="cuda", dtype=torch.bfloat16)
+    for e, c in enumerate(counts):
+        x[offs[e] : offs[e] + c] = torch.randn(c, Md, device="cuda", dtype=torch.bfloat16)
+        dy[offs[e] : offs[e] + c] = torch.randn(c, Nd, device="cuda", dtype=torch.bfloat16)
+    go = torch.tensor(offs, dtype=torch.int32, device="cuda")
+    d0 = torch.randn(E, Md, Nd, device="cuda", dtype=torch.float32)
+    d = d0.clone()
+    ops.gemm_grouped_k(x, dy, d, go, accumulate)
+    for e in range(E):
+        ref = x[offs[e] : offs[e + 1]].float().t() @ dy[offs[e] : offs[e + 1]].float() + (d0[e] if accumulate else 0)
+        assert (d[e] - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+# ----------------------------------------------------------------------------- fused linear CE
+@pytest.mark.parametrize("T,V,K", [(256, 1000, 128), (1000, 5003 * 8 // 8 * 8, 256), (2048, 32000, 768)])
+def test_linear_ce(ops, T, V, K):
+    h = (torch.randn(T, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(V, K, device="cuda") * 0.1).bfloat16()
+    tgt = torch.randint(0, V, (T,), device="cuda")
+    tgt[::7] = -100
+    nll, lse = ops.ce_forward(h, w, tgt, -100)
+    logits = h.float() @ w.float().t()
+    ref = torch.nn.functional.cross_entropy(logits, tgt, ignore_index=-100, reduction="none")
+    assert torch.allclose(nll, ref, atol=2e-3, rtol=2e-3)
+    assert torch.allclose(lse, torch.logsumexp(logits, -1), atol=2e-3, rtol=2e-3)
+    g = torch.rand(T, device="cuda")
+    out = torch.empty(T, V, device="cuda", dtype=torch.bfloat16)
+    ops.ce_dlogits(h, w, tgt, lse, g, out, -100)
+    p = torch.softmax(logits, -1)
+    onehot = torch.zeros_like(p)
+    valid = tgt != -100
+    onehot[valid, tgt[valid]] = 1
+    refg = (p - onehot) * (g * valid)[:, None]
+    assert _rel_err(out, refg) < 2e-2
+
+
+# ----------------------------------------------------------------------------- RMSNorm
+@pytest.mark.parametrize("N", [64, 128, 256, 768, 1024, 2048, 4096, 7168])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("zc", [False, True])
+def test_rms_norm(ops, N, dtype, zc):
+    M = 517
+    x = torch.randn(M, N, device="cuda", dtype=dtype)
+    w = (torch.randn(N, device="cuda") * 0.1 + (0 if zc else 1)).to(dtype)
+    out, inv = ops.rms_norm_fwd(x, w, 1e-6, zc)
+    xf, wf = x.float(), w.float() + (1 if zc else 0)
+    inv_ref = torch.rsqrt(xf.pow(2).mean(-1) + 1e-6)
+    ref = xf * inv_ref[:, None] * wf
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+    assert torch.allclose(out.float(), ref, atol=tol, rtol=tol)
+    assert torch.allclose(inv, inv_ref, atol=1e-5, rtol=1e-5)
+    dout = torch.randn_like(x)
+    dx, dw = ops.rms_norm_bwd(dout, x, w, inv, zc)
+    xr = xf.clone().requires_grad_(True)
+    wr = w.float().clone().requires_grad_(True)
+    y = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * (wr + (1 if zc else 0))
+    y.backward(dout.float())
+    assert _rel_err(dx, xr.grad) < (1e-2 if dtype == torch.bfloat16 else 1e-5)
+    assert _rel_err(dw, wr.grad) < (1e-2 if dtype == torch.bfloat16 else 1e-4)
+
+
+# ----------------------------------------------------------------------------- SiLU * mul
+@pytest.mark.parametrize("n", [8, 1000, 12345, 1 << 20])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_silu_mul(ops, n, dtype):
+    x = torch.randn(n, device="cuda", dtype=dtype)
+    y = torch.randn(n, device="cuda", dtype=dtype)
+    out = ops.silu_mul_fwd(x, y)
+    ref = torch.nn.functional.silu(x.float()) * y.float()
+    assert torch.allclose(out.float(), ref, atol=3e-2 if dtype == torch.bfloat16 else 1e-5, rtol=2e-2)
+    g = torch.randn(n, device="cuda", dtype=dtype)
+    dx, dy = ops.silu_mul_bwd(g, x, y)
+    xr, yr = x.float().requires_grad_(True), y.float().requires_grad_(True)
+    (torch.nn.functional.silu(xr) * yr).backward(g.float())
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    assert _rel_err(dx, xr.grad) < tol and _rel_err(dy, yr.grad) < tol
+
+
+def test_silu_mul_probs(ops):
+    R, C = 777, 576
+    x = torch.randn(R, C, device="cuda", dtype=torch.bfloat16)
+    y = torch.randn(R, C, device="cuda", dtype=torch.bfloat16)
+    p = torch.rand(R, device="cuda")
+    out = ops.silu_mul_probs_fwd(x, y, p)
+    xr, yr, pr = x.float().requires_grad_(True), y.float().requires_grad_(True), p.clone().requires_grad_(True)
+    ref = torch.nn.functional.silu(xr) * yr * pr[:, None]
+    assert _rel_err(out, ref) < 1e-2
+    g = torch.randn(R, C, device="cuda", dtype=torch.bfloat16)
+    dx, dy, dp = ops.silu_mul_probs_bwd(g, x, y, p)
+    ref.backward(g.float())
+    assert _rel_err(dx, xr.grad) < 1e-2 and _rel_err(dy, yr.grad) < 1e-2 and _rel_err(dp, pr.grad) < 1e-3
+
+
+# ----------------------------------------------------------------------------- stochastic rounding
+def test_sr_copy_statistics(ops):
+    n = 1 << 20
+    src = torch.full((n,), 1.0 + 2.0**-10, device="cuda")  # between two bf16 values (spacing 2^-7)
+    dst = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    ops.sr_copy_(dst, src, 123)
+    assert abs(dst.float().mean().item() - src[0].item()) < 2e-4  # unbiased
+    vals = dst.float().unique()
+    assert len(vals) == 2
+    dst2 = torch.empty_like(dst)
+    ops.sr_copy_(dst2, src, 123)
+    assert torch.equal(dst, dst2)  # reproducible for a (seed, offset)
+    ops.sr_copy_(dst2, src, 124)
+    assert not torch.equal(dst, dst2)
+    x = torch.randn(1001, device="cuda")
+    y = torch.empty(1001, device="cuda", dtype=torch.bfloat16)
+    ops.sr_copy_(y, x, 5)
+    assert (y.float() - x).abs().max() < 2.0**-7 * x.abs().max() * 1.01
+    exact = torch.randn(4096, device="cuda").bfloat16().float()
+    y2 = torch.empty(4096, device="cuda", dtype=torch.bfloat16)
+    ops.sr_copy_(y2, exact, 9)
+    assert torch.equal(y2.float(), exact)  # representable values are never perturbed
+
+
+# ----------------------------------------------------------------------------- AdamW
+@pytest.mark.parametrize("grad_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("state_dtype", [torch.float32, torch.bfloat16])
+def test_adamw_sr_multi(grad_dtype, state_dtype):
+    from d9d_b200.kernel.stochastic import adamw_stochastic_bf16_multi_
+
+    sizes = [5, 1000, 8192, 8193, 70001]
+    ps = [torch.randn(s, device="cuda").bfloat16() for s in sizes]
+    gs = [torch.randn(s, device="cuda").to(grad_dtype) for s in sizes]
+    ms = [(torch.randn(s, device="cuda") * 0.1).to(state_dtype) for s in sizes]
+    vs = [(torch.rand(s, device="cuda") * 0.1).to(state_dtype) for s in sizes]
+    p0 = [p.float().clone() for p in ps]
+    m0 = [m.float().clone() for m in ms]
+    v0 = [v.float().clone() for v in vs]
+    lr, b1, b2, eps, wd, step = 1e-2, 0.9, 0.95, 1e-8, 0.1, 3
+    adamw_stochastic_bf16_multi_(ps, gs, ms, vs, lr=lr, beta1=b1, beta2=b2, eps=eps, weight_decay=wd, step=step, seed=77)
+    for p, g, m, v, pp, mm, vv in zip(ps, gs, ms, vs, p0, m0, v0):
+        gf = g.float()
+        pe = pp * (1 - lr * wd)
+        me = b1 * mm + (1 - b1) * gf
+        ve = b2 * vv + (1 - b2) * gf * gf
+        pe = pe - lr * (me / (1 - b1**step)) / ((ve / (1 - b2**step)).sqrt() + eps)
+        ulp = pe.abs().clamp_min(1e-30) * 2.0**-7
+        assert ((p.float() - pe).abs() <= ulp * 1.01 + 1e-30).all()
+        tol = 2.0**-7 if state_dtype == torch.bfloat16 else 1e-6
+        assert ((m.float() - me).abs() <= me.abs() * tol + 1e-7).all()
+        assert ((v.float() - ve).abs() <= ve.abs() * tol + 1e-7).all()
+
+
+# ----------------------------------------------------------------------------- RoPE
+@pytest.mark.parametrize("D,rope_dim", [(128, 128), (64, 64), (128, 64), (256, 256)])
+@pytest.mark.parametrize("style", [0, 1])
+def test_rope(ops, D, rope_dim, style):
+    T, H, maxpos = 300, 5, 512
+    x = torch.randn(T, H, D, device="cuda", dtype=torch.bfloat16)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, rope_dim, 2, device="cuda").float() / rope_dim))
+    ang = torch.arange(maxpos, device="cuda").float()[:, None] * inv_freq[None]
+    if style == 0:
+        cos, sin = torch.cat([ang.cos(), ang.cos()], -1), torch.cat([ang.sin(), ang.sin()], -1)
+    else:
+        cos, sin = ang.cos().repeat_interleave(2, -1), ang.sin().repeat_interleave(2, -1)
+    pos = torch.randint(0, maxpos, (T,), device="cuda")
+    out = ops.rope_apply(x, cos.contiguous(), sin.contiguous(), pos, style, False)
+    xf = x.float()
+    xr, xpass = xf[..., :rope_dim], xf[..., rope_dim:]
+    c, s = cos[pos][:, None, :], sin[pos][:, None, :]
+    if style == 0:
+        rot = torch.cat([-xr[..., rope_dim // 2 :], xr[..., : rope_dim // 2]], -1)
+    else:
+        rot = torch.stack([-xr[..., 1::2], xr[..., 0::2]], -1).flatten(-2)
+    ref = torch.cat([xr * c + rot * s, xpass], -1)
+    assert torch.allclose(out.float(), ref, atol=3e-2, rtol=2e-2)
+    back = ops.rope_apply(out, cos.contiguous(), sin.contiguous(), pos, style, True)
+    assert torch.allclose(back.float(), xf, atol=6e-2, rtol=3e-2)  # inverse rotation == transpose
+
+
+# ----------------------------------------------------------------------------- MoE layout / permute
+@pytest.mark.parametrize("T,k,E", [(1000, 4, 16), (4096, 8, 128), (37, 2, 8)])
+def test_moe_layout_and_permute(ops, T, k, E):
+    H = 256
+    ids = torch.stack([torch.randperm(E, device="cuda")[:k] for _ in range(T)])
+    ids[::13, 0] = -1  # dropped
+    cap = (T * k + E * 127 + 127) // 128 * 128
+    counts, seg, row_map, tile_group = ops.moe_build_layout(ids, E, 128, cap)
+    flat = ids.flatten()
+    ref_counts = torch.bincount(flat[flat >= 0], minlength=E)
+    assert torch.equal(counts.long(), ref_counts)
+    aligned = (ref_counts + 127) // 128 * 128
+    ref_seg = torch.cat([torch.zeros(1, dtype=torch.long, device="cuda"), aligned.cumsum(0)])
+    assert torch.equal(seg.long(), ref_seg)
+    # stable sort order
+    rm = row_map.long()
+    for e in range(0, E, max(1, E // 8)):
+        idx = (flat == e).nonzero().flatten()
+        assert torch.equal(rm[idx], ref_seg[e] + torch.arange(len(idx), device="cuda"))
+    assert (rm[flat < 0] == -1).all()
+    tg = tile_group.long()
+    for e in range(E):
+        assert (tg[ref_seg[e] // 128 : ref_seg[e + 1] // 128] == e).all()
+    assert (tg[ref_seg[-1] // 128 :] == -1).all()
+
+    x = torch.randn(T, H, device="cuda", dtype=torch.bfloat16)
+    probs = torch.rand(T, k, device="cuda")
+    xp, pp = ops.moe_permute(x, probs, row_map, counts, seg, cap)
+    valid = rm >= 0
+    tok = torch.arange(T, device="cuda").repeat_interleave(k)
+    assert torch.equal(xp[rm[valid]], x[tok[valid]])
+    assert torch.equal(pp[rm[valid]], probs.flatten()[valid])
+    used = torch.zeros(cap, dtype=torch.bool, device="cuda")
+    used[rm[valid]] = True
+    pad = ~used
+    pad[ref_seg[-1] :] = False
+    assert (xp[pad] == 0).all() and (pp[pad] == 0).all()
+
+    yp = torch.randn(cap, H, device="cuda", dtype=torch.bfloat16)
+    y, _ = ops.moe_gather(yp, None, row_map, T, k)
+    ref = torch.zeros(T, H, device="cuda")
+    ref.index_add_(0, tok[valid], yp[rm[valid]].float())
+    assert torch.allclose(y.float(), ref, atol=3e-2, rtol=2e-2)
+    dpp = torch.randn(cap, device="cuda")
+    y2, dprobs = ops.moe_gather(yp, dpp, row_map, T, k)
+    assert torch.equal(y2, y)
+    refp = torch.zeros(T * k, device="cuda")
+    refp[valid] = dpp[rm[valid]]
+    assert torch.equal(dprobs.flatten(), refp)
+
+
+def test_grad_utils(ops):
+    x = torch.randn(100003, device="cuda")
+    out = torch.zeros(1, device="cuda")
+    ops.sumsq_accumulate_(x, out)
+    assert math.isclose(out.item(), x.pow(2).sum().item(), rel_tol=1e-4)
+    xb = x.bfloat16()
+    out.zero_()
+    ops.sumsq_accumulate_(xb, out)
+    assert math.isclose(out.item(), xb.float().pow(2).sum().item(), rel_tol=1e-4)
+    sc = torch.tensor([0.5], device="cuda")
+    ref = x * 0.5
+    ops.scale_inplace_(x, sc)
+    assert torch.allclose(x, ref)
