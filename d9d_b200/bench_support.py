@@ -1,0 +1,104 @@
+"""Training-step driver used by ``bench.py`` and ``__graft_entry__.smoke``.
+
+One optimizer step = ``accum`` microbatches of forward+backward (loss = per-token mean weighted by token count,
+exactly the reference's SFT task contract), gradients accumulated in a flat fp32 arena that every ``param.grad``
+aliases, data-parallel SUM all-reduce of the arena, device-side ``1/sum(weight)`` scaling + global-norm clipping
+folded into the fused stochastic-rounding AdamW launch.  No host synchronisation inside a step.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from d9d_b200.kernel._native import native_launch_count, native_ops
+from d9d_b200.optim.stochastic import StochasticAdamW
+
+LM_IGNORE_INDEX = -100
+
+
+class TrainStepRunner:
+    def __init__(self, args, device: torch.device, world: int, build_model, lr: float = 2.5e-4, max_norm: float = 5.0):
+        self.args = args
+        self.device = device
+        self.world = world
+        if world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+        torch.manual_seed(1337)  # identical init on every replica
+        self.model = build_model(args, device)
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        # flat fp32 gradient arena; every param.grad is a view (accumulated in place by autograd)
+        total = sum((p.numel() + 63) // 64 * 64 for p in self.params)
+        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for p in self.params:
+            p.grad_dtype = torch.float32
+            p.grad = self.grad_arena[off : off + p.numel()].view_as(p)
+            off += (p.numel() + 63) // 64 * 64
+        self.opt = StochasticAdamW(self.params, lr=lr, state_dtype=torch.bfloat16)
+        self.grad_scale = torch.ones(1, dtype=torch.float32, device=device)
+        self.opt.grad_scale = self.grad_scale
+        self.max_norm = max_norm
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
+        self.weight_sum = torch.zeros(1, dtype=torch.float32, device=device)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=device)
+        self.comm_stream = torch.cuda.Stream(device=device) if world > 1 else None
+        self.pos = torch.arange(args.seq_len, device=device)[None].expand(args.microbatch, -1).contiguous()
+
+    # ---------------------------------------------------------------- data
+    def synthetic_batch(self, vocab: int, gen: torch.Generator) -> dict[str, torch.Tensor]:
+        tok = torch.randint(0, vocab, (self.args.microbatch, self.args.seq_len + 1), device=self.device, generator=gen)
+        return {"input_ids": tok[:, :-1].contiguous(), "labels": tok[:, 1:].contiguous()}
+
+    def synthetic_host_batch(self, vocab: int, seed: int) -> dict[str, torch.Tensor]:
+        g = torch.Generator().manual_seed(seed)
+        tok = torch.randint(0, vocab, (self.args.microbatch, self.args.seq_len + 1), generator=g)
+        return {"input_ids": tok[:, :-1].contiguous().pin_memory(), "labels": tok[:, 1:].contiguous().pin_memory()}
+
+    # ---------------------------------------------------------------- one optimizer step
+    def _forward_backward(self, batch: dict[str, torch.Tensor]) -> None:
+        labels = batch["labels"]
+        out = self.model(input_ids=batch["input_ids"], position_ids=self.pos, labels=labels)
+        n_tok = (labels != LM_IGNORE_INDEX).sum()
+        loss = out["logps"].sum() / n_tok
+        weight = n_tok / 1000.0
+        (loss * weight).backward()
+        self.weight_sum += weight.detach()
+        self.loss_sum += (loss.detach() * weight.detach()).float()
+
+    def step(self, batches: list[dict[str, torch.Tensor]]) -> torch.Tensor:
+        for b in batches:
+            self._forward_backward(b)
+        ops = native_ops()
+        if self.world > 1:
+            dist.all_reduce(self.grad_arena)
+            stats = torch.cat([self.weight_sum, self.loss_sum])
+            dist.all_reduce(stats)
+            self.weight_sum, self.loss_sum = stats[:1].clone(), stats[1:].clone()
+        # global grad norm of the *scaled* gradient, clip coefficient, all on the device
+        self.sumsq.zero_()
+        ops.sumsq_accumulate_(self.grad_arena, self.sumsq)
+        inv_w = 1.0 / self.weight_sum
+        norm = self.sumsq.sqrt() * inv_w
+        clip = torch.clamp(self.max_norm / (norm + 1e-6), max=1.0)
+        self.grad_scale.copy_(inv_w * clip)
+        self.opt.step()
+        self.grad_arena.zero_()
+        loss = (self.loss_sum / self.weight_sum).clone()
+        self.weight_sum.zero_()
+        self.loss_sum.zero_()
+        return loss
+
+    def step_from_host(self, host_batches: list[dict[str, torch.Tensor]]) -> tuple[float, int, int]:
+        h2d = 0
+        dev_batches = []
+        for hb in host_batches:
+            db = {k: v.to(self.device, non_blocking=True) for k, v in hb.items()}
+            h2d += sum(v.numel() * v.element_size() for v in hb.values())
+            dev_batches.append(db)
+        loss = self.step(dev_batches)
+        loss_host = loss.to("cpu")  # device -> host read of the step's result (synchronises this step)
+        return float(loss_host), h2d, loss_host.numel() * loss_host.element_size()
+
+    def launch_count(self) -> int:
+        return native_launch_count()

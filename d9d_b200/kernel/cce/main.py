@@ -56,8 +56,9 @@ class _LinearCEFunction(Function):
         g = grad_nll.float().contiguous()
         de = torch.empty_like(e) if need_e else None
         dc = torch.zeros(V, K, device=c.device, dtype=torch.float32) if need_c else None
-        chunk = max(128, min(T, (_CHUNK_BYTES // (2 * V)) // 128 * 128))
-        buf = torch.empty(chunk, V, device=e.device, dtype=torch.bfloat16)
+        v_pitch = (V + 7) // 8 * 8  # TMA needs 16-byte aligned row pitch
+        chunk = max(128, min(T, (_CHUNK_BYTES // (2 * v_pitch)) // 128 * 128))
+        buf = torch.empty(chunk, v_pitch, device=e.device, dtype=torch.bfloat16)[:, :V]
         for t0 in range(0, T, chunk):
             t1 = min(t0 + chunk, T)
             dl = buf[: t1 - t0]

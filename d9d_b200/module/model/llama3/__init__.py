@@ -1,0 +1,22 @@
+from .decoder_layer import Llama3Layer
+from .model import Llama3ForCausalLM, Llama3ForClassification, Llama3ForEmbedding, Llama3Model
+from .params import (
+    Llama3ForCausalLMParameters,
+    Llama3ForClassificationParameters,
+    Llama3ForEmbeddingParameters,
+    Llama3LayerParameters,
+    Llama3Parameters,
+)
+
+__all__ = [
+    "Llama3ForCausalLM",
+    "Llama3ForCausalLMParameters",
+    "Llama3ForClassification",
+    "Llama3ForClassificationParameters",
+    "Llama3ForEmbedding",
+    "Llama3ForEmbeddingParameters",
+    "Llama3Layer",
+    "Llama3LayerParameters",
+    "Llama3Model",
+    "Llama3Parameters",
+]

@@ -123,7 +123,8 @@ std::tuple<Tensor, Tensor> ce_forward(const Tensor& h, const Tensor& w, const Te
 void ce_dlogits(const Tensor& h, const Tensor& w, const Tensor& target, const Tensor& lse, const Tensor& grad,
                 Tensor out, int64_t ignore_index) {
   CHECK_CUDA_CONTIG(h); CHECK_CUDA_CONTIG(w); CHECK_CUDA_CONTIG(target); CHECK_CUDA_CONTIG(lse);
-  CHECK_CUDA_CONTIG(grad); CHECK_CUDA_CONTIG(out);
+  CHECK_CUDA_CONTIG(grad);
+  TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.stride(1) == 1, "ce_dlogits: out must be row-major (row pitch may be padded)");
   TORCH_CHECK(out.scalar_type() == at::kBFloat16 && lse.scalar_type() == at::kFloat && grad.scalar_type() == at::kFloat);
   c10::cuda::CUDAGuard guard(h.device());
   const int T = static_cast<int>(h.size(0)), K = static_cast<int>(h.size(1)), V = static_cast<int>(w.size(0));
@@ -131,7 +132,7 @@ void ce_dlogits(const Tensor& h, const Tensor& w, const Tensor& target, const Te
   d9d::GemmArgs g;
   g.mode = 0; g.epi = 5;
   g.M = T; g.N = V; g.K = K;
-  g.A = h.data_ptr(); g.B = w.data_ptr(); g.D = out.data_ptr(); g.lda = K; g.ldb = K; g.ldd = V;
+  g.A = h.data_ptr(); g.B = w.data_ptr(); g.D = out.data_ptr(); g.lda = K; g.ldb = K; g.ldd = out.stride(0);
   g.ce_target = reinterpret_cast<const long long*>(target.data_ptr<int64_t>());
   g.ce_lse = lse.data_ptr<float>(); g.ce_grad = grad.data_ptr<float>();
   g.ce_ignore_index = ignore_index;
