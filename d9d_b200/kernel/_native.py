@@ -54,3 +54,14 @@ def native_launch_count() -> int:
 def on_gpu(*tensors: torch.Tensor) -> bool:
     """True if the op must run on the native CUDA path."""
     return any(t is not None and t.is_cuda for t in tensors)
+
+
+def grad_dtype_of(t: torch.Tensor) -> torch.dtype:
+    """Dtype autograd expects for the gradient of ``t`` (``grad_dtype`` is only defined on leaves)."""
+    try:
+        gd = t.grad_dtype if t.is_leaf else None
+    except (RuntimeError, AttributeError):
+        gd = None
+    if gd not in (torch.bfloat16, torch.float32):
+        return t.dtype
+    return gd

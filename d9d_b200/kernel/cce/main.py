@@ -18,7 +18,7 @@ from torch.autograd import Function
 
 from d9d_b200.core.autograd import GLOBAL_GRAD_CONTEXT, GradDirection
 
-from .._native import native_ops, on_gpu
+from .._native import grad_dtype_of, native_ops, on_gpu
 
 IGNORE_INDEX = -100
 _CHUNK_BYTES = 1 << 30  # size of the dlogits chunk buffer used by the backward pass
@@ -68,7 +68,7 @@ class _LinearCEFunction(Function):
             if need_c:
                 ops.gemm(dl, e[t0:t1], dc, True, True, True)  # dC += dL^T @ E
         if dc is not None:
-            grad_dtype = getattr(c, "grad_dtype", None) or c.dtype
+            grad_dtype = grad_dtype_of(c)
             dc = dc if grad_dtype == torch.float32 else dc.to(grad_dtype)
         return de, dc, None, None
 

@@ -16,7 +16,7 @@ from torch.autograd import Function
 
 from d9d_b200.core.autograd import GLOBAL_GRAD_CONTEXT, GradDirection
 
-from .._native import native_ops, on_gpu
+from .._native import grad_dtype_of, native_ops, on_gpu
 
 
 def _tma_ok(*tensors: torch.Tensor) -> bool:
@@ -60,9 +60,7 @@ class LinearFunction(Function):
             ops.gemm(dy, weight, dx, False, True, False)  # dy[M,out] @ W[out,in]
             dx = dx.view(ctx.x_shape)
         if ctx.needs_input_grad[1] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight):
-            grad_dtype = getattr(weight, "grad_dtype", None) or weight.dtype
-            if grad_dtype not in (torch.bfloat16, torch.float32):
-                grad_dtype = weight.dtype
+            grad_dtype = grad_dtype_of(weight)
             dw = torch.empty(weight.shape, device=weight.device, dtype=grad_dtype)
             ops.gemm(dy, x2, dw, True, True, False)  # dy^T[out,M] @ x[M,in]
         return dx, dw

@@ -8,7 +8,7 @@ from torch.autograd import Function
 
 from d9d_b200.core.autograd import GLOBAL_GRAD_CONTEXT, GradDirection
 
-from .._native import native_ops, on_gpu
+from .._native import grad_dtype_of, native_ops, on_gpu
 
 ALIGN = 128  # GEMM BLOCK_M: expert segments never share an M-tile, per-expert K ranges are BLOCK_K aligned
 
@@ -180,9 +180,7 @@ class _GroupedLinearFunction(Function):
             dx = torch.empty_like(xp)
             ops.gemm_grouped_m(dy, weight, dx, layout.tile_group, False)  # W[e] read as [N'=in, K'=out]
         if ctx.needs_input_grad[1] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight):
-            grad_dtype = getattr(weight, "grad_dtype", None) or weight.dtype
-            if grad_dtype not in (torch.bfloat16, torch.float32):
-                grad_dtype = weight.dtype
+            grad_dtype = grad_dtype_of(weight)
             dw = torch.empty(weight.shape, device=weight.device, dtype=grad_dtype)
             ops.gemm_grouped_k(xp, dy, dw, layout.seg_offsets, False)
         return dx, dw, None
