@@ -1,0 +1,16 @@
+"""High-level helpers applying a parallelism strategy to a module (reference ``d9d/module/parallelism/api``)."""
+
+from .expert_parallel import parallelize_expert_parallel
+from .fully_sharded import parallelize_fsdp
+from .hybrid_sharded import parallelize_hsdp
+from .replicate_parallel import parallelize_replicate
+from .tensor_parallel import parallelize_colwise, parallelize_rowwise
+
+__all__ = [
+    "parallelize_colwise",
+    "parallelize_expert_parallel",
+    "parallelize_fsdp",
+    "parallelize_hsdp",
+    "parallelize_replicate",
+    "parallelize_rowwise",
+]
