@@ -1,0 +1,97 @@
+from __future__ import annotations
+
+import enum
+from collections.abc import Iterable
+from typing import Any
+
+import torch
+import torch.distributed as dist
+from torch.distributed.checkpoint.stateful import Stateful
+
+
+class MetricReduceOp(enum.StrEnum):
+    """No ``avg`` on purpose: averaging partial accumulators is not a safe way to combine metric state."""
+
+    sum = "sum"
+    max = "max"
+    min = "min"
+
+
+_TORCH_OP = {MetricReduceOp.sum: dist.ReduceOp.SUM, MetricReduceOp.max: dist.ReduceOp.MAX, MetricReduceOp.min: dist.ReduceOp.MIN}
+
+
+class MetricAccumulator(Stateful):
+    """A tensor accumulated locally every step plus a synchronised copy filled by an all-reduce over the world.
+
+    Parity: reference ``d9d/metric/component/accumulator.py:42-141``.
+    """
+
+    def __init__(self, initial_value: torch.Tensor, reduce_op: MetricReduceOp = MetricReduceOp.sum):
+        self._initial = initial_value.clone()
+        self._local = initial_value.clone()
+        self._synchronized = initial_value.clone()
+        self._reduce_op = reduce_op
+        self._is_synchronized = False
+
+    @property
+    def reduce_op(self) -> MetricReduceOp:
+        return self._reduce_op
+
+    def update(self, value: torch.Tensor | float | bool) -> None:
+        if self._reduce_op == MetricReduceOp.sum:
+            self._local.add_(value)
+        else:
+            if not isinstance(value, torch.Tensor):
+                raise ValueError(f"Non-tensor inputs are not supported for `{self._reduce_op.value}` reduce op")
+            pick = torch.maximum if self._reduce_op == MetricReduceOp.max else torch.minimum
+            self._local.copy_(pick(self._local, value))
+        self._is_synchronized = False
+
+    def sync(self) -> None:
+        self._synchronized.copy_(self._local)
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(self._synchronized, op=_TORCH_OP[self._reduce_op])
+        self._is_synchronized = True
+
+    @property
+    def value(self) -> torch.Tensor:
+        return self._synchronized if self._is_synchronized else self._local
+
+    def reset(self) -> None:
+        self._local.copy_(self._initial)
+        self._is_synchronized = False
+
+    def to(self, device: str | torch.device | int) -> None:
+        self._initial = self._initial.to(device)
+        self._local = self._local.to(device)
+        self._synchronized = self._synchronized.to(device)
+
+    def state_dict(self) -> dict[str, Any]:
+        return {"local": self._local, "synchronized": self._synchronized, "is_synchronized": self._is_synchronized}
+
+    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
+        self._local = state_dict["local"].to(self._local.device)
+        self._synchronized = state_dict["synchronized"].to(self._synchronized.device)
+        self._is_synchronized = bool(state_dict["is_synchronized"])
+
+
+def sync_accumulators(accumulators: Iterable[MetricAccumulator]) -> None:
+    """Synchronise many accumulators with ONE collective per (reduce op, dtype, device) by flattening them into a
+    single buffer — metric tensors are tiny, so launch latency, not bandwidth, is what matters."""
+    accs = list(accumulators)
+    if not (dist.is_available() and dist.is_initialized()):
+        for a in accs:
+            a.sync()
+        return
+    groups: dict[tuple, list[MetricAccumulator]] = {}
+    for a in accs:
+        groups.setdefault((a.reduce_op, a._local.dtype, a._local.device), []).append(a)  # noqa: SLF001
+    for (op, _dtype, _device), members in groups.items():
+        flat = torch.cat([m._local.reshape(-1) for m in members])  # noqa: SLF001
+        dist.all_reduce(flat, op=_TORCH_OP[op])
+        off = 0
+        for m in members:
+            n = m._local.numel()  # noqa: SLF001
+            m._synchronized.copy_(flat[off : off + n].view_as(m._synchronized))  # noqa: SLF001
+            m._is_synchronized = True  # noqa: SLF001
+            off += n
