@@ -8,8 +8,9 @@ class SyntheticTokenDataset(Dataset[dict[str, torch.Tensor]]):
     """Deterministic random-token causal-LM samples of fixed length (``input_ids``, shifted ``labels``,
     ``position_ids``); sample ``i`` only depends on ``(seed, i)``.  Used by benchmarks and smoke tests."""
 
-    def __init__(self, num_samples: int, seq_len: int, vocab_size: int, seed: int = 0):
+    def __init__(self, num_samples: int, seq_len: int, vocab_size: int, seed: int = 0, learnable: bool = False):
         self._n, self._s, self._v, self._seed = num_samples, seq_len, vocab_size, seed
+        self._learnable = learnable  # next token is a fixed function of the current one (so a model can fit it)
 
     def __len__(self) -> int:
         return self._n
@@ -19,7 +20,11 @@ class SyntheticTokenDataset(Dataset[dict[str, torch.Tensor]]):
 
     def __getitem__(self, index: int) -> dict[str, torch.Tensor]:
         g = torch.Generator().manual_seed(self._seed * 1_000_003 + index)
-        tokens = torch.randint(0, self._v, (self._s + 1,), generator=g)
+        if self._learnable:
+            start = int(torch.randint(0, self._v, (1,), generator=g))
+            tokens = (start + 7 * torch.arange(self._s + 1)) % self._v
+        else:
+            tokens = torch.randint(0, self._v, (self._s + 1,), generator=g)
         return {"input_ids": tokens[:-1], "labels": tokens[1:], "position_ids": torch.arange(self._s)}
 
     @staticmethod

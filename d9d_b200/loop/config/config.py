@@ -1,0 +1,97 @@
+from pathlib import Path
+
+from pydantic import BaseModel
+
+from d9d_b200.pipelining.factory import AnyPipelineScheduleConfig
+from d9d_b200.tracker import AnyTrackerConfig, RunConfig
+
+from .types import StepActionPeriod
+
+
+class BatchingConfig(BaseModel):
+    global_batch_size: int  # over all replicas and accumulation steps
+    microbatch_size: int  # one forward on one device
+
+
+class DeterminismConfig(BaseModel):
+    base_seed: int
+
+
+class PipeliningConfig(BaseModel):
+    schedule: AnyPipelineScheduleConfig
+
+
+class GarbageCollectionConfig(BaseModel):
+    period_steps: StepActionPeriod
+
+
+class DataLoadingConfig(BaseModel):
+    num_workers: int
+    pin_memory: bool
+    persistent_workers: bool
+
+
+class CheckpointingConfig(BaseModel):
+    save_dir: Path
+    period_steps: StepActionPeriod
+    num_to_keep: int | None
+
+
+class ModelStageFactoryConfig(BaseModel):
+    source_checkpoint: Path | None
+    checkpoint_only_trainable_parameters: bool
+
+
+class GradientClippingConfig(BaseModel):
+    max_norm: float | None
+    log_total_steps: StepActionPeriod
+
+
+class ProfilingConfig(BaseModel):
+    enabled: bool
+    traces_dir: Path
+    period_steps: int
+    warmup_steps: int
+    active_steps: int
+
+
+class JobLoggerConfig(BaseModel):
+    period_steps: StepActionPeriod
+    tracker: AnyTrackerConfig
+
+
+class GradientManagerConfig(BaseModel):
+    grad_dtype: str | None  # None => parameter dtype
+    bucket_size_mb: int
+
+
+class TimeoutConfig(BaseModel):
+    init_timeout: int = 10000
+    step_timeout: int = 100
+
+
+class TrainerConfig(BaseModel):
+    run: RunConfig
+    batching: BatchingConfig
+    data_loading: DataLoadingConfig
+    logging: JobLoggerConfig
+    pipelining: PipeliningConfig
+    model_stage_factory: ModelStageFactoryConfig
+    determinism: DeterminismConfig
+    gc: GarbageCollectionConfig
+    checkpointing: CheckpointingConfig
+    gradient_clipping: GradientClippingConfig
+    profiling: ProfilingConfig | None
+    gradient_manager: GradientManagerConfig
+    timeout: TimeoutConfig = TimeoutConfig()
+
+
+class InferenceConfig(BaseModel):
+    batching: BatchingConfig
+    data_loading: DataLoadingConfig
+    model_stage_factory: ModelStageFactoryConfig
+    determinism: DeterminismConfig
+    gc: GarbageCollectionConfig
+    checkpointing: CheckpointingConfig
+    profiling: ProfilingConfig | None
+    timeout: TimeoutConfig = TimeoutConfig()

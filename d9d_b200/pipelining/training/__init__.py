@@ -13,6 +13,43 @@ def _key(pp_rank: int, i: int) -> str:
     return f"pp_{pp_rank}_stage_{i}"
 
 
+def ensure_optimizer_state_initialized(optimizer: Any) -> None:
+    """Materialise lazily-created optimizer state (moments, step counters) without changing any parameter.
+
+    ``torch.distributed.checkpoint`` loads *into the structure* returned by ``state_dict()``; an optimizer that has
+    not stepped yet exposes an empty ``state`` and would silently resume with fresh moments (the reference has this
+    problem).  A step with zero gradients, ``lr = 0`` and ``weight_decay = 0`` creates the state and is otherwise a
+    no-op; the loaded values then overwrite it.
+    """
+    import torch
+
+    groups = getattr(optimizer, "param_groups", None)
+    if groups is None:
+        return
+    params = [p for g in groups for p in g["params"] if p.requires_grad]
+    if not params or all(len(optimizer.state.get(p, {})) > 0 for p in params):
+        return
+    saved = []
+    for g in groups:
+        saved.append({k: g[k] for k in ("lr", "weight_decay") if k in g})
+        if "lr" in g:
+            g["lr"] = torch.zeros_like(g["lr"]) if isinstance(g["lr"], torch.Tensor) else 0.0
+        if "weight_decay" in g:
+            g["weight_decay"] = 0.0
+    had_no_grad = []
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p, dtype=getattr(p, "grad_dtype", None) or p.dtype)
+            had_no_grad.append(p)
+    try:
+        optimizer.step()
+    finally:
+        for p in had_no_grad:
+            p.grad = None
+        for g, old in zip(groups, saved, strict=True):
+            g.update(old)
+
+
 class PipelinedOptimizer(OptimizerProtocol):
     """State-dict keys ``pp_{pp_rank}_stage_{i}`` (reference ``pipelining/training/optimizer.py:23-30``)."""
 
@@ -25,6 +62,8 @@ class PipelinedOptimizer(OptimizerProtocol):
         return self._optimizers
 
     def state_dict(self) -> dict[str, Any]:
+        for o in self._optimizers:
+            ensure_optimizer_state_initialized(o)
         return {_key(self._pp_rank, i): o.state_dict() for i, o in enumerate(self._optimizers)}
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
