@@ -24,19 +24,20 @@ class MoELayout:
     num_tokens: int
     top_k: int
     num_experts: int
-    capacity: int  # static upper bound on rows (T*k + E*(ALIGN-1) rounded up)
+    capacity: int  # static upper bound on rows (T*k + E*(align-1) rounded up)
+    align: int = ALIGN  # 128 for GEMM-ready layouts, 1 for the compact send order of the expert-parallel all-to-all
 
 
-def layout_capacity(num_tokens: int, top_k: int, num_experts: int) -> int:
-    n = num_tokens * top_k + num_experts * (ALIGN - 1)
-    return (n + ALIGN - 1) // ALIGN * ALIGN
+def layout_capacity(num_tokens: int, top_k: int, num_experts: int, align: int = ALIGN) -> int:
+    n = num_tokens * top_k + num_experts * (align - 1)
+    return (n + align - 1) // align * align
 
 
-def _build_layout_reference(topk_ids: torch.Tensor, num_experts: int, capacity: int):
+def _build_layout_reference(topk_ids: torch.Tensor, num_experts: int, capacity: int, align: int = ALIGN):
     flat = topk_ids.reshape(-1)
     valid = (flat >= 0) & (flat < num_experts)
     counts = torch.bincount(flat[valid], minlength=num_experts)
-    aligned = (counts + ALIGN - 1) // ALIGN * ALIGN
+    aligned = (counts + align - 1) // align * align
     seg = torch.zeros(num_experts + 1, dtype=torch.long, device=flat.device)
     seg[1:] = aligned.cumsum(0)
     key = torch.where(valid, flat, torch.full_like(flat, num_experts))
@@ -47,26 +48,31 @@ def _build_layout_reference(topk_ids: torch.Tensor, num_experts: int, capacity: 
     dest_sorted = torch.where(sorted_key < num_experts, seg[sorted_key.clamp_max(num_experts - 1)] + rank, torch.full_like(rank, -1))
     row_map = torch.empty_like(flat)
     row_map[order] = dest_sorted
-    tiles = torch.full((capacity // ALIGN,), -1, dtype=torch.long, device=flat.device)
-    tile_idx = torch.arange(capacity // ALIGN, device=flat.device) * ALIGN
+    num_tiles = capacity // ALIGN if align % ALIGN == 0 else 0
+    tiles = torch.full((num_tiles,), -1, dtype=torch.long, device=flat.device)
+    tile_idx = torch.arange(num_tiles, device=flat.device) * ALIGN
     owner = torch.searchsorted(seg, tile_idx, right=True) - 1
     used = tile_idx < seg[-1]
     tiles[used] = owner[used]
     return counts.int(), seg.int(), row_map.int(), tiles.int()
 
 
-def build_moe_layout(topk_ids: torch.Tensor, num_experts: int) -> MoELayout:
-    """``topk_ids [T, k]`` (ids outside ``[0, E)`` are dropped) -> layout. No host synchronisation."""
+def build_moe_layout(topk_ids: torch.Tensor, num_experts: int, align: int = ALIGN) -> MoELayout:
+    """``topk_ids [T, k]`` (ids outside ``[0, E)`` are dropped) -> layout. No host synchronisation.
+
+    ``align=128`` gives the GEMM-ready layout; ``align=1`` a compact stable sort by expert (used as the send order
+    of the expert-parallel exchange, where padding would waste NVLink bandwidth).
+    """
     T, k = topk_ids.shape
-    cap = layout_capacity(T, k, num_experts)
+    cap = layout_capacity(T, k, num_experts, align)
     ids = topk_ids.contiguous()
     if ids.dtype != torch.int64:
         ids = ids.long()
     if on_gpu(ids):
-        counts, seg, row_map, tile_group = native_ops().moe_build_layout(ids, num_experts, ALIGN, cap)
+        counts, seg, row_map, tile_group = native_ops().moe_build_layout(ids, num_experts, align, cap)
     else:
-        counts, seg, row_map, tile_group = _build_layout_reference(ids, num_experts, cap)
-    return MoELayout(counts, seg, row_map, tile_group, T, k, num_experts, cap)
+        counts, seg, row_map, tile_group = _build_layout_reference(ids, num_experts, cap, align)
+    return MoELayout(counts, seg, row_map, tile_group, T, k, num_experts, cap, align)
 
 
 # ------------------------------------------------------------------------------------------ permute / unpermute

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(1024) moe_scan_kernel(int* __restrict__ chunk_
   }
   __syncthreads();
   for (int e = threadIdx.x; e <= E; e += blockDim.x) seg_offsets[e] = s_off[e];
-  const int num_tiles = static_cast<int>(capacity_rows / 128);
+  // the tile->expert table only exists for GEMM-aligned layouts (compact align=1 layouts feed the all-to-all)
+  const int num_tiles = (align % 128 == 0) ? static_cast<int>(capacity_rows / 128) : 0;
   for (int t = threadIdx.x; t < num_tiles; t += blockDim.x) tile_group[t] = -1;
   __syncthreads();
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
@@ -209,7 +210,8 @@ void moe_build_layout(const long long* topk_ids, long long T, int k, int E, int 
                       int* counts, int* seg_offsets, int* row_map, int* tile_group, int* chunk_scratch,
                       cudaStream_t stream) {
   if (E > 1024) throw std::runtime_error("d9d moe: at most 1024 local experts supported");
-  if (align % 128 != 0 || capacity_rows % 128 != 0) throw std::runtime_error("d9d moe: align/capacity must be multiples of 128");
+  if (align < 1 || (align % 128 == 0 && capacity_rows % 128 != 0))
+    throw std::runtime_error("d9d moe: capacity of a 128-aligned layout must be a multiple of 128");
   const long long n = T * k;
   const long long chunks = (n + CHUNK - 1) / CHUNK;
   const int warps_per_block = 8;
