@@ -114,25 +114,26 @@ def reference_arm(args) -> None:
         print(json.dumps({"impl": "reference", "unavailable": reason}))
 
 
-def build_model(args, device):
-    import torch
-
-    from d9d_b200.module.block.hidden_states_aggregator import HiddenStatesAggregationMode
-    from d9d_b200.module.model.qwen3_moe import (
-        Qwen3MoEForCausalLM,
-        Qwen3MoEForCausalLMParameters,
-        Qwen3MoELayerParameters,
-        Qwen3MoEParameters,
-    )
-    from d9d_b200.pipelining.api import PipelineStageInfo
+def flagship_params(args):
+    from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLMParameters, Qwen3MoELayerParameters, Qwen3MoEParameters
 
     layer = Qwen3MoELayerParameters(**{k: FLAGSHIP[k] for k in (
         "hidden_size", "intermediate_size", "num_experts", "experts_top_k", "num_attention_heads",
         "num_key_value_heads", "rms_norm_eps", "head_dim")})
-    params = Qwen3MoEForCausalLMParameters(model=Qwen3MoEParameters(
+    return Qwen3MoEForCausalLMParameters(model=Qwen3MoEParameters(
         layer=layer, num_hidden_layers=args.layers, rope_base=FLAGSHIP["rope_base"],
         max_position_ids=max(args.seq_len, 4096), split_vocab_size=FLAGSHIP["split_vocab_size"],
         split_vocab_order=FLAGSHIP["split_vocab_order"]))
+
+
+def build_model(args, device):
+    import torch
+
+    from d9d_b200.module.block.hidden_states_aggregator import HiddenStatesAggregationMode
+    from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM
+    from d9d_b200.pipelining.api import PipelineStageInfo
+
+    params = flagship_params(args)
     with torch.device(device):
         model = Qwen3MoEForCausalLM(params, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False).bfloat16()
     model.reset_parameters()
@@ -197,27 +198,28 @@ def main():
     launches = runner.launch_count() - launches_before
     value = tokens_per_step_per_gpu * world / (ms_per_step / 1e3)
 
-    # ---------------------------------------------------------------- end-to-end (pinned host inputs, loss read-back)
+    # ---------------------------------------------------------------- end-to-end through the public Trainer API
     e2e = None
     if not args.no_e2e:
-        host_batches = [runner.synthetic_host_batch(vocab, seed=77 + rank + 1000 * i) for i in range(args.accum * (args.steps + 1))]
-        hit = iter(host_batches)
-        runner.step_from_host([next(hit) for _ in range(args.accum)])
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        h2d = d2h = 0
-        for _ in range(args.steps):
-            loss_host, bi, bo = runner.step_from_host([next(hit) for _ in range(args.accum)])
-            h2d, d2h = bi, bo
-        t1.record()
-        barrier()
-        ms2 = torch.tensor([t0.elapsed_time(t1)], device=device)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e = {"value": tokens_per_step_per_gpu * world / (ms2.item() / args.steps / 1e3), "unit": "tokens/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "final_loss": loss_host}
+        import gc
+        import tempfile
+
+        from d9d_b200.bench_support import TrainerEndToEnd
+
+        final_loss = float(loss)
+        del runner, batches, it, loss
+        gc.collect()
+        torch.cuda.empty_cache()
+        import contextlib
+
+        with tempfile.TemporaryDirectory() as workdir, contextlib.redirect_stdout(sys.stderr):  # stdout carries ONE json line
+            res = TrainerEndToEnd(args, world, flagship_params(args), vocab, workdir).run()
+        e2e = {"value": tokens_per_step_per_gpu * world / (res["ms_per_step"] / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": res["h2d_bytes_per_step"], "d2h_bytes_per_step": res["d2h_bytes_per_step"],
+               "ms_per_step": res["ms_per_step"], "final_loss": res["final_loss"], "gpu_launches": res["launches"],
+               "api": "d9d_b200.loop.run.TrainingConfigurator(...).configure().train(); pinned-memory StatefulDataLoader"}
+    else:
+        final_loss = float(loss)
 
     if rank == 0:
         print(json.dumps({
@@ -246,7 +248,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
-            "final_loss": float(loss),
+            "final_loss": final_loss,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -102,3 +102,96 @@ class TrainStepRunner:
 
     def launch_count(self) -> int:
         return native_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# End-to-end measurement through the public training API (TrainingConfigurator -> Trainer.train())
+# ------------------------------------------------------------------------------------------------------------------
+def trainer_config_for_bench(args, world: int, total_steps: int, workdir: str) -> dict:
+    """The reference example's trainer section (``example/qwen3_moe/pretrain.json``) with checkpointing/tracking off."""
+    return {
+        "run": {"name": "bench", "description": None, "hparams": {}},
+        "batching": {"global_batch_size": args.accum * args.microbatch * world, "microbatch_size": args.microbatch},
+        "data_loading": {"num_workers": 0, "pin_memory": True, "persistent_workers": False},
+        "logging": {"period_steps": 10_000, "tracker": {"provider": "null"}},
+        "pipelining": {"schedule": {"schedule": "gpipe"}},
+        "model_stage_factory": {"source_checkpoint": None, "checkpoint_only_trainable_parameters": False},
+        "determinism": {"base_seed": 1337},
+        "gc": {"period_steps": 10_000},
+        "checkpointing": {"save_dir": workdir, "period_steps": "disable", "num_to_keep": 1},
+        "gradient_clipping": {"max_norm": 5.0, "log_total_steps": 10_000},
+        "profiling": None,
+        "gradient_manager": {"grad_dtype": "float32", "bucket_size_mb": 32},
+        "timeout": {"init_timeout": 10_000, "step_timeout": 600},
+    }
+
+
+class TrainerEndToEnd:
+    """Runs ``warmup + steps`` optimizer steps through ``Trainer.train()`` and times the last ``steps`` of them.
+
+    Every step's batches come out of the framework's ``StatefulDataLoader`` in pinned host memory and are copied to
+    the device inside the loop; the step's loss is copied back to the host by the job logger.  Timing uses CUDA
+    events recorded from ``EVENT_TRAIN_STEP_PRE`` / ``EVENT_TRAIN_STEP_POST`` subscribers.
+    """
+
+    def __init__(self, args, world: int, model_params, vocab: int, workdir: str):
+        from d9d_b200.core.dist_context import DeviceMeshParameters
+        from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
+        from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
+        from d9d_b200.loop.auto.auto_optimizer import StochasticAdamWOptimizerConfig
+        from d9d_b200.loop.config import TrainerConfig
+        from d9d_b200.loop.run import TrainingConfigurator
+        from d9d_b200.recipes import (
+            CausalLMTask,
+            Qwen3MoEModelProvider,
+            Qwen3MoEModelProviderConfig,
+            SyntheticDataConfig,
+            SyntheticDataProvider,
+        )
+
+        self.args, self.world = args, world
+        self.total_steps = args.warmup + args.steps
+        global_batch = args.accum * args.microbatch * world
+        lr_cfg = PiecewiseConfig.model_validate({"name": "piecewise", "scheduler": {"initial_multiplier": 1.0, "phases": [
+            {"mode": "rest", "target_multiplier": 1.0, "curve": {"type": "linear"}}]}})
+        self.trainer = TrainingConfigurator(
+            mesh=DeviceMeshParameters(data_parallel_replicate=world),
+            parameters=TrainerConfig.model_validate(trainer_config_for_bench(args, world, self.total_steps, workdir)),
+            task_provider=lambda ctx: CausalLMTask(),
+            model_provider=Qwen3MoEModelProvider(Qwen3MoEModelProviderConfig(model=model_params)),
+            data_provider=SyntheticDataProvider(SyntheticDataConfig(
+                num_samples=global_batch * self.total_steps, seq_len=args.seq_len, vocab_size=vocab, seed=5)),
+            optimizer_provider=AutoOptimizerProvider(StochasticAdamWOptimizerConfig(lr=2.5e-4, state_dtype="bfloat16")),
+            lr_scheduler_provider=AutoLRSchedulerProvider(lr_cfg),
+        ).configure()
+
+    def run(self) -> dict:
+        from d9d_b200.loop.event.catalogue.train import EVENT_TRAIN_STEP_POST, EVENT_TRAIN_STEP_PRE
+
+        args, state = self.args, self.trainer.state
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = {}
+
+        def pre(ctx) -> None:
+            if ctx.stepper.current_step == args.warmup:
+                state.dist_context.wait_world()
+                launches["before"] = native_launch_count()
+                start.record()
+
+        def post(ctx) -> None:
+            if ctx.stepper.current_step == self.total_steps - 1:
+                end.record()
+                state.dist_context.wait_world()
+                launches["after"] = native_launch_count()
+
+        state.event_bus.subscribe(EVENT_TRAIN_STEP_PRE, pre)
+        state.event_bus.subscribe(EVENT_TRAIN_STEP_POST, post)
+        self.trainer.train()
+        torch.cuda.synchronize()
+        ms = torch.tensor([start.elapsed_time(end)], device=state.dist_context.current_device)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # bytes moved per optimizer step and rank: input_ids + labels + position_ids (int64) up, one fp32 loss down
+        h2d = args.accum * 3 * args.microbatch * args.seq_len * 8
+        return {"ms_per_step": ms.item() / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "final_loss": state.logger.last_loss, "launches": launches.get("after", 0) - launches.get("before", 0)}

@@ -1,0 +1,19 @@
+"""Ready-made providers / tasks for common jobs (used by ``example/`` and ``bench.py``)."""
+
+from .causal_lm import (
+    CausalLMTask,
+    CausalLMPerplexityTask,
+    Qwen3MoEModelProvider,
+    Qwen3MoEModelProviderConfig,
+    SyntheticDataConfig,
+    SyntheticDataProvider,
+)
+
+__all__ = [
+    "CausalLMPerplexityTask",
+    "CausalLMTask",
+    "Qwen3MoEModelProvider",
+    "Qwen3MoEModelProviderConfig",
+    "SyntheticDataConfig",
+    "SyntheticDataProvider",
+]

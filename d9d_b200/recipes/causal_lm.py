@@ -1,0 +1,132 @@
+"""Causal-LM pre-training / evaluation building blocks.
+
+The same roles as the user code of the reference's ``example/qwen3_moe/pretrain.py`` (dataset provider, model
+provider, SFT task), packaged so that the example script, the benchmark and the tests share one implementation.
+"""
+
+from __future__ import annotations
+
+import torch
+from pydantic import BaseModel
+
+from d9d_b200.core.types import ScalarTree
+from d9d_b200.dataset import SyntheticTokenDataset, shard_dataset_data_parallel
+from d9d_b200.loop.control import (
+    BuildForwardInputsContext,
+    BuildForwardInputsResult,
+    ComputeLossContext,
+    ComputeLossResult,
+    CreateMetricsContext,
+    CreateMetricsResult,
+    DatasetProvider,
+    InferenceTask,
+    InitializeDatasetContext,
+    InitializeDatasetResult,
+    InitializeModelStageContext,
+    InitializeModelStageResult,
+    ModelProvider,
+    ParallelizeModelStageContext,
+    PrepareExportModelStageContext,
+    PrepareExportModelStageResult,
+    ProcessOutputsContext,
+    TrainTask,
+    UpdateMetricsContext,
+)
+from d9d_b200.metric.impl.aggregation import SumMetric
+from d9d_b200.model_state.mapper.adapters import identity_mapper_from_module
+from d9d_b200.module.block.head import LM_IGNORE_INDEX
+from d9d_b200.module.block.hidden_states_aggregator import HiddenStatesAggregationMode
+from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM, Qwen3MoEForCausalLMParameters
+from d9d_b200.module.parallelism.model.qwen3_moe import parallelize_qwen3_moe_for_causal_lm
+
+
+class SyntheticDataConfig(BaseModel):
+    num_samples: int
+    seq_len: int
+    vocab_size: int
+    seed: int = 0
+    learnable: bool = False
+
+
+class SyntheticDataProvider(DatasetProvider):
+    """Fixed-length random token samples (``input_ids`` / next-token ``labels`` / ``position_ids``), sharded over the
+    data-parallel ranks.  There is no network in CI, so this stands in for a tokenised corpus."""
+
+    def __init__(self, config: SyntheticDataConfig):
+        self._config = config
+
+    def __call__(self, context: InitializeDatasetContext) -> InitializeDatasetResult:
+        c = self._config
+        data = SyntheticTokenDataset(c.num_samples, c.seq_len, c.vocab_size, seed=c.seed, learnable=c.learnable)
+        return InitializeDatasetResult(dataset=shard_dataset_data_parallel(data, context.dist_context),
+                                       collator=SyntheticTokenDataset.collate)
+
+
+class Qwen3MoEModelProviderConfig(BaseModel):
+    model: Qwen3MoEForCausalLMParameters
+    checkpointing: bool = False
+    dtype: str = "bfloat16"
+
+
+class Qwen3MoEModelProvider(ModelProvider):
+    def __init__(self, config: Qwen3MoEModelProviderConfig):
+        self._config = config
+
+    def initialize_model_stage(self, context: InitializeModelStageContext) -> InitializeModelStageResult:
+        model = Qwen3MoEForCausalLM(self._config.model, context.stage, HiddenStatesAggregationMode.no,
+                                    self._config.checkpointing).to(getattr(torch, self._config.dtype))
+        return InitializeModelStageResult(model=model, state_mapper=identity_mapper_from_module(model))
+
+    def parallelize_model_stage(self, context: ParallelizeModelStageContext) -> None:
+        parallelize_qwen3_moe_for_causal_lm(context.dist_context, context.model, context.stage)
+
+    def prepare_export_model_stage(self, context: PrepareExportModelStageContext) -> PrepareExportModelStageResult:
+        return PrepareExportModelStageResult(state_mapper=identity_mapper_from_module(context.model))
+
+    def dump_hparams(self) -> ScalarTree:
+        return self._config.model_dump(mode="json")
+
+
+class CausalLMTask(TrainTask):
+    """Token-mean next-token loss; the loss weight is the number of target tokens (so gradient accumulation and
+    data parallelism produce the exact global token mean)."""
+
+    def build_forward_inputs(self, ctx: BuildForwardInputsContext) -> BuildForwardInputsResult:
+        ctx.state["labels"] = ctx.batch["labels"]
+        return BuildForwardInputsResult(
+            inputs={"input_ids": ctx.batch["input_ids"]},
+            kwargs={"labels": ctx.batch["labels"], "position_ids": ctx.batch["position_ids"]},
+        )
+
+    def create_metrics(self, ctx: CreateMetricsContext) -> CreateMetricsResult:
+        return CreateMetricsResult(metrics={"num_tokens": SumMetric()})
+
+    def update_metrics(self, ctx: UpdateMetricsContext) -> None:
+        ctx.metrics["num_tokens"].update(ctx.state["num_tokens"])
+
+    def compute_loss(self, ctx: ComputeLossContext) -> ComputeLossResult:
+        num_tokens = (ctx.state["labels"] != LM_IGNORE_INDEX).sum()
+        ctx.state["num_tokens"] = num_tokens
+        return ComputeLossResult(loss=ctx.pipeline_results["logps"].sum() / num_tokens, loss_weight=num_tokens / 1000)
+
+
+class CausalLMPerplexityTask(InferenceTask):
+    """Accumulates summed negative log-likelihood and token counts; ``perplexity()`` after the run."""
+
+    def __init__(self) -> None:
+        self.nll_sum = 0.0
+        self.num_tokens = 0
+
+    def build_forward_inputs(self, ctx: BuildForwardInputsContext) -> BuildForwardInputsResult:
+        ctx.state["labels"] = ctx.batch["labels"]
+        return BuildForwardInputsResult(
+            inputs={"input_ids": ctx.batch["input_ids"]},
+            kwargs={"labels": ctx.batch["labels"], "position_ids": ctx.batch["position_ids"]},
+        )
+
+    def process_outputs(self, ctx: ProcessOutputsContext) -> None:
+        self.nll_sum += float(ctx.pipeline_results["logps"].sum())
+        self.num_tokens += int((ctx.state["labels"] != LM_IGNORE_INDEX).sum())
+
+    def perplexity(self) -> float:
+        return float(torch.tensor(self.nll_sum / max(self.num_tokens, 1)).exp())
