@@ -34,6 +34,7 @@ class TrainStepRunner:
         for p in self.params:
             p.grad_dtype = torch.float32
             p.grad = self.grad_arena[off : off + p.numel()].view_as(p)
+            p._d9d_fused_wgrad = True  # wgrad GEMMs accumulate into the arena in their epilogue
             off += (p.numel() + 63) // 64 * 64
         self.opt = StochasticAdamW(self.params, lr=lr, state_dtype=torch.bfloat16)
         self.grad_scale = torch.ones(1, dtype=torch.float32, device=device)

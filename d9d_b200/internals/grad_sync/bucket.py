@@ -10,6 +10,8 @@ from torch.distributed import DeviceMesh
 from torch.distributed.tensor import DTensor
 from torch.utils.hooks import RemovableHandle
 
+from d9d_b200.kernel._native import FUSED_WGRAD_ATTR
+
 
 def local_of(t: torch.Tensor) -> torch.Tensor:
     return t.to_local() if isinstance(t, DTensor) else t
@@ -69,12 +71,15 @@ class _FlatBucket(AbstractGradientBucket):
     @torch.no_grad()
     def bind(self) -> None:
         self._alias_grads()
+        for p in self._params:
+            setattr(p, FUSED_WGRAD_ATTR, True)  # wgrad GEMMs may accumulate into the arena in their epilogue
         self._bound = True
 
     @torch.no_grad()
     def unbind(self) -> None:
         for p in self._params:
             p.grad = None
+            setattr(p, FUSED_WGRAD_ATTR, False)
         self._bound = False
 
     @torch.no_grad()

@@ -65,3 +65,42 @@ def grad_dtype_of(t: torch.Tensor) -> torch.dtype:
     if gd not in (torch.bfloat16, torch.float32):
         return t.dtype
     return gd
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Weight-gradient accumulation fused into the wgrad GEMM epilogue
+# ------------------------------------------------------------------------------------------------------------------
+MAIN_PARAM_ATTR = "_d9d_main_param"  # set on local views handed to modules: the (D)Tensor parameter that owns .grad
+FUSED_WGRAD_ATTR = "_d9d_fused_wgrad"  # set by the gradient infrastructure on parameters whose .grad is pre-allocated
+
+
+def fused_wgrad_owner(weight: torch.Tensor) -> torch.Tensor | None:
+    """The leaf parameter whose pre-allocated ``.grad`` the wgrad GEMM of ``weight`` may accumulate into, or None.
+
+    Writing ``dW`` straight into the flat gradient arena (``beta = 1`` in the GEMM epilogue, a TMA reduce-add)
+    removes the temporary ``dW`` tensor and autograd's ``grad += dW`` pass.  Protocol used by the autograd functions:
+
+    * forward receives the *detached* weight plus the owner as an extra (unused) input, so the owner stays a leaf of
+      the graph;
+    * backward accumulates into ``fused_wgrad_buffer(owner)`` and returns ``None`` for the owner – the autograd engine
+      still runs the owner's ``AccumulateGrad`` node with an undefined gradient, which fires its post-accumulate-grad
+      hooks exactly once (this is what drives the bucketed gradient all-reduce).
+
+    Only parameters the gradient infrastructure opted in (``GradientSynchronizer.bind`` / the bench runner) qualify.
+    """
+    if not torch.is_grad_enabled() or not weight.requires_grad:
+        return None
+    owner = getattr(weight, MAIN_PARAM_ATTR, weight)
+    if not getattr(owner, FUSED_WGRAD_ATTR, False) or not owner.is_leaf or owner.grad is None:
+        return None
+    local = getattr(owner.grad, "_local_tensor", owner.grad)
+    if local.shape != weight.shape or not local.is_contiguous() or local.dtype not in (torch.float32, torch.bfloat16):
+        return None
+    return owner
+
+
+def fused_wgrad_buffer(owner: torch.Tensor) -> torch.Tensor:
+    grad = owner.grad
+    if grad is None:
+        raise RuntimeError("d9d_b200: the gradient buffer of a fused-wgrad parameter disappeared between forward and backward")
+    return getattr(grad, "_local_tensor", grad)  # DTensor -> local shard

@@ -8,7 +8,7 @@ from torch.autograd import Function
 
 from d9d_b200.core.autograd import GLOBAL_GRAD_CONTEXT, GradDirection
 
-from .._native import grad_dtype_of, native_ops, on_gpu
+from .._native import fused_wgrad_buffer, fused_wgrad_owner, grad_dtype_of, native_ops, on_gpu
 
 ALIGN = 128  # GEMM BLOCK_M: expert segments never share an M-tile, per-expert K ranges are BLOCK_K aligned
 
@@ -168,8 +168,9 @@ def _grouped_linear_reference(xp: torch.Tensor, weight: torch.Tensor, layout: Mo
 
 class _GroupedLinearFunction(Function):
     @staticmethod
-    def forward(ctx: Any, xp: torch.Tensor, weight: torch.Tensor, layout: MoELayout):
+    def forward(ctx: Any, xp: torch.Tensor, weight: torch.Tensor, layout: MoELayout, owner: torch.Tensor | None = None):
         ctx.layout = layout
+        ctx.owner = owner  # see ``fused_wgrad_owner``: dW accumulates straight into owner.grad
         ctx.save_for_backward(xp, weight)
         out = torch.empty(xp.shape[0], weight.shape[2], device=xp.device, dtype=xp.dtype)
         native_ops().gemm_grouped_m(xp, weight, out, layout.tile_group, True)
@@ -185,11 +186,13 @@ class _GroupedLinearFunction(Function):
         if ctx.needs_input_grad[0] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.inputs):
             dx = torch.empty_like(xp)
             ops.gemm_grouped_m(dy, weight, dx, layout.tile_group, False)  # W[e] read as [N'=in, K'=out]
-        if ctx.needs_input_grad[1] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight):
-            grad_dtype = grad_dtype_of(weight)
-            dw = torch.empty(weight.shape, device=weight.device, dtype=grad_dtype)
-            ops.gemm_grouped_k(xp, dy, dw, layout.seg_offsets, False)
-        return dx, dw, None
+        if GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight):
+            if ctx.owner is not None and ctx.needs_input_grad[3]:
+                ops.gemm_grouped_k(xp, dy, fused_wgrad_buffer(ctx.owner), layout.seg_offsets, True)  # grad[e] += xp_e^T @ dy_e
+            elif ctx.needs_input_grad[1]:
+                dw = torch.empty(weight.shape, device=weight.device, dtype=grad_dtype_of(weight))
+                ops.gemm_grouped_k(xp, dy, dw, layout.seg_offsets, False)
+        return dx, dw, None, None
 
 
 def grouped_linear(xp: torch.Tensor, weight: torch.Tensor, layout: MoELayout) -> torch.Tensor:
@@ -198,5 +201,8 @@ def grouped_linear(xp: torch.Tensor, weight: torch.Tensor, layout: MoELayout) ->
     NOTE: rows past the last expert segment are left uninitialised (they are never read back).
     """
     if on_gpu(xp):
-        return _GroupedLinearFunction.apply(xp, weight, layout)
+        owner = fused_wgrad_owner(weight)
+        if owner is None:
+            return _GroupedLinearFunction.apply(xp, weight, layout, None)
+        return _GroupedLinearFunction.apply(xp, weight.detach(), layout, owner)
     return _grouped_linear_reference(xp, weight, layout)

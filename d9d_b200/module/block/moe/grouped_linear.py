@@ -7,6 +7,7 @@ from torch import nn
 from torch.distributed.tensor import DTensor
 
 from d9d_b200.core.autograd import GradDirection
+from d9d_b200.kernel._native import MAIN_PARAM_ATTR
 from d9d_b200.kernel.gmm import gmm
 from d9d_b200.kernel.moe import MoELayout, grouped_linear
 from d9d_b200.module.base import ModuleLateInit
@@ -33,6 +34,7 @@ class GroupedLinear(nn.Module, ModuleLateInit):
         weight: torch.Tensor = self.weight
         if isinstance(weight, DTensor):
             weight = weight.to_local()
+            setattr(weight, MAIN_PARAM_ATTR, self.weight)  # wgrad accumulates straight into the sharded .grad
         if isinstance(x_groups, MoELayout):
             return grouped_linear(x, weight, x_groups)
         return gmm(x, weight, x_groups, a_grad_direction=GradDirection.inputs, b_grad_direction=GradDirection.weight)

@@ -7,6 +7,8 @@ from torch.distributed import DeviceMesh
 from torch.distributed.tensor import DTensor, Placement, distribute_tensor
 from torch.distributed.tensor.parallel import ParallelStyle
 
+from d9d_b200.kernel._native import MAIN_PARAM_ATTR
+
 
 class _LocalParameterView:
     """Forward pre/post hook pair that lends *local* tensors to the modules for the duration of a forward.
@@ -32,7 +34,9 @@ class _LocalParameterView:
             param = owner._parameters[name]  # noqa: SLF001
             stash.append(param)
             if isinstance(param, DTensor):
-                owner._parameters[name] = param.to_local(grad_placements=self._grad_placement)  # noqa: SLF001
+                local = param.to_local(grad_placements=self._grad_placement)
+                setattr(local, MAIN_PARAM_ATTR, param)  # lets wgrad kernels accumulate straight into param.grad
+                owner._parameters[name] = local  # noqa: SLF001
         self._stash = stash
 
     def exit(self, module: nn.Module, args: Any, output: Any) -> None:

@@ -25,6 +25,7 @@ struct GemmArgs {
   const int* tile_group = nullptr;     // GROUPED_M
   const int* group_offsets = nullptr;  // GROUPED_K
   int block_n = 0;                     // 0 => heuristic
+  int k_splits = 0;                    // dense fp32-accumulate epilogue only: 0 => heuristic, 1 => off
   // fused linear cross entropy
   const long long* ce_target = nullptr;
   const float* ce_lse = nullptr;

@@ -46,6 +46,23 @@ inline CUtensorMap make_tmap_bf16_3d(const void* base, uint64_t d0, uint64_t d1,
   return m;
 }
 
+// Output tensor map: [groups, rows, cols] row-major, box = 32 rows x 128 bytes, 128B swizzle (matches the epilogue's
+// staging layout).  Returns false when base / pitches do not meet TMA's 16-byte alignment rules.
+inline bool make_tmap_out(CUtensorMap* m, void* base, bool bf16, uint64_t cols, uint64_t rows, uint64_t groups,
+                          uint64_t row_pitch_elems, uint64_t group_pitch_elems) {
+  const uint64_t esz = bf16 ? 2 : 4;
+  cuuint64_t dims[3] = {cols, rows, groups};
+  cuuint64_t strides[2] = {row_pitch_elems * esz, (groups > 1 ? group_pitch_elems : row_pitch_elems * rows) * esz};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / esz), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (strides[0] & 15) != 0 || (strides[1] & 15) != 0) return false;
+  CUresult r = get_encode_fn()(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base,
+                               dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("d9d gemm: cuTensorMapEncodeTiled (output) failed: " + std::to_string(r));
+  return true;
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -79,6 +96,23 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
     else       tb = make_tmap_bf16_3d(a.B, a.N, a.K, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.K, 64, BLOCK_K);
   }
   Params p{};
+  CUtensorMap td = ta;  // placeholder when the direct-store epilogue is used
+  if (EPI != EPI_CE_LSE) {
+    constexpr bool out_bf16 = (EPI == EPI_BF16 || EPI == EPI_BF16_ACC || EPI == EPI_CE_DLOGITS);
+    const uint64_t groups = (MODE == GROUPED_K) ? a.num_groups : 1;
+    p.tma_epilogue = make_tmap_out(&td, a.D, out_bf16, a.N, a.M, groups, a.ldd, a.d_group_stride) ? 1 : 0;
+  }
+  p.k_splits = 1;
+  if (MODE == DENSE && EPI == EPI_F32_ACC && p.tma_epilogue) {
+    // split-K: reduce-adds from several CTAs land on the same tile (fp32 adds in L2; order is not deterministic)
+    const long long mn_tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N);
+    const long long k_blocks = (a.K + BLOCK_K - 1) / BLOCK_K;
+    long long splits = a.k_splits > 0 ? a.k_splits : sm_count() / mn_tiles;
+    const long long max_splits = k_blocks / 8;  // keep >= 8 k-blocks (512 deep) per slice
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.k_splits = static_cast<int>(splits);
+  }
   p.M = a.M; p.N = a.N; p.K = a.K; p.num_groups = a.num_groups;
   p.D = a.D; p.ldd = a.ldd; p.d_group_stride = a.d_group_stride;
   p.tile_group = a.tile_group; p.group_offsets = a.group_offsets;
@@ -87,10 +121,10 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   p.ce_ignore_index = a.ce_ignore_index; p.ce_softcap = 0.f;
 
   const long long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
-  long long tiles = m_tiles * n_tiles * (MODE == GROUPED_K ? a.num_groups : 1);
+  long long tiles = m_tiles * n_tiles * (MODE == GROUPED_K ? a.num_groups : 1) * p.k_splits;
   if (tiles <= 0) return;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, td, p);
 }
 
 // pick BLOCK_N minimising (waves x tile cost); ties go to the wider tile
@@ -122,6 +156,16 @@ inline int pick_block_n(long long m_tiles_x_groups, int N) {
       case EPI_F32_ACC: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_F32_ACC, bn, args, stream); break;    \
       case EPI_BF16_ACC: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_BF16_ACC, bn, args, stream); break;  \
       default: throw std::runtime_error("d9d gemm: unsupported epilogue for this mode");          \
+    }                                                                                             \
+  } while (0)
+
+// store-only epilogues (layouts that never receive an accumulate request keep the instantiation count down)
+#define D9D_DISPATCH_EPI2(MODE, AMN, BMN, epi, bn, args, stream)                                  \
+  do {                                                                                            \
+    switch (epi) {                                                                                \
+      case EPI_BF16: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_BF16, bn, args, stream); break;          \
+      case EPI_F32: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_F32, bn, args, stream); break;            \
+      default: throw std::runtime_error("d9d gemm: accumulate epilogue not built for this operand layout"); \
     }                                                                                             \
   } while (0)
 

@@ -11,7 +11,12 @@
 //     GROUPED_M  rows of A/D are grouped by expert (128-row aligned segments, device-side tile->expert table),
 //                B is [E, ...]  -> MoE forward / dgrad without any host sync
 //     GROUPED_K  the reduction dim is grouped (per-expert weight gradients), D is [E, M, N]
-// * epilogues: bf16 store, fp32 store, fp32 accumulate, and the fused linear-cross-entropy epilogues.
+// * epilogues: bf16 store, fp32 store, fp32/bf16 accumulate, and the fused linear-cross-entropy epilogues.
+//   Output tiles leave the SM through TMA: TMEM -> registers -> 128B-swizzled smem staging -> cp.async.bulk.tensor
+//   store, or cp.reduce.async.bulk.tensor (.add) for the accumulate epilogues, so `D += acc` costs no global loads
+//   in the SM (the add happens in L2) and partial tiles are clipped by the tensor map.
+// * split-K (DENSE, accumulate epilogues): several CTAs reduce-add K-slices of one output tile; used when a wgrad
+//   has few output tiles but a long reduction dim.
 #pragma once
 
 #include "common.cuh"
@@ -38,6 +43,8 @@ enum Epi : int {
 struct Params {
   int M, N, K;            // DENSE: problem dims. GROUPED_M: M = padded row capacity. GROUPED_K: M,N = per-expert out dims
   int num_groups;         // experts (1 for dense)
+  int k_splits;           // DENSE + accumulate epilogue: K is cut into this many slices (1 => off)
+  int tma_epilogue;       // 1: output through the tmap_d TMA store/reduce path, 0: direct global stores
   void* D;                // output
   long long ldd;          // leading dim of D (elements)
   long long d_group_stride;  // GROUPED_K: elements between per-expert outputs
@@ -59,7 +66,8 @@ struct Cfg {
   static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int SMEM_BUDGET = 212 * 1024;
+  static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 2 * 4096;  // per epilogue warp: 2 x (32 rows x 128 B)
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256 - EPI_STAGING_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS_NEEDED = 2 * BLOCK_N;
@@ -68,7 +76,7 @@ struct Cfg {
                                         : TMEM_COLS_NEEDED <= 128 ? 128
                                         : TMEM_COLS_NEEDED <= 256 ? 256
                                                                   : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct TileCoord {
@@ -82,6 +90,7 @@ __device__ __forceinline__ int num_tiles(const Params& p) {
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   if (MODE == GROUPED_K) return p.num_groups * m_tiles * n_tiles;
+  if (MODE == DENSE) return m_tiles * n_tiles * p.k_splits;
   return m_tiles * n_tiles;
 }
 
@@ -102,6 +111,11 @@ __device__ __forceinline__ TileCoord get_tile(const Params& p, int tile) {
     t.k_blocks = (k1 - k0 + BLOCK_K - 1) / BLOCK_K;
     return t;
   }
+  int k_split = 0;
+  if (MODE == DENSE && p.k_splits > 1) {  // tile = split * (m_tiles * n_tiles) + mn: one K-slice per wave
+    k_split = tile / (m_tiles * n_tiles);
+    tile -= k_split * (m_tiles * n_tiles);
+  }
   // L2-friendly rasterisation: walk GROUP_M m-blocks for each n-block before moving on.
   constexpr int GROUP_M = 8;
   const int group_span = GROUP_M * n_tiles;
@@ -113,6 +127,13 @@ __device__ __forceinline__ TileCoord get_tile(const Params& p, int tile) {
   t.n_blk = r / gm;
   t.k_begin = 0;
   t.k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  if (MODE == DENSE && p.k_splits > 1) {
+    const int per_split = (t.k_blocks + p.k_splits - 1) / p.k_splits;
+    const int first = k_split * per_split;
+    t.k_begin = first * BLOCK_K;
+    t.k_blocks = max(0, min(per_split, t.k_blocks - first));
+    t.valid = t.k_blocks > 0;  // an empty slice has nothing to add
+  }
   t.group = 0;
   if (MODE == GROUPED_M) {
     t.group = p.tile_group[t.m_blk];
@@ -123,14 +144,16 @@ __device__ __forceinline__ TileCoord get_tile(const Params& p, int tile) {
 
 template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_d, const Params p) {
   using C = Cfg<BLOCK_N>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * C::A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * C::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 8 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -143,6 +166,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_epilogue) tma_prefetch_desc(&tmap_d);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -235,6 +259,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int lane = lane_id();
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t epi_chunk = 0;  // running count of staged chunks (selects the staging buffer)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
       if (!t.valid) continue;
@@ -281,6 +306,80 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (row_ok) {
           p.ce_part_max[static_cast<long long>(t.n_blk) * p.M + row] = run_max;
           p.ce_part_sum[static_cast<long long>(t.n_blk) * p.M + row] = run_sum;
+        }
+      } else if (p.tma_epilogue) {
+        // ---- TMA epilogue: 128-byte output chunks (32 fp32 / 64 bf16 columns) staged in swizzled smem ----
+        constexpr bool OUT_BF16 = (EPI == EPI_BF16 || EPI == EPI_BF16_ACC || EPI == EPI_CE_DLOGITS);
+        constexpr bool REDUCE = (EPI == EPI_F32_ACC || EPI == EPI_BF16_ACC);
+        constexpr int CHUNK_COLS = OUT_BF16 ? 64 : 32;
+        static_assert(BLOCK_N % CHUNK_COLS == 0, "BLOCK_N must be a multiple of the epilogue chunk");
+        float lse = 0.f, g = 0.f;
+        long long tgt = -1;
+        if constexpr (EPI == EPI_CE_DLOGITS) {
+          if (row_ok) {
+            tgt = p.ce_target[row];
+            lse = p.ce_lse[row];
+            g = (tgt == p.ce_ignore_index) ? 0.f : p.ce_grad[row];
+          }
+        }
+        if (have_acc || !REDUCE) {
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N / CHUNK_COLS; ++c) {
+            const int cbase = col0 + c * CHUNK_COLS;
+            if (cbase >= p.N) break;  // warp-uniform
+            uint8_t* stage_buf = smem_epi + (quad * 2 + (epi_chunk & 1)) * 4096;
+            ++epi_chunk;
+            if (lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
+            __syncwarp();
+            uint32_t packed[32];
+            if constexpr (OUT_BF16) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                if (have_acc) {
+                  tmem_ld_32x32b_x32(taddr + c * 64 + h * 32, r);
+                  tmem_ld_wait();
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) r[i] = 0;
+                }
+                if constexpr (EPI == EPI_CE_DLOGITS) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    float pr = __expf(__uint_as_float(r[i]) - lse);
+                    if (cbase + h * 32 + i == tgt) pr -= 1.f;
+                    r[i] = __float_as_uint(pr * g);
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  packed[h * 16 + i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+              }
+            } else {
+              if (have_acc) {
+                tmem_ld_32x32b_x32(taddr + c * 32, packed);
+                tmem_ld_wait();
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) packed[i] = 0;
+              }
+            }
+            // row `lane` of the 32 x 128B box; 16-byte chunk j lives at j ^ (row & 7) under the 128B swizzle
+            uint8_t* my_row = stage_buf + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int r0 = t.m_blk * BLOCK_M + quad * 32;
+              const int g0 = (MODE == GROUPED_K) ? t.group : 0;
+              if constexpr (REDUCE) tma_reduce_add_3d(&tmap_d, stage_buf, cbase, r0, g0);
+              else tma_store_3d(&tmap_d, stage_buf, cbase, r0, g0);
+              tma_store_commit();
+            }
+          }
         }
       } else {
         long long d_off = static_cast<long long>(row) * p.ldd;
@@ -381,6 +480,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp are complete before smem is released
   }
 
   tc_fence_before();

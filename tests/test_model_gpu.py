@@ -73,3 +73,33 @@ def test_smoke_entry():
     import __graft_entry__ as entry
 
     entry.smoke()
+
+
+@pytest.mark.parametrize("grad_dtype", [torch.float32, torch.bfloat16])
+def test_wgrad_accumulates_into_preallocated_grad(grad_dtype):
+    """Opted-in parameters get ``grad += dW`` from the wgrad GEMM epilogue; result == autograd accumulation and the
+    autograd still fires the post-accumulate hooks once per backward."""
+    torch.manual_seed(1)
+    base = _tiny(moe=True)
+    base.reset_parameters()
+    a = copy.deepcopy(base).bfloat16().cuda()
+    b = copy.deepcopy(base).bfloat16().cuda()
+    fired = {}
+    for n, p in b.named_parameters():
+        p.grad_dtype = grad_dtype
+        p.grad = torch.zeros(p.shape, device="cuda", dtype=grad_dtype)
+        p._d9d_fused_wgrad = True
+        p.register_post_accumulate_grad_hook(lambda q, n=n: fired.__setitem__(n, fired.get(n, 0) + 1))
+    for p in a.parameters():
+        p.grad_dtype = grad_dtype
+    ids = torch.randint(0, 1024, (2, 128), device="cuda")
+    labels = torch.randint(0, 1024, (2, 128), device="cuda")
+    pos = torch.arange(128, device="cuda")[None].expand(2, -1).contiguous()
+    for _ in range(2):  # two accumulation rounds
+        for m in (a, b):
+            (m(input_ids=ids, position_ids=pos, labels=labels)["logps"].sum() / 256).backward()
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert fired.get(n) == 2, (n, fired.get(n))
+        tol = 2e-2 if grad_dtype == torch.bfloat16 else 1e-4
+        torch.testing.assert_close(pb.grad.float(), pa.grad.float(), rtol=tol, atol=tol * float(pa.grad.float().abs().max()),
+                                   msg=lambda m: f"{n}: {m}")  # noqa: B023

@@ -350,3 +350,30 @@ def test_grad_utils(ops):
     ref = x * 0.5
     ops.scale_inplace_(x, sc)
     assert torch.allclose(x, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gemm_unaligned_output_uses_direct_epilogue(ops, dtype, accumulate):
+    # an output whose base address is not 16-byte aligned cannot go through TMA: the direct-store epilogue must kick in
+    M, N, K = 300, 200, 256
+    a = torch.randn(K, M, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    flat = torch.randn(M * N + 1, device="cuda", dtype=dtype)
+    d = flat[1:].view(M, N)
+    d0 = d.clone()
+    ops.gemm(a, b, d, True, True, accumulate)
+    ref = a.float().t() @ b.float() + (d0.float() if accumulate else 0)
+    assert _rel_err(d, ref) < (1e-2 if dtype == torch.bfloat16 else 1e-4)
+    assert flat[0] == flat[0]  # untouched guard element is still a number
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 768, 16384), (512, 768, 8192), (2048, 768, 4096)])
+def test_gemm_split_k_accumulate(ops, M, N, K):
+    # few output tiles + long K: the fp32-accumulate epilogue splits K across CTAs (TMA reduce-add into the output)
+    a = torch.randn(K, M, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    d0 = torch.randn(M, N, device="cuda", dtype=torch.float32)
+    d = d0.clone()
+    ops.gemm(a, b, d, True, True, True)
+    assert _rel_err(d, a.float().t() @ b.float() + d0) < 1e-4
