@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--accum", type=int, default=2, help="microbatches per GPU per optimizer step")
     ap.add_argument("--layers", type=int, default=FLAGSHIP["num_hidden_layers"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dp-impl", default="nvlink", choices=["nvlink", "nccl"],
+                    help="multi-GPU gradient path of the device-timed arm: own NVLink peer-memory kernels or NCCL all-reduce")
     return ap.parse_args()
 
 
@@ -241,7 +243,8 @@ def main():
                 "global_batch": args.accum * args.microbatch * world,
                 "microbatch": args.microbatch,
                 "seq_len": args.seq_len,
-                "parallelism": f"dp{world}" if world > 1 else "single",
+                "parallelism": (f"dp{world} ({'NVLink reduce-scatter+AdamW+all-gather kernels' if args.dp_impl == 'nvlink' else 'NCCL all-reduce'})"
+                                if world > 1 else "single"),
                 "optimizer": "stochastic_adamw bf16 states, fp32 grads, clip 5.0",
                 "l2": "working set (>10 GB weights+grads+activations) exceeds the 126 MB L2; 192 MB flush before timing",
             },

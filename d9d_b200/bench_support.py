@@ -27,19 +27,29 @@ class TrainStepRunner:
         torch.manual_seed(1337)  # identical init on every replica
         self.model = build_model(args, device)
         self.params = [p for p in self.model.parameters() if p.requires_grad]
-        # flat fp32 gradient arena; every param.grad is a view (accumulated in place by autograd)
-        total = sum((p.numel() + 63) // 64 * 64 for p in self.params)
-        self.grad_arena = torch.zeros(total, dtype=torch.float32, device=device)
-        off = 0
-        for p in self.params:
-            p.grad_dtype = torch.float32
-            p.grad = self.grad_arena[off : off + p.numel()].view_as(p)
-            p._d9d_fused_wgrad = True  # wgrad GEMMs accumulate into the arena in their epilogue
-            off += (p.numel() + 63) // 64 * 64
-        self.opt = StochasticAdamW(self.params, lr=lr, state_dtype=torch.bfloat16)
         self.grad_scale = torch.ones(1, dtype=torch.float32, device=device)
-        self.opt.grad_scale = self.grad_scale
         self.max_norm = max_norm
+        self.nvlink = world > 1 and getattr(args, "dp_impl", "nvlink") == "nvlink"
+        if self.nvlink:
+            # gradients / parameters live in symmetric NVLink arenas; reduce-scatter + AdamW + all-gather are two
+            # peer-memory kernels inside opt.step() (no NCCL all-reduce of the gradients)
+            from d9d_b200.optim.nvlink import NvlinkShardedAdamW
+
+            self.opt = NvlinkShardedAdamW(self.params, dist.group.WORLD, lr=lr, state_dtype=torch.bfloat16, max_norm=max_norm)
+            self.opt.grad_scale = self.grad_scale
+            self.grad_arena = self.opt.grad_arena.buffer
+        else:
+            # flat fp32 gradient arena; every param.grad is a view (accumulated in place by autograd)
+            total = sum((p.numel() + 63) // 64 * 64 for p in self.params)
+            self.grad_arena = torch.zeros(total, dtype=torch.float32, device=device)
+            off = 0
+            for p in self.params:
+                p.grad_dtype = torch.float32
+                p.grad = self.grad_arena[off : off + p.numel()].view_as(p)
+                p._d9d_fused_wgrad = True  # wgrad GEMMs accumulate into the arena in their epilogue
+                off += (p.numel() + 63) // 64 * 64
+            self.opt = StochasticAdamW(self.params, lr=lr, state_dtype=torch.bfloat16)
+            self.opt.grad_scale = self.grad_scale
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
         self.weight_sum = torch.zeros(1, dtype=torch.float32, device=device)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=device)
@@ -72,19 +82,24 @@ class TrainStepRunner:
             self._forward_backward(b)
         ops = native_ops()
         if self.world > 1:
-            dist.all_reduce(self.grad_arena)
+            if not self.nvlink:
+                dist.all_reduce(self.grad_arena)
             stats = torch.cat([self.weight_sum, self.loss_sum])
             dist.all_reduce(stats)
             self.weight_sum, self.loss_sum = stats[:1].clone(), stats[1:].clone()
-        # global grad norm of the *scaled* gradient, clip coefficient, all on the device
-        self.sumsq.zero_()
-        ops.sumsq_accumulate_(self.grad_arena, self.sumsq)
         inv_w = 1.0 / self.weight_sum
-        norm = self.sumsq.sqrt() * inv_w
-        clip = torch.clamp(self.max_norm / (norm + 1e-6), max=1.0)
-        self.grad_scale.copy_(inv_w * clip)
-        self.opt.step()
-        self.grad_arena.zero_()
+        if self.nvlink:
+            self.grad_scale.copy_(inv_w)  # reduction, clipping, update, broadcast and zeroing happen inside step()
+            self.opt.step()
+        else:
+            # global grad norm of the *scaled* gradient, clip coefficient, all on the device
+            self.sumsq.zero_()
+            ops.sumsq_accumulate_(self.grad_arena, self.sumsq)
+            norm = self.sumsq.sqrt() * inv_w
+            clip = torch.clamp(self.max_norm / (norm + 1e-6), max=1.0)
+            self.grad_scale.copy_(inv_w * clip)
+            self.opt.step()
+            self.grad_arena.zero_()
         loss = (self.loss_sum / self.weight_sum).clone()
         self.weight_sum.zero_()
         self.loss_sum.zero_()

@@ -337,6 +337,43 @@ void scale_inplace_(Tensor x, const Tensor& scale) {
 
 }  // namespace
 
+// ------------------------------------------------------------------ NVLink data-parallel optimizer -----------
+// `peer_ptrs_dev` / `multicast_ptr` come from torch.distributed._symmetric_memory (buffer_ptrs_dev, multicast_ptr).
+void nvl_reduce_shard_(Tensor own_grad, int64_t peer_ptrs_dev, int64_t multicast_ptr, int64_t begin, int64_t end,
+                       int64_t world, int64_t rank, Tensor sumsq) {
+  CHECK_CUDA_CONTIG(own_grad); CHECK_CUDA_CONTIG(sumsq);
+  TORCH_CHECK(own_grad.scalar_type() == at::kFloat && sumsq.scalar_type() == at::kFloat);
+  TORCH_CHECK(0 <= begin && begin <= end && end <= own_grad.numel(), "nvl_reduce_shard_: bad shard bounds");
+  c10::cuda::CUDAGuard guard(own_grad.device());
+  d9d::nvl_reduce_shard(reinterpret_cast<const float* const*>(peer_ptrs_dev), reinterpret_cast<const float*>(multicast_ptr),
+                        own_grad.data_ptr<float>(), begin, end, static_cast<int>(world), static_cast<int>(rank),
+                        sumsq.data_ptr<float>(), cur_stream());
+}
+
+void nvl_adamw_shard_(Tensor own_param, const Tensor& own_grad, Tensor exp_avg, Tensor exp_avg_sq, int64_t peer_ptrs_dev,
+                      int64_t multicast_ptr, int64_t begin, int64_t end, int64_t world, int64_t rank, double lr,
+                      double beta1, double beta2, double eps, double weight_decay, double bias_corr1, double bias_corr2,
+                      int64_t seed, const c10::optional<Tensor>& grad_scale) {
+  CHECK_CUDA_CONTIG(own_param); CHECK_CUDA_CONTIG(own_grad); CHECK_CUDA_CONTIG(exp_avg); CHECK_CUDA_CONTIG(exp_avg_sq);
+  TORCH_CHECK(own_param.scalar_type() == at::kBFloat16 && own_grad.scalar_type() == at::kFloat);
+  TORCH_CHECK(exp_avg.scalar_type() == exp_avg_sq.scalar_type() &&
+              (exp_avg.scalar_type() == at::kBFloat16 || exp_avg.scalar_type() == at::kFloat));
+  TORCH_CHECK(0 <= begin && begin <= end && end <= own_param.numel() && end <= own_grad.numel(), "nvl_adamw_shard_: bad shard bounds");
+  TORCH_CHECK(exp_avg.numel() >= end - begin && exp_avg_sq.numel() >= end - begin, "nvl_adamw_shard_: state smaller than shard");
+  c10::cuda::CUDAGuard guard(own_param.device());
+  const float* gs = nullptr;
+  if (grad_scale.has_value()) {
+    TORCH_CHECK(grad_scale->is_cuda() && grad_scale->scalar_type() == at::kFloat);
+    gs = grad_scale->data_ptr<float>();
+  }
+  d9d::nvl_adamw_shard(reinterpret_cast<void* const*>(peer_ptrs_dev), reinterpret_cast<void*>(multicast_ptr), own_param.data_ptr(),
+                       own_grad.data_ptr<float>(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), begin, end,
+                       static_cast<int>(world), static_cast<int>(rank), static_cast<float>(lr), static_cast<float>(beta1),
+                       static_cast<float>(beta2), static_cast<float>(eps), static_cast<float>(weight_decay),
+                       static_cast<float>(bias_corr1), static_cast<float>(bias_corr2), static_cast<uint64_t>(seed), gs,
+                       exp_avg.scalar_type() == at::kBFloat16, cur_stream());
+}
+
 TORCH_LIBRARY(d9d_b200, m) {
   m.def("gemm(Tensor a, Tensor b, Tensor(a!) d, bool a_mn, bool b_mn, bool accumulate) -> ()");
   m.def("gemm_grouped_m(Tensor a, Tensor b, Tensor(a!) d, Tensor tile_group, bool b_mn) -> ()");
@@ -358,6 +395,11 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_permute(Tensor x, Tensor? probs, Tensor row_map, Tensor counts, Tensor seg_offsets, int capacity) -> (Tensor, Tensor)");
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
+  m.def("nvl_reduce_shard_(Tensor(a!) own_grad, int peer_ptrs_dev, int multicast_ptr, int begin, int end, int world, int rank, "
+        "Tensor(b!) sumsq) -> ()");
+  m.def("nvl_adamw_shard_(Tensor(a!) own_param, Tensor own_grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, int peer_ptrs_dev, "
+        "int multicast_ptr, int begin, int end, int world, int rank, float lr, float beta1, float beta2, float eps, "
+        "float weight_decay, float bias_corr1, float bias_corr2, int seed, Tensor? grad_scale) -> ()");
   m.def("scale_inplace_(Tensor(a!) x, Tensor scale) -> ()");
 }
 
@@ -380,5 +422,7 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("moe_permute", &moe_permute);
   m.impl("moe_gather", &moe_gather);
   m.impl("sumsq_accumulate_", &sumsq_accumulate_);
+  m.impl("nvl_reduce_shard_", &nvl_reduce_shard_);
+  m.impl("nvl_adamw_shard_", &nvl_adamw_shard_);
   m.impl("scale_inplace_", &scale_inplace_);
 }

@@ -114,4 +114,14 @@ void sumsq_accumulate(const void* x, long long n, int dtype, float* out, cudaStr
 // x *= *scale (device scalar)
 void scale_inplace(void* x, long long n, int dtype, const float* scale, cudaStream_t stream);
 
+// ------------------------------------------------------------------ NVLink data-parallel optimizer -----------
+// peer_* : device array [world] of per-replica base pointers of the symmetric arena; mc_* : multicast (NVLS) mapping
+// of the same arena or nullptr.  [begin, end) is this rank's shard (multiples of 8 elements).
+void nvl_reduce_shard(const float* const* peer_grads, const float* mc_grad, float* own_grad, long long begin,
+                      long long end, int world, int rank, float* sumsq, cudaStream_t stream);
+void nvl_adamw_shard(void* const* peer_params, void* mc_param, void* own_param, const float* own_grad, void* exp_avg,
+                     void* exp_avg_sq, long long begin, long long end, int world, int rank, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float bias_corr1, float bias_corr2, uint64_t seed,
+                     const float* grad_scale, bool state_bf16, cudaStream_t stream);
+
 }  // namespace d9d

@@ -1,0 +1,93 @@
+"""Multi-GPU tests of the NVLink peer-memory kernels (need >= 2 GPUs; skipped otherwise)."""
+
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpus(n):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def _spawn(fn, world, *args):
+    import torch.multiprocessing as mp
+
+    port = 29600 + (os.getpid() % 300)
+    mp.spawn(_entry, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn, args):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.destroy_process_group()
+
+
+def _sharded_adamw_worker(rank, world, state_dtype, max_norm):
+    import torch.distributed as dist
+
+    from d9d_b200.optim.nvlink import NvlinkShardedAdamW
+
+    torch.manual_seed(0)  # identical parameters on every replica
+    shapes = [(300, 64), (1000,), (7, 24, 40), (129,)]
+    params = [torch.nn.Parameter(torch.randn(s, device="cuda").bfloat16()) for s in shapes]
+    ref_p = [p.detach().float().clone() for p in params]
+    opt = NvlinkShardedAdamW(params, dist.group.WORLD, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
+                             state_dtype=state_dtype, max_norm=max_norm, seed=5)
+    assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in params)
+    for p, r in zip(params, ref_p):
+        torch.testing.assert_close(p.detach().float(), r)  # moving into the arena kept the values
+
+    ref_m = [torch.zeros_like(r) for r in ref_p]
+    ref_v = [torch.zeros_like(r) for r in ref_p]
+    for step in range(1, 4):
+        all_grads = []
+        for r in range(world):
+            g = torch.Generator(device="cuda").manual_seed(100 * step + r)
+            all_grads.append([torch.randn(s, device="cuda", generator=g) for s in shapes])
+        for p, g in zip(params, all_grads[rank]):
+            p.grad.add_(g)  # what backward would accumulate on this replica
+        opt.grad_scale = torch.full((1,), 0.5, device="cuda")
+        opt.step()
+        # fp32 reference of: sum over replicas -> *0.5 -> clip -> AdamW
+        summed = [sum(all_grads[r][i] for r in range(world)) * 0.5 for i in range(len(shapes))]
+        if max_norm is not None:
+            norm = torch.sqrt(sum((g**2).sum() for g in summed))
+            torch.testing.assert_close(opt.last_grad_norm.reshape(()), norm, rtol=1e-4, atol=1e-4)
+            coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+            summed = [g * coef for g in summed]
+        for i, g in enumerate(summed):
+            ref_p[i] *= 1 - 1e-2 * 0.1
+            ref_m[i] = 0.9 * ref_m[i] + 0.1 * g
+            ref_v[i] = 0.95 * ref_v[i] + 0.05 * g * g
+            ref_p[i] -= 1e-2 * (ref_m[i] / (1 - 0.9**step)) / ((ref_v[i] / (1 - 0.95**step)).sqrt() + 1e-8)
+        for p, r in zip(params, ref_p):
+            diff = p.detach().float() - r
+            assert diff.abs().max() < 0.04, diff.abs().max()  # one bf16 ulp at |p| ~ 4 (stochastic rounding)
+            if r.numel() > 5000:
+                assert abs(float(diff.mean())) < 1.5e-3  # ... and unbiased
+            assert float(p.grad.abs().max()) == 0.0  # gradients were zeroed
+        # every replica holds bit-identical parameters
+        flat = torch.cat([p.detach().float().flatten() for p in params])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        for other in gathered:
+            assert torch.equal(other, gathered[0])
+        # keep the fp32 reference from drifting away from the bf16 trajectory
+        ref_p = [p.detach().float().clone() for p in params]
+
+
+@pytest.mark.parametrize("state_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("max_norm", [None, 1.0])
+def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm):
+    _need_gpus(2)
+    _spawn(_sharded_adamw_worker, 2, state_dtype, max_norm)
