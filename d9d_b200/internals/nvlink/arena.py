@@ -32,12 +32,6 @@ class SymmetricArena:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.group = group
-        enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
-        if enable is not None:
-            try:
-                enable(group.group_name)
-            except Exception:  # newer torch releases enable every group implicitly
-                pass
         self.buffer = symm_mem.empty(numel, dtype=dtype, device=device)
         self.handle = symm_mem.rendezvous(self.buffer, group.group_name)
         self.world_size: int = self.handle.world_size

@@ -54,30 +54,55 @@ __device__ __forceinline__ void st_peer_b32x4(void* p, uint4 v) {
                : "memory");
 }
 
-// own_grad[begin:end) = sum_r grad_r[begin:end); sumsq += sum of squares of the reduced values
+// own_grad[begin:end) = sum_r grad_r[begin:end); sumsq += sum of squares of the reduced values.
+// UNROLL independent 16-byte requests per thread are issued back to back: NVLink / NVSwitch round trips are several
+// microseconds, so throughput is set by the bytes in flight.
+template <int UNROLL>
 __global__ void __launch_bounds__(512) nvl_reduce_shard_kernel(const float* const* __restrict__ peer_grads,
                                                                const float* __restrict__ mc_grad,
                                                                float* __restrict__ own_grad, long long begin,
                                                                long long end, int world, int rank,
                                                                float* __restrict__ sumsq) {
   const long long n4 = (end - begin) >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   float acc = 0.f;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long e = begin + (i << 2);
-    float4 v;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UNROLL) {
+    float4 v[UNROLL];
     if (mc_grad != nullptr) {
-      v = multimem_ld_reduce_add_f32x4(mc_grad + e);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < n4) v[u] = multimem_ld_reduce_add_f32x4(mc_grad + begin + (i << 2));
+      }
     } else {
-      v = *reinterpret_cast<const float4*>(own_grad + e);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < n4) v[u] = *reinterpret_cast<const float4*>(own_grad + begin + (i << 2));
+      }
       for (int r = 1; r < world; ++r) {  // start at the next rank so that the peers are not all hit at once
-        const int peer = (rank + r) % world;
-        const float4 o = ld_peer_f32x4(peer_grads[peer] + e);
-        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        const float* peer = peer_grads[(rank + r) % world] + begin;
+        float4 o[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < n4) o[u] = ld_peer_f32x4(peer + (i << 2));
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < n4) { v[u].x += o[u].x; v[u].y += o[u].y; v[u].z += o[u].z; v[u].w += o[u].w; }
+        }
       }
     }
-    *reinterpret_cast<float4*>(own_grad + e) = v;
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        *reinterpret_cast<float4*>(own_grad + begin + (i << 2)) = v[u];
+        acc += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+      }
+    }
   }
   acc = warp_sum(acc);
   __shared__ float part[16];
@@ -191,11 +216,11 @@ void nvl_reduce_shard(const float* const* peer_grads, const float* mc_grad, floa
   if (end <= begin) return;
   if (((begin | end) & 7) != 0) throw std::runtime_error("d9d nvl_reduce_shard: shard bounds must be multiples of 8 elements");
   const long long n4 = (end - begin) >> 2;
-  long long blocks = (n4 + 511) / 512;
+  long long blocks = (n4 + 512 * 4 - 1) / (512 * 4);
   const long long cap = static_cast<long long>(sms()) * 4;
   if (blocks > cap) blocks = cap;
-  nvl_reduce_shard_kernel<<<static_cast<int>(blocks), 512, 0, stream>>>(peer_grads, mc_grad, own_grad, begin, end, world,
-                                                                        rank, sumsq);
+  nvl_reduce_shard_kernel<4><<<static_cast<int>(blocks), 512, 0, stream>>>(peer_grads, mc_grad, own_grad, begin, end,
+                                                                           world, rank, sumsq);
 }
 
 void nvl_adamw_shard(void* const* peer_params, void* mc_param, void* own_param, const float* own_grad, void* exp_avg,

@@ -88,6 +88,8 @@ def _sharded_adamw_worker(rank, world, state_dtype, max_norm):
 
 @pytest.mark.parametrize("state_dtype", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("max_norm", [None, 1.0])
-def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm):
+@pytest.mark.parametrize("multimem", ["0", "1"])
+def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm, multimem, monkeypatch):
     _need_gpus(2)
+    monkeypatch.setenv("D9D_NVLINK_MULTIMEM", multimem)  # peer loads/stores vs NVSwitch multicast
     _spawn(_sharded_adamw_worker, 2, state_dtype, max_norm)
