@@ -1,0 +1,149 @@
+"""HF <-> native mappers: round trip over every family / head / expert layout, and numerical parity with the
+transformers implementation where it is importable (CPU, fp32, tiny configs)."""
+
+import pytest
+import torch
+
+from d9d_b200.model_state.mapper import ModelStateMapper
+from d9d_b200.module.block.hidden_states_aggregator import HiddenStatesAggregationMode
+from d9d_b200.pipelining.api import PipelineStageInfo
+
+
+def _run(mapper: ModelStateMapper, state: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+    out = {}
+    used = set()
+    for group in mapper.state_dependency_groups():
+        assert group.inputs <= state.keys(), sorted(group.inputs - state.keys())[:3]
+        out.update(mapper.apply({k: state[k] for k in group.inputs}))
+        used |= group.inputs
+    assert used == set(state), sorted(set(state) - used)[:5]
+    return out
+
+
+VOCAB = dict(split_vocab_size={"text": 96}, split_vocab_order=["text"])
+
+
+def _moe_model(family):
+    if family == "qwen3_moe":
+        from d9d_b200.module.model.qwen3_moe import (Qwen3MoEForCausalLM as M, Qwen3MoEForCausalLMParameters as P,
+                                                     Qwen3MoELayerParameters as L, Qwen3MoEParameters as B)
+    else:
+        from d9d_b200.module.model.mixtral import (MixtralForCausalLM as M, MixtralForCausalLMParameters as P,
+                                                   MixtralLayerParameters as L, MixtralParameters as B)
+    p = P(model=B(layer=L(hidden_size=32, intermediate_size=16, num_experts=4, experts_top_k=2, num_attention_heads=4,
+                          num_key_value_heads=2, rms_norm_eps=1e-6, head_dim=8), num_hidden_layers=2, rope_base=10000,
+                  max_position_ids=64, **VOCAB))
+    m = M(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    m.reset_parameters()
+    return p, m
+
+
+@pytest.mark.parametrize("family", ["qwen3_moe", "mixtral"])
+@pytest.mark.parametrize("fmt", ["module_list", "fused"])
+def test_moe_round_trip(family, fmt):
+    import importlib
+
+    hfmod = importlib.import_module(f"d9d_b200.module.model.{family}.huggingface")
+    p, m = _moe_model(family)
+    native = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    to_hf = getattr(hfmod, f"mapper_to_huggingface_{family}_for_causal_lm")(p, fmt)
+    from_hf = getattr(hfmod, f"mapper_from_huggingface_{family}_for_causal_lm")(p, fmt)
+    hf_state = _run(to_hf, native)
+    assert "lm_head.weight" in hf_state and "model.embed_tokens.weight" in hf_state
+    if fmt == "module_list":
+        key = "model.layers.0.mlp.experts.3.down_proj.weight" if family == "qwen3_moe" else "model.layers.1.block_sparse_moe.experts.3.w2.weight"
+        assert hf_state[key].shape == (32, 16)  # HF nn.Linear layout [out, in]
+    else:
+        assert hf_state["model.layers.0.mlp.experts.gate_up_proj"].shape == (4, 32, 32)  # [E, 2I, H]
+        assert hf_state["model.layers.0.mlp.experts.down_proj"].shape == (4, 32, 16)  # [E, H, I]
+    back = _run(from_hf, hf_state)
+    assert back.keys() == native.keys()
+    for k in native:
+        torch.testing.assert_close(back[k], native[k], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("family", ["qwen3_dense", "llama3"])
+@pytest.mark.parametrize("head", ["causal_lm", "classification", "embedding"])
+def test_dense_round_trip(family, head):
+    import importlib
+
+    mod = importlib.import_module(f"d9d_b200.module.model.{family}")
+    hfmod = importlib.import_module(f"d9d_b200.module.model.{family}.huggingface")
+    cls = "Qwen3Dense" if family == "qwen3_dense" else "Llama3"
+    base = getattr(mod, f"{cls}Parameters")(layer=getattr(mod, f"{cls}LayerParameters")(
+        hidden_size=32, intermediate_size=48, num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-6, head_dim=8),
+        num_hidden_layers=2, rope_base=10000, max_position_ids=64, **VOCAB)
+    if head == "causal_lm":
+        p = getattr(mod, f"{cls}ForCausalLMParameters")(model=base)
+        m = getattr(mod, f"{cls}ForCausalLM")(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    elif head == "classification":
+        p = getattr(mod, f"{cls}ForClassificationParameters")(model=base, num_labels=3, classifier_dropout=0.0)
+        m = getattr(mod, f"{cls}ForClassification")(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.mean, False)
+    else:
+        p = getattr(mod, f"{cls}ForEmbeddingParameters")(model=base)
+        m = getattr(mod, f"{cls}ForEmbedding")(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.mean, False)
+    m.reset_parameters()
+    native = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    hf_state = _run(getattr(hfmod, f"mapper_to_huggingface_{family}_for_{head}")(p), native)
+    if head == "embedding":
+        assert "embed_tokens.weight" in hf_state  # bare backbone
+    back = _run(getattr(hfmod, f"mapper_from_huggingface_{family}_for_{head}")(p), hf_state)
+    assert back.keys() == native.keys()
+    for k in native:
+        torch.testing.assert_close(back[k], native[k], rtol=0, atol=0)
+
+
+def test_qwen3_dense_matches_transformers():
+    transformers = pytest.importorskip("transformers")
+    from d9d_b200.module.model.qwen3_dense import (Qwen3DenseForCausalLM, Qwen3DenseForCausalLMParameters,
+                                                   Qwen3DenseLayerParameters, Qwen3DenseParameters)
+    from d9d_b200.module.model.qwen3_dense.huggingface import mapper_from_huggingface_qwen3_dense_for_causal_lm
+
+    cfg = transformers.Qwen3Config(vocab_size=96, hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=2, head_dim=8, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=64,
+                                   tie_word_embeddings=False, attention_bias=False)
+    torch.manual_seed(0)
+    hf_model = transformers.Qwen3ForCausalLM(cfg).eval()
+    p = Qwen3DenseForCausalLMParameters(model=Qwen3DenseParameters(
+        layer=Qwen3DenseLayerParameters(hidden_size=32, intermediate_size=48, num_attention_heads=4, num_key_value_heads=2,
+                                        rms_norm_eps=1e-6, head_dim=8), num_hidden_layers=2, rope_base=10000, max_position_ids=64, **VOCAB))
+    ours = Qwen3DenseForCausalLM(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    ours.reset_parameters()
+    state = _run(mapper_from_huggingface_qwen3_dense_for_causal_lm(p), dict(hf_model.state_dict()))
+    missing, unexpected = ours.load_state_dict(state, strict=False)
+    assert not unexpected and all("rope" in k or "cos" in k or "sin" in k for k in missing), (missing, unexpected)
+    ids = torch.randint(0, 96, (2, 12))
+    labels = torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        logits = hf_model(input_ids=ids, position_ids=pos).logits.float()
+        want = torch.nn.functional.cross_entropy(logits.view(-1, 96), labels.view(-1), reduction="none").view(2, 12)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+
+def test_qwen3_moe_matches_transformers():
+    transformers = pytest.importorskip("transformers")
+    from d9d_b200.module.model.qwen3_moe.huggingface import mapper_from_huggingface_qwen3_moe_for_causal_lm
+
+    cfg = transformers.Qwen3MoeConfig(vocab_size=96, hidden_size=32, intermediate_size=48, moe_intermediate_size=16, num_hidden_layers=2,
+                                      num_attention_heads=4, num_key_value_heads=2, head_dim=8, rms_norm_eps=1e-6, rope_theta=10000.0,
+                                      max_position_embeddings=64, tie_word_embeddings=False, attention_bias=False, num_experts=4,
+                                      num_experts_per_tok=2, norm_topk_prob=True, decoder_sparse_step=1, mlp_only_layers=[],
+                                      router_aux_loss_coef=0.0, output_router_logits=False)
+    torch.manual_seed(0)
+    hf_model = transformers.Qwen3MoeForCausalLM(cfg).eval()
+    hf_state = dict(hf_model.state_dict())
+    fmt = "fused" if any(k.endswith("experts.gate_up_proj") for k in hf_state) else "module_list"
+    p, ours = _moe_model("qwen3_moe")
+    state = _run(mapper_from_huggingface_qwen3_moe_for_causal_lm(p, fmt), hf_state)
+    missing, unexpected = ours.load_state_dict(state, strict=False)
+    assert not unexpected and all("rope" in k or "cos" in k or "sin" in k or "tokens_per_expert" in k for k in missing), (missing, unexpected)
+    ids = torch.randint(0, 96, (2, 12))
+    labels = torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        logits = hf_model(input_ids=ids, position_ids=pos).logits.float()
+        want = torch.nn.functional.cross_entropy(logits.view(-1, 96), labels.view(-1), reduction="none").view(2, 12)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
