@@ -219,7 +219,8 @@ def main():
         e2e = {"value": tokens_per_step_per_gpu * world / (res["ms_per_step"] / 1e3), "unit": "tokens/s",
                "h2d_bytes_per_step": res["h2d_bytes_per_step"], "d2h_bytes_per_step": res["d2h_bytes_per_step"],
                "ms_per_step": res["ms_per_step"], "final_loss": res["final_loss"], "gpu_launches": res["launches"],
-               "api": "d9d_b200.loop.run.TrainingConfigurator(...).configure().train(); pinned-memory StatefulDataLoader"}
+               "api": "d9d_b200.loop.run.TrainingConfigurator(...).configure().train(); pinned-memory StatefulDataLoader; optimizer="
+                      + ("nvlink_sharded_adamw" if world > 1 and args.dp_impl == "nvlink" else "stochastic_adamw")}
     else:
         final_loss = float(loss)
 

@@ -154,7 +154,7 @@ class TrainerEndToEnd:
         from d9d_b200.core.dist_context import DeviceMeshParameters
         from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
         from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
-        from d9d_b200.loop.auto.auto_optimizer import StochasticAdamWOptimizerConfig
+        from d9d_b200.loop.auto.auto_optimizer import NvlinkShardedAdamWOptimizerConfig, StochasticAdamWOptimizerConfig
         from d9d_b200.loop.config import TrainerConfig
         from d9d_b200.loop.run import TrainingConfigurator
         from d9d_b200.recipes import (
@@ -177,7 +177,10 @@ class TrainerEndToEnd:
             model_provider=Qwen3MoEModelProvider(Qwen3MoEModelProviderConfig(model=model_params)),
             data_provider=SyntheticDataProvider(SyntheticDataConfig(
                 num_samples=global_batch * self.total_steps, seq_len=args.seq_len, vocab_size=vocab, seed=5)),
-            optimizer_provider=AutoOptimizerProvider(StochasticAdamWOptimizerConfig(lr=2.5e-4, state_dtype="bfloat16")),
+            optimizer_provider=AutoOptimizerProvider(
+                NvlinkShardedAdamWOptimizerConfig(lr=2.5e-4, state_dtype="bfloat16")
+                if world > 1 and getattr(args, "dp_impl", "nvlink") == "nvlink"
+                else StochasticAdamWOptimizerConfig(lr=2.5e-4, state_dtype="bfloat16")),
             lr_scheduler_provider=AutoLRSchedulerProvider(lr_cfg),
         ).configure()
 

@@ -7,6 +7,8 @@ from torch import nn
 from torch.distributed import DeviceMesh
 from torch.distributed.tensor import DTensor, Replicate, Shard
 
+from d9d_b200.kernel._native import EXTERNAL_GRAD_OWNER_ATTR
+
 from .bucket import AbstractGradientBucket, LocalGradientBucket, SyncGradientBucket, local_of
 
 _ARENA_ALIGN = 64  # elements; keeps every bucket / parameter slice 256-byte aligned for vectorised kernels
@@ -69,8 +71,8 @@ class GradientSynchronizer:
         classes: dict[_ArenaKey, list[nn.Parameter]] = {}
         for gi, group in enumerate(self._param_groups):
             for p in reversed(group):
-                if not p.requires_grad:
-                    continue
+                if not p.requires_grad or getattr(p, EXTERNAL_GRAD_OWNER_ATTR, None) is not None:
+                    continue  # frozen, or reduced by an optimizer that owns its gradients (optim/nvlink)
                 mesh = find_reduce_mesh(p.data) if isinstance(p.data, DTensor) else None
                 grad_dtype = p.grad_dtype or p.dtype
                 classes.setdefault(_ArenaKey(gi, mesh, p.device, grad_dtype), []).append(p)

@@ -72,6 +72,9 @@ def grad_dtype_of(t: torch.Tensor) -> torch.dtype:
 # ------------------------------------------------------------------------------------------------------------------
 MAIN_PARAM_ATTR = "_d9d_main_param"  # set on local views handed to modules: the (D)Tensor parameter that owns .grad
 FUSED_WGRAD_ATTR = "_d9d_fused_wgrad"  # set by the gradient infrastructure on parameters whose .grad is pre-allocated
+# set on parameters whose gradient reduction, scaling, clipping and zeroing belong to an optimizer that reduces over
+# NVLink itself (value: that optimizer); GradientSynchronizer / GradientManager / GradientClipper leave them alone
+EXTERNAL_GRAD_OWNER_ATTR = "_d9d_external_grad_owner"
 
 
 def fused_wgrad_owner(weight: torch.Tensor) -> torch.Tensor | None:

@@ -82,8 +82,34 @@ class SGDOptimizerConfig(BaseAutoOptimizerConfig):
                    nesterov=self.nesterov, maximize=self.maximize, fused=_fused_ok(params))
 
 
+class NvlinkShardedAdamWOptimizerConfig(BaseAutoOptimizerConfig):
+    """Stochastic-rounding AdamW whose data-parallel gradient reduction, update and parameter broadcast are NVLink
+    peer-memory kernels (``d9d_b200.optim.nvlink``).  Pure data-parallel-replicate jobs only."""
+
+    name: Literal["nvlink_sharded_adamw"] = "nvlink_sharded_adamw"
+    lr: float
+    betas: tuple[float, float] = (0.9, 0.999)
+    eps: float = 1e-8
+    weight_decay: float = 1e-2
+    state_dtype: str = "bfloat16"
+
+    def build(self, params: Iterable[nn.Parameter]) -> Optimizer:
+        raise ValueError("nvlink_sharded_adamw needs the distributed context: use AutoOptimizerProvider")
+
+    def build_distributed(self, params: Iterable[nn.Parameter], context: InitializeOptimizerStageContext) -> Optimizer:
+        import torch.distributed as dist
+
+        from d9d_b200.optim.nvlink import NvlinkShardedAdamW
+
+        mesh = context.dist_context.mesh_params
+        if mesh.world_size != mesh.data_parallel_replicate or mesh.has_expert_parallel or not mesh.is_distributed:
+            raise ValueError("nvlink_sharded_adamw supports pure data-parallel-replicate meshes (dp_replicate == world size > 1)")
+        return NvlinkShardedAdamW(params, dist.group.WORLD, lr=self.lr, betas=self.betas, eps=self.eps,
+                                  weight_decay=self.weight_decay, state_dtype=getattr(torch, self.state_dtype))
+
+
 AutoOptimizerConfig = Annotated[
-    StochasticAdamWOptimizerConfig | AdamWOptimizerConfig | AdamOptimizerConfig | SGDOptimizerConfig,
+    StochasticAdamWOptimizerConfig | AdamWOptimizerConfig | AdamOptimizerConfig | SGDOptimizerConfig | NvlinkShardedAdamWOptimizerConfig,
     Field(discriminator="name"),
 ]
 
@@ -93,4 +119,7 @@ class AutoOptimizerProvider(OptimizerProvider):
         self._config = config
 
     def __call__(self, context: InitializeOptimizerStageContext) -> Optimizer:
-        return self._config.build(p for p in context.model.parameters() if p.requires_grad)
+        params = (p for p in context.model.parameters() if p.requires_grad)
+        if isinstance(self._config, NvlinkShardedAdamWOptimizerConfig):
+            return self._config.build_distributed(params, context)
+        return self._config.build(params)

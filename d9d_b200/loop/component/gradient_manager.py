@@ -8,6 +8,7 @@ from torch.distributed.tensor import DTensor
 
 from d9d_b200.core.dist_context import DistributedContext
 from d9d_b200.internals.grad_sync import GradientSynchronizer
+from d9d_b200.kernel._native import EXTERNAL_GRAD_OWNER_ATTR
 from d9d_b200.loop.config import GradientManagerConfig
 from d9d_b200.metric.impl.aggregation import WeightedMeanMetric
 
@@ -36,6 +37,7 @@ class GradientManager:
                                           bucket_size_mb=config.bucket_size_mb,
                                           require_accumulations=batch_maths.num_backward_calls)
         self._installed = False
+        self._external_owners: list = []
 
     def _apply_grad_dtype(self) -> None:
         if self._config.grad_dtype is None:
@@ -55,6 +57,13 @@ class GradientManager:
         """Set gradient dtypes, allocate the arenas / hooks; torn down on exit."""
         self._apply_grad_dtype()
         self._sync.bind()
+        owners = {}
+        for module in self._modules.modules:
+            for p in module.parameters():
+                owner = getattr(p, EXTERNAL_GRAD_OWNER_ATTR, None)
+                if owner is not None:
+                    owners[id(owner)] = owner
+        self._external_owners = list(owners.values())  # optimizers that reduce / scale / zero their gradients themselves
         self._installed = True
         try:
             yield
@@ -72,7 +81,7 @@ class GradientManager:
         grads = []
         for module in self._modules.modules:
             for p in module.parameters():
-                if p.grad is not None:
+                if p.grad is not None and getattr(p, EXTERNAL_GRAD_OWNER_ATTR, None) is None:
                     grads.append(p.grad.to_local() if isinstance(p.grad, DTensor) else p.grad)
         return grads
 
@@ -83,9 +92,11 @@ class GradientManager:
         if self._ctx.mesh_params.is_distributed:
             self._loss.sync(self._ctx)
         grads = self._local_grads()
+        inv = 1.0 / self._loss.accumulated_weight
         if grads:
-            inv = 1.0 / self._loss.accumulated_weight
             torch._foreach_mul_(grads, inv)  # noqa: SLF001  tensor scalar: no host sync
+        for owner in self._external_owners:
+            owner.set_grad_scale(inv)  # applied inside the NVLink update kernel after the cross-replica reduction
 
     def compute_global_loss(self) -> torch.Tensor:
         return self._loss.compute()

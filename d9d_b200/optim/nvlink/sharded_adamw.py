@@ -10,7 +10,7 @@ from torch import nn
 from torch.distributed.tensor import DTensor
 
 from d9d_b200.internals.nvlink import SymmetricArena
-from d9d_b200.kernel._native import FUSED_WGRAD_ATTR, native_ops
+from d9d_b200.kernel._native import EXTERNAL_GRAD_OWNER_ATTR, FUSED_WGRAD_ATTR, native_ops
 
 _ALIGN = 8  # elements: 16-byte vectors of bf16 parameters / 32-byte pairs of fp32 gradient vectors
 
@@ -85,6 +85,7 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
                     p.data = view
                     p.grad = gview
                 setattr(p, FUSED_WGRAD_ATTR, True)
+                setattr(p, EXTERNAL_GRAD_OWNER_ATTR, self)
         self.exp_avg = torch.zeros(self._shard, dtype=state_dtype, device=device)
         self.exp_avg_sq = torch.zeros(self._shard, dtype=state_dtype, device=device)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=device)
@@ -107,6 +108,22 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         if override is not None:
             return available and override == "1"
         return available and self._world >= 4
+
+    state_is_materialized = True  # nothing is created lazily: checkpoint loading needs no warm-up step
+
+    @property
+    def max_norm(self) -> float | None:
+        return self._max_norm
+
+    @max_norm.setter
+    def max_norm(self, value: float | None) -> None:
+        self._max_norm = value
+
+    def set_grad_scale(self, scale: torch.Tensor) -> None:
+        """Device scalar multiplied into every (reduced) gradient inside the update kernel, e.g. ``1/sum(weights)``."""
+        if self.grad_scale is None:
+            self.grad_scale = torch.ones(1, dtype=torch.float32, device=self._sumsq.device)
+        self.grad_scale.copy_(scale.reshape(-1)[:1])
 
     @torch.no_grad()
     def step(self, closure: Any = None) -> None:  # type: ignore[override]

@@ -24,7 +24,7 @@ def ensure_optimizer_state_initialized(optimizer: Any) -> None:
     import torch
 
     groups = getattr(optimizer, "param_groups", None)
-    if groups is None:
+    if groups is None or getattr(optimizer, "state_is_materialized", False):
         return
     params = [p for g in groups for p in g["params"] if p.requires_grad]
     if not params or all(len(optimizer.state.get(p, {})) > 0 for p in params):

@@ -86,10 +86,68 @@ def _sharded_adamw_worker(rank, world, state_dtype, max_norm):
         ref_p = [p.detach().float().clone() for p in params]
 
 
-@pytest.mark.parametrize("state_dtype", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("max_norm", [None, 1.0])
-@pytest.mark.parametrize("multimem", ["0", "1"])
+@pytest.mark.parametrize("state_dtype,max_norm,multimem", [(torch.bfloat16, 1.0, "0"), (torch.bfloat16, None, "1"),
+                                                           (torch.float32, 1.0, "1"), (torch.float32, None, "0")])
 def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm, multimem, monkeypatch):
     _need_gpus(2)
     monkeypatch.setenv("D9D_NVLINK_MULTIMEM", multimem)  # peer loads/stores vs NVSwitch multicast
     _spawn(_sharded_adamw_worker, 2, state_dtype, max_norm)
+
+
+def _trainer_worker(rank, world, optimizer_name, tmp):
+    from pathlib import Path
+
+    import torch.distributed as dist
+
+    from d9d_b200.core.dist_context import DeviceMeshParameters
+    from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
+    from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
+    from d9d_b200.loop.auto.auto_optimizer import NvlinkShardedAdamWOptimizerConfig, StochasticAdamWOptimizerConfig
+    from d9d_b200.loop.run import TrainingConfigurator
+    from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLMParameters, Qwen3MoELayerParameters, Qwen3MoEParameters
+    from d9d_b200.recipes import (CausalLMTask, Qwen3MoEModelProvider, Qwen3MoEModelProviderConfig, SyntheticDataConfig,
+                                  SyntheticDataProvider)
+    from tests.helpers_train import trainer_config
+
+    params = Qwen3MoEForCausalLMParameters(model=Qwen3MoEParameters(
+        layer=Qwen3MoELayerParameters(hidden_size=256, intermediate_size=192, num_experts=8, experts_top_k=2, num_attention_heads=4,
+                                      num_key_value_heads=2, rms_norm_eps=1e-6, head_dim=64),
+        num_hidden_layers=2, rope_base=10000, max_position_ids=256, split_vocab_size={"regular": 1000, "special": 24},
+        split_vocab_order=["regular", "special"]))
+    opt_cfg = (NvlinkShardedAdamWOptimizerConfig(lr=3e-3, weight_decay=0.0) if optimizer_name == "nvlink"
+               else StochasticAdamWOptimizerConfig(lr=3e-3, weight_decay=0.0, state_dtype="bfloat16"))
+    lr_cfg = PiecewiseConfig.model_validate({"name": "piecewise", "scheduler": {"initial_multiplier": 1.0, "phases": [
+        {"mode": "rest", "target_multiplier": 1.0, "curve": {"type": "linear"}}]}})
+    trainer = TrainingConfigurator(
+        mesh=DeviceMeshParameters(data_parallel_replicate=world),
+        parameters=trainer_config(Path(tmp) / f"r{rank}", total_batch=16, micro=4),
+        task_provider=lambda ctx: CausalLMTask(),
+        model_provider=Qwen3MoEModelProvider(Qwen3MoEModelProviderConfig(model=params)),
+        data_provider=SyntheticDataProvider(SyntheticDataConfig(num_samples=16 * 12, seq_len=128, vocab_size=1024, seed=1, learnable=True)),
+        optimizer_provider=AutoOptimizerProvider(opt_cfg),
+        lr_scheduler_provider=AutoLRSchedulerProvider(lr_cfg),
+    ).configure()
+    losses = []
+    from d9d_b200.loop.event.catalogue.train import EVENT_TRAIN_STEP_POST
+
+    state = trainer.state
+    state.event_bus.subscribe(EVENT_TRAIN_STEP_POST, lambda ctx: losses.append(state.gradient_manager.compute_global_loss().item()))
+    trainer.train()
+    assert len(losses) == 12 and losses[-1] < losses[0] - 0.5, losses
+    flat = torch.cat([(p._local_tensor if hasattr(p, "_local_tensor") else p.data).float().flatten()
+                      for m in state.tracked_modules.modules for p in m.parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)  # replicas stayed bit-identical
+    if rank == 0:
+        torch.save(torch.tensor(losses), Path(tmp) / f"losses_{optimizer_name}.pt")
+
+
+def test_trainer_with_nvlink_optimizer_tracks_nccl_path(tmp_path):
+    _need_gpus(2)
+    for name in ("nvlink", "nccl"):
+        _spawn(_trainer_worker, 2, name, str(tmp_path))
+    a = torch.load(tmp_path / "losses_nvlink.pt")
+    b = torch.load(tmp_path / "losses_nccl.pt")
+    assert abs(float(a[0] - b[0])) < 1e-3  # same data, same init
+    assert float((a - b).abs().max()) < 0.25, (a, b)  # same trajectory up to stochastic-rounding noise
