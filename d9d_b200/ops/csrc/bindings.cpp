@@ -337,6 +337,74 @@ void scale_inplace_(Tensor x, const Tensor& scale) {
 
 }  // namespace
 
+// ------------------------------------------------------------------ tensor-parallel GEMMs with fused communication
+// peer pointer lists come from torch.distributed._symmetric_memory (handle.buffer_ptrs) plus a byte offset.
+static std::vector<const void*> to_ptrs(at::IntArrayRef v) {
+  std::vector<const void*> out;
+  out.reserve(v.size());
+  for (int64_t p : v) out.push_back(reinterpret_cast<const void*>(p));
+  return out;
+}
+
+// d[M,N] = all_gather(a_shards)[M,K] · B ; every peer holds a_shard[rows_local, K] (bf16, leading dim lda)
+void gemm_ag_a(at::IntArrayRef a_peer_ptrs, int64_t rows_local, int64_t lda, int64_t block_rows, const Tensor& b, Tensor d,
+               bool b_mn) {
+  TORCH_CHECK(b.is_cuda() && d.is_cuda() && b.dim() == 2 && d.dim() == 2 && b.stride(1) == 1 && d.stride(1) == 1);
+  TORCH_CHECK(b.scalar_type() == at::kBFloat16 && d.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(d.device());
+  auto ptrs = to_ptrs(a_peer_ptrs);
+  d9d::GemmArgs g;
+  g.mode = 0; g.a_mn = false; g.b_mn = b_mn; g.epi = 0;
+  g.M = static_cast<int>(d.size(0)); g.N = static_cast<int>(d.size(1));
+  g.K = static_cast<int>(b_mn ? b.size(0) : b.size(1));
+  TORCH_CHECK((b_mn ? b.size(1) : b.size(0)) == g.N, "gemm_ag_a: N mismatch");
+  TORCH_CHECK(rows_local * static_cast<int64_t>(ptrs.size()) == g.M, "gemm_ag_a: shards do not add up to M");
+  g.B = b.data_ptr(); g.D = d.data_ptr(); g.ldb = b.stride(0); g.ldd = d.stride(0);
+  g.comm = 1; g.comm_world = static_cast<int>(ptrs.size()); g.comm_block_rows = static_cast<int>(block_rows);
+  g.comm_peer_ptrs = ptrs.data(); g.comm_rows_local = rows_local; g.comm_ld = lda;
+  d9d::gemm_comm(g, cur_stream());
+}
+
+// d_shards[owner][rows_local, N] += (a[M,K] · B) rows owned by `owner` (bf16 reduce-add over NVLink)
+void gemm_rs_d(const Tensor& a, const Tensor& b, at::IntArrayRef d_peer_ptrs, int64_t rows_local, int64_t ldd, int64_t block_rows,
+               bool b_mn) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(a.device());
+  auto ptrs = to_ptrs(d_peer_ptrs);
+  d9d::GemmArgs g;
+  g.mode = 0; g.a_mn = false; g.b_mn = b_mn; g.epi = 3;
+  g.M = static_cast<int>(a.size(0)); g.K = static_cast<int>(a.size(1));
+  g.N = static_cast<int>(b_mn ? b.size(1) : b.size(0));
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == g.K, "gemm_rs_d: K mismatch");
+  TORCH_CHECK(rows_local * static_cast<int64_t>(ptrs.size()) == g.M, "gemm_rs_d: shards do not add up to M");
+  g.A = a.data_ptr(); g.B = b.data_ptr(); g.lda = a.stride(0); g.ldb = b.stride(0);
+  g.comm = 2; g.comm_world = static_cast<int>(ptrs.size()); g.comm_block_rows = static_cast<int>(block_rows);
+  g.comm_peer_ptrs = ptrs.data(); g.comm_rows_local = rows_local; g.comm_ld = ldd;
+  d9d::gemm_comm(g, cur_stream());
+}
+
+// d[M,N] (+)= A^T · B over the token dim where one operand ([tokens, M] or [tokens, N], MN-major) is sharded by tokens
+void gemm_ag_k(const Tensor& local, at::IntArrayRef peer_ptrs, bool peer_is_a, int64_t rows_local, int64_t peer_ld,
+               int64_t block_rows, Tensor d, bool accumulate) {
+  TORCH_CHECK(local.is_cuda() && d.is_cuda() && local.dim() == 2 && d.dim() == 2 && local.stride(1) == 1 && d.stride(1) == 1);
+  TORCH_CHECK(local.scalar_type() == at::kBFloat16);
+  c10::cuda::CUDAGuard guard(d.device());
+  auto ptrs = to_ptrs(peer_ptrs);
+  d9d::GemmArgs g;
+  g.mode = 0; g.a_mn = true; g.b_mn = true;
+  g.M = static_cast<int>(d.size(0)); g.N = static_cast<int>(d.size(1)); g.K = static_cast<int>(local.size(0));
+  TORCH_CHECK(rows_local * static_cast<int64_t>(ptrs.size()) == g.K, "gemm_ag_k: shards do not add up to the token dim");
+  TORCH_CHECK(local.size(1) == (peer_is_a ? g.N : g.M), "gemm_ag_k: local operand width mismatch");
+  if (peer_is_a) { g.B = local.data_ptr(); g.ldb = local.stride(0); }
+  else { g.A = local.data_ptr(); g.lda = local.stride(0); }
+  g.D = d.data_ptr(); g.ldd = d.stride(0);
+  g.epi = epi_for(d, accumulate);
+  g.comm = peer_is_a ? 3 : 4; g.comm_world = static_cast<int>(ptrs.size()); g.comm_block_rows = static_cast<int>(block_rows);
+  g.comm_peer_ptrs = ptrs.data(); g.comm_rows_local = rows_local; g.comm_ld = peer_ld;
+  d9d::gemm_comm(g, cur_stream());
+}
+
 // ------------------------------------------------------------------ NVLink data-parallel optimizer -----------
 // `peer_ptrs_dev` / `multicast_ptr` come from torch.distributed._symmetric_memory (buffer_ptrs_dev, multicast_ptr).
 void nvl_reduce_shard_(Tensor own_grad, int64_t peer_ptrs_dev, int64_t multicast_ptr, int64_t begin, int64_t end,
@@ -395,6 +463,10 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_permute(Tensor x, Tensor? probs, Tensor row_map, Tensor counts, Tensor seg_offsets, int capacity) -> (Tensor, Tensor)");
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
+  m.def("gemm_ag_a(int[] a_peer_ptrs, int rows_local, int lda, int block_rows, Tensor b, Tensor(a!) d, bool b_mn) -> ()");
+  m.def("gemm_rs_d(Tensor a, Tensor b, int[] d_peer_ptrs, int rows_local, int ldd, int block_rows, bool b_mn) -> ()");
+  m.def("gemm_ag_k(Tensor local, int[] peer_ptrs, bool peer_is_a, int rows_local, int peer_ld, int block_rows, Tensor(a!) d, "
+        "bool accumulate) -> ()");
   m.def("nvl_reduce_shard_(Tensor(a!) own_grad, int peer_ptrs_dev, int multicast_ptr, int begin, int end, int world, int rank, "
         "Tensor(b!) sumsq) -> ()");
   m.def("nvl_adamw_shard_(Tensor(a!) own_param, Tensor own_grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, int peer_ptrs_dev, "
@@ -422,6 +494,9 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("moe_permute", &moe_permute);
   m.impl("moe_gather", &moe_gather);
   m.impl("sumsq_accumulate_", &sumsq_accumulate_);
+  m.impl("gemm_ag_a", &gemm_ag_a);
+  m.impl("gemm_rs_d", &gemm_rs_d);
+  m.impl("gemm_ag_k", &gemm_ag_k);
   m.impl("nvl_reduce_shard_", &nvl_reduce_shard_);
   m.impl("nvl_adamw_shard_", &nvl_adamw_shard_);
   m.impl("scale_inplace_", &scale_inplace_);

@@ -26,6 +26,13 @@ struct GemmArgs {
   const int* group_offsets = nullptr;  // GROUPED_K
   int block_n = 0;                     // 0 => heuristic
   int k_splits = 0;                    // dense fp32-accumulate epilogue only: 0 => heuristic, 1 => off
+  // fused tensor-parallel communication (gemm::Comm); the sharded operand / output is described by its peers
+  int comm = 0;
+  int comm_world = 1;
+  int comm_block_rows = 0;                     // rows per (rank, block) of the sharded dim
+  const void* const* comm_peer_ptrs = nullptr; // host array [comm_world]: base pointer of every peer's shard
+  long long comm_rows_local = 0;               // rows of one shard
+  long long comm_ld = 0;                       // leading dim (elements) of the shards
   // fused linear cross entropy
   const long long* ce_target = nullptr;
   const float* ce_lse = nullptr;
@@ -39,6 +46,7 @@ struct GemmArgs {
 void gemm_dense(const GemmArgs& a, cudaStream_t stream);
 void gemm_grouped(const GemmArgs& a, cudaStream_t stream);
 void gemm_ce(const GemmArgs& a, cudaStream_t stream);
+void gemm_comm(const GemmArgs& a, cudaStream_t stream);  // dense GEMM with a.comm != 0 (gemm_comm_*.cu)
 int gemm_ce_block_n();
 // (part_max, part_sum)[n_tiles, M] + tgt_logit[M] -> lse[M], nll[M] (0 where target == ignore_index)
 void ce_finalize(const float* part_max, const float* part_sum, const float* tgt_logit, const long long* target,

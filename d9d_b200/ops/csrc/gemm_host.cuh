@@ -73,10 +73,10 @@ inline int sm_count() {
   return n;
 }
 
-template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI, int COMM = COMM_NONE>
 void launch_one(const GemmArgs& a, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
-  auto kern = gemm_kernel<MODE, BLOCK_N, A_MN, B_MN, EPI>;
+  auto kern = gemm_kernel<MODE, BLOCK_N, A_MN, B_MN, EPI, COMM>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -84,20 +84,48 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   }
   // ---- tensor maps ----
   CUtensorMap ta, tb;
+  typename PeerArg<COMM>::type peers{};
+  if constexpr (COMM != COMM_NONE) {
+    if (a.comm_world < 1 || a.comm_world > MAX_PEERS || a.comm_peer_ptrs == nullptr)
+      throw std::runtime_error("d9d gemm: fused communication needs 1..8 peer pointers");
+    const int unit = (COMM == COMM_AG_A) ? BLOCK_M : (COMM == COMM_RS_D ? 32 : BLOCK_K);
+    if (a.comm_block_rows <= 0 || a.comm_block_rows % unit != 0)
+      throw std::runtime_error("d9d gemm: the per-rank block of the sharded dim must be a multiple of the tile size");
+    for (int r = 0; r < a.comm_world; ++r) {
+      const void* base = a.comm_peer_ptrs[r];
+      const uint64_t rows = a.comm_rows_local, ld = a.comm_ld;
+      if constexpr (COMM == COMM_AG_A) peers.m[r] = make_tmap_bf16_3d(base, a.K, rows, 1, ld, ld * rows, 64, BLOCK_M);
+      else if constexpr (COMM == COMM_AG_KA) peers.m[r] = make_tmap_bf16_3d(base, a.M, rows, 1, ld, ld * rows, 64, BLOCK_K);
+      else if constexpr (COMM == COMM_AG_KB) peers.m[r] = make_tmap_bf16_3d(base, a.N, rows, 1, ld, ld * rows, 64, BLOCK_K);
+      else if (!make_tmap_out(&peers.m[r], const_cast<void*>(base), EPI == EPI_BF16_ACC, a.N, rows, 1, ld, 0))
+        throw std::runtime_error("d9d gemm: reduce-scatter output shards must be 16-byte aligned");
+    }
+  }
+  constexpr bool A_FROM_PEERS = (COMM == COMM_AG_A || COMM == COMM_AG_KA);
+  constexpr bool B_FROM_PEERS = (COMM == COMM_AG_KB);
   if (MODE == GROUPED_K) {
     // A: [R, M] (M contiguous), B: [R, N] (N contiguous); reduction over grouped rows
     ta = make_tmap_bf16_3d(a.A, a.M, a.k_total, 1, a.lda, a.lda * a.k_total, 64, BLOCK_K);
     tb = make_tmap_bf16_3d(a.B, a.N, a.k_total, 1, a.ldb, a.ldb * a.k_total, 64, BLOCK_K);
   } else {
-    if (!A_MN) ta = make_tmap_bf16_3d(a.A, a.K, a.M, 1, a.lda, a.lda * a.M, 64, BLOCK_M);
-    else       ta = make_tmap_bf16_3d(a.A, a.M, a.K, 1, a.lda, a.lda * a.K, 64, BLOCK_K);
     const uint64_t g = (MODE == GROUPED_M) ? a.num_groups : 1;
-    if (!B_MN) tb = make_tmap_bf16_3d(a.B, a.K, a.N, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.N, 64, BLOCK_N);
-    else       tb = make_tmap_bf16_3d(a.B, a.N, a.K, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.K, 64, BLOCK_K);
+    if (!B_FROM_PEERS) {
+      if (!B_MN) tb = make_tmap_bf16_3d(a.B, a.K, a.N, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.N, 64, BLOCK_N);
+      else       tb = make_tmap_bf16_3d(a.B, a.N, a.K, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.K, 64, BLOCK_K);
+    }
+    if (!A_FROM_PEERS) {
+      if (!A_MN) ta = make_tmap_bf16_3d(a.A, a.K, a.M, 1, a.lda, a.lda * a.M, 64, BLOCK_M);
+      else       ta = make_tmap_bf16_3d(a.A, a.M, a.K, 1, a.lda, a.lda * a.K, 64, BLOCK_K);
+    } else {
+      ta = tb;  // placeholder: the kernel loads A through the peer maps
+    }
+    if (B_FROM_PEERS) tb = ta;
   }
   Params p{};
   CUtensorMap td = ta;  // placeholder when the direct-store epilogue is used
-  if (EPI != EPI_CE_LSE) {
+  if (COMM == COMM_RS_D) {
+    p.tma_epilogue = 1;  // output tiles are reduce-added through the peer maps
+  } else if (EPI != EPI_CE_LSE) {
     constexpr bool out_bf16 = (EPI == EPI_BF16 || EPI == EPI_BF16_ACC || EPI == EPI_CE_DLOGITS);
     const uint64_t groups = (MODE == GROUPED_K) ? a.num_groups : 1;
     p.tma_epilogue = make_tmap_out(&td, a.D, out_bf16, a.N, a.M, groups, a.ldd, a.d_group_stride) ? 1 : 0;
@@ -114,6 +142,7 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
     p.k_splits = static_cast<int>(splits);
   }
   p.M = a.M; p.N = a.N; p.K = a.K; p.num_groups = a.num_groups;
+  p.comm_world = a.comm_world; p.comm_block_rows = a.comm_block_rows;
   p.D = a.D; p.ldd = a.ldd; p.d_group_stride = a.d_group_stride;
   p.tile_group = a.tile_group; p.group_offsets = a.group_offsets;
   p.ce_target = a.ce_target; p.ce_lse = a.ce_lse; p.ce_grad = a.ce_grad;
@@ -124,7 +153,7 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   long long tiles = m_tiles * n_tiles * (MODE == GROUPED_K ? a.num_groups : 1) * p.k_splits;
   if (tiles <= 0) return;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, td, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, td, p, peers);
 }
 
 // pick BLOCK_N minimising (waves x tile cost); ties go to the wider tile

@@ -40,11 +40,30 @@ enum Epi : int {
   EPI_CE_DLOGITS = 5  // fused linear-CE backward: D(bf16) = g[row] * (exp(acc - lse[row]) - [col == target[row]])
 };
 
+// Tensor-parallel communication fused into the GEMM (operands / outputs living in NVLink peer memory):
+//   COMM_AG_A   A's rows (the M dim) are sharded over the peers: every m-tile is TMA-loaded straight from the owner's
+//               shard                                   => all-gather -> GEMM without a gathered copy of A
+//   COMM_RS_D   every output tile is TMA reduce-added into the shard of the peer that owns those rows
+//                                                        => GEMM -> reduce-scatter without a partial-sum buffer
+//   COMM_AG_KA / COMM_AG_KB   A / B (MN-major) is sharded along the *reduction* dim (wgrad of a sequence-parallel
+//               layer): every k-block is loaded from the owner's shard
+// Row index -> (owner, local row):  blk = idx / comm_block_rows; owner = blk % comm_world;
+//                                   local = (blk / comm_world) * comm_block_rows + idx % comm_block_rows
+// (covers both "tokens sharded as one contiguous block per rank" and "[batch, seq/W] per rank, batch-major").
+enum Comm : int { COMM_NONE = 0, COMM_AG_A = 1, COMM_RS_D = 2, COMM_AG_KA = 3, COMM_AG_KB = 4 };
+constexpr int MAX_PEERS = 8;
+struct PeerMaps { CUtensorMap m[MAX_PEERS]; };
+struct NoPeerMaps {};
+template <int COMM> struct PeerArg { using type = PeerMaps; };
+template <> struct PeerArg<COMM_NONE> { using type = NoPeerMaps; };
+
 struct Params {
   int M, N, K;            // DENSE: problem dims. GROUPED_M: M = padded row capacity. GROUPED_K: M,N = per-expert out dims
   int num_groups;         // experts (1 for dense)
   int k_splits;           // DENSE + accumulate epilogue: K is cut into this many slices (1 => off)
   int tma_epilogue;       // 1: output through the tmap_d TMA store/reduce path, 0: direct global stores
+  int comm_world;         // COMM_*: number of peers
+  int comm_block_rows;    // COMM_*: rows per (rank, block) of the sharded dim
   void* D;                // output
   long long ldd;          // leading dim of D (elements)
   long long d_group_stride;  // GROUPED_K: elements between per-expert outputs
@@ -142,10 +161,22 @@ __device__ __forceinline__ TileCoord get_tile(const Params& p, int tile) {
   return t;
 }
 
-template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+__device__ __forceinline__ void comm_locate(const Params& p, int idx, int& owner, int& local) {
+  const int blk = idx / p.comm_block_rows;
+  owner = blk % p.comm_world;
+  local = (blk / p.comm_world) * p.comm_block_rows + (idx - blk * p.comm_block_rows);
+}
+
+template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI, int COMM = COMM_NONE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const __grid_constant__ CUtensorMap tmap_d, const Params p) {
+            const __grid_constant__ CUtensorMap tmap_d, const Params p,
+            const __grid_constant__ typename PeerArg<COMM>::type peers) {
+  static_assert(COMM == COMM_NONE || MODE == DENSE, "fused communication is implemented for dense GEMMs");
+  static_assert(COMM != COMM_AG_A || !A_MN, "COMM_AG_A gathers a K-major A");
+  static_assert(COMM != COMM_AG_KA || A_MN, "COMM_AG_KA gathers an MN-major A along K");
+  static_assert(COMM != COMM_AG_KB || B_MN, "COMM_AG_KB gathers an MN-major B along K");
+  static_assert(COMM != COMM_RS_D || EPI == EPI_F32_ACC || EPI == EPI_BF16_ACC, "COMM_RS_D needs a reduce-add epilogue");
   using C = Cfg<BLOCK_N>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -167,6 +198,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (p.tma_epilogue) tma_prefetch_desc(&tmap_d);
+    if constexpr (COMM != COMM_NONE)
+      for (int r = 0; r < p.comm_world; ++r) tma_prefetch_desc(&peers.m[r]);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -198,7 +231,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           const int k_idx = t.k_begin + kb * BLOCK_K;
           uint8_t* sa = smem_a + stage * C::A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
-          if (!A_MN) {
+          if constexpr (COMM == COMM_AG_A) {  // the m-tile lives in its owner's shard: load it over NVLink
+            int owner, m_local;
+            comm_locate(p, m_idx, owner, m_local);
+            tma_load_3d(sa, &peers.m[owner], &full_bar[stage], k_idx, m_local, 0);
+          } else if constexpr (COMM == COMM_AG_KA) {
+            int owner, k_local;
+            comm_locate(p, k_idx, owner, k_local);
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_3d(sa + j * (BLOCK_K * 128), &peers.m[owner], &full_bar[stage], m_idx + j * 64, k_local, 0);
+          } else if (!A_MN) {
             tma_load_3d(sa, &tmap_a, &full_bar[stage], k_idx, m_idx, 0);
           } else {
 #pragma unroll
@@ -206,7 +249,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               tma_load_3d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_idx + j * 64, k_idx, 0);
           }
           const int bg = (MODE == GROUPED_M) ? t.group : 0;
-          if (!B_MN) {
+          if constexpr (COMM == COMM_AG_KB) {
+            int owner, k_local;
+            comm_locate(p, k_idx, owner, k_local);
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(sb + j * (BLOCK_K * 128), &peers.m[owner], &full_bar[stage], n_idx + j * 64, k_local, 0);
+          } else if (!B_MN) {
             tma_load_3d(sb, &tmap_b, &full_bar[stage], k_idx, n_idx, bg);
           } else {
 #pragma unroll
@@ -375,7 +424,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             if (lane == 0) {
               const int r0 = t.m_blk * BLOCK_M + quad * 32;
               const int g0 = (MODE == GROUPED_K) ? t.group : 0;
-              if constexpr (REDUCE) tma_reduce_add_3d(&tmap_d, stage_buf, cbase, r0, g0);
+              if constexpr (COMM == COMM_RS_D) {  // reduce-add into the shard of the peer that owns these rows
+                int owner, r_local;
+                comm_locate(p, r0, owner, r_local);
+                tma_reduce_add_3d(&peers.m[owner], stage_buf, cbase, r_local, 0);
+              } else if constexpr (REDUCE) tma_reduce_add_3d(&tmap_d, stage_buf, cbase, r0, g0);
               else tma_store_3d(&tmap_d, stage_buf, cbase, r0, g0);
               tma_store_commit();
             }

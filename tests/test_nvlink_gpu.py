@@ -151,3 +151,71 @@ def test_trainer_with_nvlink_optimizer_tracks_nccl_path(tmp_path):
     b = torch.load(tmp_path / "losses_nccl.pt")
     assert abs(float(a[0] - b[0])) < 1e-3  # same data, same init
     assert float((a - b).abs().max()) < 0.25, (a, b)  # same trajectory up to stochastic-rounding noise
+
+
+def _tp_gemm_worker(rank, world):
+    import torch.distributed as dist
+
+    from d9d_b200.internals.nvlink import SymmetricArena
+    from d9d_b200.kernel._native import native_ops
+
+    ops = native_ops()
+    dev = torch.device("cuda", rank)
+    group = dist.group.WORLD
+    K, N = 512, 384
+    for batch, rows_block in ((1, 256), (2, 128)):  # contiguous token shards, and [batch, seq/W] batch-major shards
+        rows_local = batch * rows_block
+        M = rows_local * world
+        g = torch.Generator(device="cuda").manual_seed(11 + batch)
+        all_x = torch.randn(world, rows_local, K, device=dev, generator=g).bfloat16()  # same on every rank
+        w = torch.randn(N, K, device=dev, generator=g).bfloat16()
+
+        def gathered(shards):  # [world, batch*rows_block, C] -> [batch * world * rows_block, C] in (b, rank, s) order
+            c = shards.shape[-1]
+            return shards.view(world, batch, rows_block, c).permute(1, 0, 2, 3).reshape(M, c)
+
+        full_x = gathered(all_x).float()
+
+        # ---- all-gather -> GEMM
+        arena = SymmetricArena(rows_local * K, torch.bfloat16, dev, group)
+        arena.buffer.copy_(all_x[rank].reshape(-1))
+        arena.barrier()
+        ptrs = [int(p) for p in arena.handle.buffer_ptrs]
+        y = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ops.gemm_ag_a(ptrs, rows_local, K, rows_block, w, y, False)
+        torch.testing.assert_close(y.float(), full_x @ w.float().t(), rtol=2e-2, atol=2e-1)
+        wt = w.t().contiguous()  # [K, N]: MN-major B (dgrad layout)
+        y2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        ops.gemm_ag_a(ptrs, rows_local, K, rows_block, wt, y2, True)
+        torch.testing.assert_close(y2.float(), full_x @ w.float().t(), rtol=2e-2, atol=2e-1)
+
+        # ---- wgrad with the token-sharded operand pulled from the peers: dW[N, K] = dY^T[N, M] · X[M, K]
+        dy = torch.randn(M, N, device=dev, generator=g).bfloat16()
+        dw = torch.zeros(N, K, device=dev, dtype=torch.float32)
+        ops.gemm_ag_k(dy, ptrs, False, rows_local, K, rows_block, dw, True)  # peers hold B (= X)
+        torch.testing.assert_close(dw, dy.float().t() @ full_x, rtol=1e-3, atol=1e-2)
+        dw2 = torch.empty(K, N, device=dev, dtype=torch.float32)
+        ops.gemm_ag_k(dy, ptrs, True, rows_local, K, rows_block, dw2, False)  # peers hold A (= X): dW2[K, N] = X^T dY
+        torch.testing.assert_close(dw2, full_x.t() @ dy.float(), rtol=1e-3, atol=1e-2)
+        arena.barrier()
+
+        # ---- GEMM -> reduce-scatter: every rank contributes a_r @ w^T, rank r ends up with the summed rows it owns
+        a_r = torch.randn(M, K, device=dev, generator=torch.Generator(device="cuda").manual_seed(100 + rank)).bfloat16()
+        out = SymmetricArena(rows_local * N, torch.bfloat16, dev, group)
+        out.buffer.zero_()
+        out.barrier()
+        optrs = [int(p) for p in out.handle.buffer_ptrs]
+        ops.gemm_rs_d(a_r, w, optrs, rows_local, N, rows_block, False)
+        torch.cuda.synchronize()
+        out.barrier()
+        parts = [torch.empty_like(a_r) for _ in range(world)]
+        dist.all_gather(parts, a_r)
+        total = sum(p.float() @ w.float().t() for p in parts)  # [M, N]
+        mine = total.view(batch, world, rows_block, N)[:, rank].reshape(rows_local, N)
+        torch.testing.assert_close(out.buffer.view(rows_local, N).float(), mine, rtol=3e-2, atol=5e-1)
+        out.barrier()
+
+
+def test_tensor_parallel_gemms_with_fused_communication():
+    _need_gpus(2)
+    _spawn(_tp_gemm_worker, 2)
