@@ -7,9 +7,11 @@
 ``RowwiseLinearParallel``  shards the *input* features: ``W -> Shard(1)``; partial outputs are all-reduced
 (all-reduce forward / identity backward) or reduce-scattered along the sequence dim when ``sequence_parallel``.
 
-The collectives are autograd functions over the ``tp`` process group; the math runs on the local tcgen05 GEMM.
-The fused all-gather→GEMM / GEMM→reduce-scatter kernels over NVLink peer memory plug in behind the same styles
-(``d9d_b200.parallel``).
+With ``sequence_parallel=True`` on CUDA the collective is fused into the tcgen05 GEMM over NVLink peer memory
+(``d9d_b200.kernel.tp``): all-gather→GEMM loads every A tile from the owning peer through TMA, GEMM→reduce-scatter
+TMA reduce-adds every output tile into the owner's shard; backward uses the mirrored kernels.  Otherwise (CPU/gloo,
+unsupported shapes, plain all-reduce TP) the collectives are autograd functions over the ``tp`` process group around
+the local GEMM.
 """
 
 from __future__ import annotations
@@ -22,6 +24,8 @@ from torch import nn
 from torch.distributed import DeviceMesh
 from torch.distributed.tensor import DTensor, Replicate, Shard, distribute_tensor
 from torch.distributed.tensor.parallel import ParallelStyle
+
+from d9d_b200.kernel._native import MAIN_PARAM_ATTR
 
 
 class _CopyToGroup(torch.autograd.Function):
@@ -117,7 +121,11 @@ class _TensorParallelLinear(ParallelStyle):
 
 
 def _local(t: torch.Tensor | None) -> torch.Tensor | None:
-    return t.to_local() if isinstance(t, DTensor) else t
+    if isinstance(t, DTensor):
+        local = t.to_local()
+        setattr(local, MAIN_PARAM_ATTR, t)  # wgrad kernels may accumulate straight into the sharded parameter's .grad
+        return local
+    return t
 
 
 class ColwiseLinearParallel(_TensorParallelLinear):
@@ -130,6 +138,14 @@ class ColwiseLinearParallel(_TensorParallelLinear):
         sp, seq_dim = self._sp, self._seq_dim
 
         def forward(x: torch.Tensor) -> torch.Tensor:
+            if sp and seq_dim == x.dim() - 2:
+                from d9d_b200.kernel.tp.fused import all_gather_linear, fused_tp_supported
+
+                weight = _local(module.weight)
+                if fused_tp_supported(x, weight, group, x.shape[-2] * group.size()):
+                    out = all_gather_linear(x, weight, group)  # all-gather fused into the GEMM's TMA loads
+                    bias = _local(module.bias)
+                    return out if bias is None else out + bias
             x = _GatherSequence.apply(x, group, seq_dim) if sp else _CopyToGroup.apply(x, group)
             return linear(x, _local(module.weight), _local(module.bias))
 
@@ -147,6 +163,14 @@ class RowwiseLinearParallel(_TensorParallelLinear):
         sp, seq_dim = self._sp, self._seq_dim
 
         def forward(x: torch.Tensor) -> torch.Tensor:
+            if sp and seq_dim == x.dim() - 2:
+                from d9d_b200.kernel.tp.fused import fused_tp_supported, linear_reduce_scatter
+
+                weight = _local(module.weight)
+                if fused_tp_supported(x, weight, group, x.shape[-2]):
+                    out = linear_reduce_scatter(x, weight, group)  # reduce-scatter fused into the GEMM epilogue
+                    bias = _local(module.bias)
+                    return out if bias is None else out + bias
             partial = linear(x, _local(module.weight), None)
             out = _ScatterSequence.apply(partial, group, seq_dim) if sp else _ReduceFromGroup.apply(partial, group)
             bias = _local(module.bias)

@@ -128,10 +128,10 @@ def _trainer_worker(rank, world, optimizer_name, tmp):
         lr_scheduler_provider=AutoLRSchedulerProvider(lr_cfg),
     ).configure()
     losses = []
-    from d9d_b200.loop.event.catalogue.train import EVENT_TRAIN_STEP_POST
+    from d9d_b200.loop.event.catalogue.train import EVENT_TRAIN_OPTIMIZER_STEP_POST
 
-    state = trainer.state
-    state.event_bus.subscribe(EVENT_TRAIN_STEP_POST, lambda ctx: losses.append(state.gradient_manager.compute_global_loss().item()))
+    state = trainer.state  # (the loss accumulator is reset by zero_grad, i.e. before EVENT_TRAIN_STEP_POST)
+    state.event_bus.subscribe(EVENT_TRAIN_OPTIMIZER_STEP_POST, lambda ctx: losses.append(state.gradient_manager.compute_global_loss().item()))
     trainer.train()
     assert len(losses) == 12 and losses[-1] < losses[0] - 0.5, losses
     flat = torch.cat([(p._local_tensor if hasattr(p, "_local_tensor") else p.data).float().flatten()
@@ -219,3 +219,54 @@ def _tp_gemm_worker(rank, world):
 def test_tensor_parallel_gemms_with_fused_communication():
     _need_gpus(2)
     _spawn(_tp_gemm_worker, 2)
+
+
+def _tp_mlp_worker(rank, world):
+    from torch import nn
+    from torch.distributed.device_mesh import init_device_mesh
+
+    from d9d_b200.kernel._native import native_ops
+    from d9d_b200.module.block.linear import Linear
+    from d9d_b200.module.parallelism.api import parallelize_colwise, parallelize_rowwise
+
+    class MLP(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.up = Linear(512, 1024, bias=False)
+            self.down = Linear(1024, 512, bias=False)
+
+        def forward(self, x):
+            return self.down(torch.nn.functional.silu(self.up(x)))
+
+    mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("tp",))
+    torch.manual_seed(0)
+    ref = MLP().cuda()
+    tp = MLP().cuda().bfloat16()
+    tp.load_state_dict({k: v.bfloat16() for k, v in ref.state_dict().items()})
+    ref.load_state_dict({k: v.float() for k, v in tp.state_dict().items()})  # identical (bf16-rounded) weights
+    parallelize_colwise(tp.up, mesh, sequence_parallel=True)
+    parallelize_rowwise(tp.down, mesh, sequence_parallel=True)
+
+    x = torch.randn(2, 256 * world, 512, device="cuda").bfloat16()
+    x_ref = x.float().requires_grad_()
+    y_ref = ref(x_ref)
+    (y_ref * 0.01).square().sum().backward()
+    x_in = x.chunk(world, dim=1)[rank].contiguous().requires_grad_()
+    before = native_ops().launches
+    y = tp(x_in)
+    torch.testing.assert_close(y.float(), y_ref.detach().chunk(world, dim=1)[rank], rtol=3e-2, atol=3e-2)
+    (y.float() * 0.01).square().sum().backward()
+    assert native_ops().launches - before >= 6  # 2 fused forward GEMMs + 4 fused backward GEMMs ran on the native path
+
+    def close(a, b):
+        assert torch.nn.functional.cosine_similarity(a.float().flatten(), b.float().flatten(), dim=0) > 0.995
+        assert 0.95 < float(a.float().norm() / b.float().norm()) < 1.05
+
+    close(x_in.grad, x_ref.grad.chunk(world, dim=1)[rank])
+    close(tp.up.weight.grad.to_local(), ref.up.weight.grad.chunk(world, dim=0)[rank])
+    close(tp.down.weight.grad.to_local(), ref.down.weight.grad.chunk(world, dim=1)[rank])
+
+
+def test_sequence_parallel_mlp_uses_fused_tp_kernels():
+    _need_gpus(2)
+    _spawn(_tp_mlp_worker, 2)
