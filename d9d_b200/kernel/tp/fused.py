@@ -12,6 +12,9 @@ from d9d_b200.internals.nvlink import SymmetricArena
 from .._native import fused_wgrad_buffer, fused_wgrad_owner, grad_dtype_of, native_ops
 
 
+_DIRECT_PEER_LOAD_MAX_N = 512  # output width up to which A tiles are loaded directly from the peers (few re-reads)
+
+
 class TensorParallelWorkspace:
     """Symmetric staging buffers of one tensor-parallel group (grown on demand; every rank grows in lock-step because
     all ranks execute the same layers with the same shapes)."""
@@ -23,6 +26,7 @@ class TensorParallelWorkspace:
         self.world = group.size()
         self.rank = group.rank()
         self._arenas: dict[str, SymmetricArena] = {}
+        self._side: torch.cuda.Stream | None = None
 
     @classmethod
     def for_group(cls, group: dist.ProcessGroup) -> "TensorParallelWorkspace":
@@ -48,6 +52,39 @@ class TensorParallelWorkspace:
         arena.barrier()
         return arena, [int(p) for p in arena.handle.buffer_ptrs]
 
+    def gather_async(self, name: str, local: torch.Tensor, block_rows: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """Start an all-gather of ``local [rows_local, C]`` into a *local* buffer ``[world * rows_local, C]`` (rows in
+        ``(batch, rank, row-in-block)`` order) and return ``(gathered, flags)`` immediately.
+
+        The local shard is copied on the current stream; every remote shard is pulled over NVLink exactly once on a
+        side stream (peer-to-peer copies, no SMs), followed by ``flags[r] = 1``.  ``gemm_wait_a`` consumes the buffer
+        tile by tile, waiting on a shard's flag only when it reaches it; ``join()`` must be called before the
+        buffer is used by anything else.
+        """
+        arena, _ = self.stage(name, local)
+        rows_local, cols = local.shape
+        batch = rows_local // block_rows
+        gathered = torch.empty(self.world * rows_local, cols, device=local.device, dtype=local.dtype)
+        view = gathered.view(batch, self.world, block_rows, cols)
+        flags = torch.zeros(self.world, dtype=torch.int32, device=local.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=local.device)
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        gathered.record_stream(self._side)
+        flags.record_stream(self._side)
+        with torch.cuda.stream(self._side):
+            for step in range(1, self.world):
+                r = (self.rank + step) % self.world
+                view[:, r].copy_(arena.peer_view(r, (rows_local * cols,))[: rows_local * cols].view(batch, block_rows, cols))
+                flags[r : r + 1].fill_(1)
+        view[:, self.rank].copy_(local.view(batch, block_rows, cols))
+        return gathered, flags
+
+    def join(self) -> None:
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+
     def zeroed(self, name: str, numel: int, device: torch.device) -> tuple[SymmetricArena, list[int]]:
         arena = self.arena(name, numel, device)
         arena.barrier()
@@ -71,9 +108,17 @@ class _AllGatherLinear(Function):
     def forward(ctx: Any, x: torch.Tensor, weight: torch.Tensor, ws: TensorParallelWorkspace, owner: torch.Tensor | None):
         ops = native_ops()
         x2, block_rows, rows_local = _rows(x)
-        _, ptrs = ws.stage("ag_in", x2)
         y = torch.empty(rows_local * ws.world, weight.shape[0], device=x.device, dtype=x.dtype)
-        ops.gemm_ag_a(ptrs, rows_local, x2.shape[1], block_rows, weight, y, False)
+        if weight.shape[0] <= _DIRECT_PEER_LOAD_MAX_N:
+            # few n-tiles: every A tile is read once or twice, load it straight from its owner through TMA
+            _, ptrs = ws.stage("ag_in", x2)
+            ops.gemm_ag_a(ptrs, rows_local, x2.shape[1], block_rows, weight, y, False)
+        else:
+            # many n-tiles re-read A: pull every remote shard once (copy engines) while the GEMM already runs on the
+            # local shard; tiles of a remote shard wait for its arrival flag
+            gathered, flags = ws.gather_async("ag_in", x2, block_rows)
+            ops.gemm_wait_a(gathered, flags, ws.rank, block_rows, weight, y, False)
+            ws.join()
         ctx.save_for_backward(x2, weight)
         ctx.ws, ctx.owner, ctx.block_rows, ctx.x_shape = ws, owner, block_rows, x.shape
         return y.view(*x.shape[:-2], block_rows * ws.world, weight.shape[0])
@@ -88,19 +133,23 @@ class _AllGatherLinear(Function):
             dy = dy.contiguous()
         rows_local, k = x2.shape
         dx = dw = None
+        need_dw = GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight) and (ctx.needs_input_grad[1] or ctx.needs_input_grad[3])
+        gathered = None
+        if need_dw:  # re-gather x on the side stream; it overlaps the dgrad GEMM below
+            gathered, _ = ws.gather_async("ag_in", x2, ctx.block_rows)
         if ctx.needs_input_grad[0] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.inputs):
             # dx_shard = reduce_scatter(dy @ W): every rank reduce-adds its partial tiles into the owners' buffers
             arena, ptrs = ws.zeroed("rs_out", rows_local * k, dy.device)
             ops.gemm_rs_d(dy, weight, ptrs, rows_local, k, ctx.block_rows, True)
             arena.barrier()
             dx = arena.buffer[: rows_local * k].view(rows_local, k).clone().view(ctx.x_shape)
-        if GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight) and (ctx.needs_input_grad[1] or ctx.needs_input_grad[3]):
-            _, xptrs = ws.stage("ag_in", x2)  # dW[N, K] = dy^T @ all_gather(x): x tiles come from their owners
+        if need_dw:  # dW[N, K] = dy^T @ all_gather(x)
+            ws.join()
             if ctx.owner is not None and ctx.needs_input_grad[3]:
-                ops.gemm_ag_k(dy, xptrs, False, rows_local, k, ctx.block_rows, fused_wgrad_buffer(ctx.owner), True)
+                ops.gemm(dy, gathered, fused_wgrad_buffer(ctx.owner), True, True, True)
             else:
                 dw = torch.empty(weight.shape, device=weight.device, dtype=grad_dtype_of(weight))
-                ops.gemm_ag_k(dy, xptrs, False, rows_local, k, ctx.block_rows, dw, False)
+                ops.gemm(dy, gathered, dw, True, True, False)
         return dx, dw, None, None
 
 
@@ -135,17 +184,19 @@ class _LinearReduceScatter(Function):
         need_dx = ctx.needs_input_grad[0] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.inputs)
         need_dw = GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight) and (ctx.needs_input_grad[1] or ctx.needs_input_grad[3])
         if need_dx or need_dw:
-            _, ptrs = ws.stage("ag_in", dy)
-        if need_dx:  # dx[M, K_local] = all_gather(dy) @ W
+            gathered, flags = ws.gather_async("ag_in", dy, ctx.block_rows)
+        if need_dx:  # dx[M, K_local] = all_gather(dy) @ W, consuming the shards as they land
             dx = torch.empty_like(x2)
-            ops.gemm_ag_a(ptrs, rows_local, n, ctx.block_rows, weight, dx, True)
+            ops.gemm_wait_a(gathered, flags, ws.rank, ctx.block_rows, weight, dx, True)
             dx = dx.view(ctx.x_shape)
+        if need_dx or need_dw:
+            ws.join()
         if need_dw:  # dW[N, K_local] = all_gather(dy)^T @ x
             if ctx.owner is not None and ctx.needs_input_grad[3]:
-                ops.gemm_ag_k(x2, ptrs, True, rows_local, n, ctx.block_rows, fused_wgrad_buffer(ctx.owner), True)
+                ops.gemm(gathered, x2, fused_wgrad_buffer(ctx.owner), True, True, True)
             else:
                 dw = torch.empty(weight.shape, device=weight.device, dtype=grad_dtype_of(weight))
-                ops.gemm_ag_k(x2, ptrs, True, rows_local, n, ctx.block_rows, dw, False)
+                ops.gemm(gathered, x2, dw, True, True, False)
         return dx, dw, None, None
 
 

@@ -365,6 +365,26 @@ void gemm_ag_a(at::IntArrayRef a_peer_ptrs, int64_t rows_local, int64_t lda, int
   d9d::gemm_comm(g, cur_stream());
 }
 
+// d[M,N] = a[M,K] · B where a is a local buffer whose shards (owner(row) per the block mapping) arrive asynchronously:
+// the GEMM starts with this rank's shard and waits on flags[owner] (int32, non-zero = landed) before touching another one
+void gemm_wait_a(const Tensor& a, const Tensor& flags, int64_t rank, int64_t block_rows, const Tensor& b, Tensor d, bool b_mn) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda() && a.dim() == 2 && b.dim() == 2 && d.dim() == 2);
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && d.stride(1) == 1);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && d.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(flags.is_cuda() && flags.scalar_type() == at::kInt && flags.is_contiguous());
+  c10::cuda::CUDAGuard guard(d.device());
+  d9d::GemmArgs g;
+  g.mode = 0; g.a_mn = false; g.b_mn = b_mn; g.epi = 0;
+  g.M = static_cast<int>(a.size(0)); g.K = static_cast<int>(a.size(1));
+  g.N = static_cast<int>(b_mn ? b.size(1) : b.size(0));
+  TORCH_CHECK((b_mn ? b.size(0) : b.size(1)) == g.K && d.size(0) == g.M && d.size(1) == g.N, "gemm_wait_a: shape mismatch");
+  g.A = a.data_ptr(); g.B = b.data_ptr(); g.D = d.data_ptr();
+  g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
+  g.comm = 5; g.comm_world = static_cast<int>(flags.numel()); g.comm_block_rows = static_cast<int>(block_rows);
+  g.comm_rank = static_cast<int>(rank); g.comm_flags = flags.data_ptr<int>();
+  d9d::gemm_comm(g, cur_stream());
+}
+
 // d_shards[owner][rows_local, N] += (a[M,K] · B) rows owned by `owner` (bf16 reduce-add over NVLink)
 void gemm_rs_d(const Tensor& a, const Tensor& b, at::IntArrayRef d_peer_ptrs, int64_t rows_local, int64_t ldd, int64_t block_rows,
                bool b_mn) {
@@ -464,6 +484,7 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
   m.def("gemm_ag_a(int[] a_peer_ptrs, int rows_local, int lda, int block_rows, Tensor b, Tensor(a!) d, bool b_mn) -> ()");
+  m.def("gemm_wait_a(Tensor a, Tensor flags, int rank, int block_rows, Tensor b, Tensor(a!) d, bool b_mn) -> ()");
   m.def("gemm_rs_d(Tensor a, Tensor b, int[] d_peer_ptrs, int rows_local, int ldd, int block_rows, bool b_mn) -> ()");
   m.def("gemm_ag_k(Tensor local, int[] peer_ptrs, bool peer_is_a, int rows_local, int peer_ld, int block_rows, Tensor(a!) d, "
         "bool accumulate) -> ()");
@@ -495,6 +516,7 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("moe_gather", &moe_gather);
   m.impl("sumsq_accumulate_", &sumsq_accumulate_);
   m.impl("gemm_ag_a", &gemm_ag_a);
+  m.impl("gemm_wait_a", &gemm_wait_a);
   m.impl("gemm_rs_d", &gemm_rs_d);
   m.impl("gemm_ag_k", &gemm_ag_k);
   m.impl("nvl_reduce_shard_", &nvl_reduce_shard_);

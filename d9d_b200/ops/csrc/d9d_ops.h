@@ -33,6 +33,8 @@ struct GemmArgs {
   const void* const* comm_peer_ptrs = nullptr; // host array [comm_world]: base pointer of every peer's shard
   long long comm_rows_local = 0;               // rows of one shard
   long long comm_ld = 0;                       // leading dim (elements) of the shards
+  int comm_rank = 0;                           // COMM_WAIT_A: this rank
+  const int* comm_flags = nullptr;             // COMM_WAIT_A: device array [comm_world] of shard arrival flags
   // fused linear cross entropy
   const long long* ce_target = nullptr;
   const float* ce_lse = nullptr;

@@ -30,6 +30,10 @@ void gemm_comm(const GemmArgs& a, cudaStream_t stream) {
       if (a.epi != EPI_BF16) throw std::runtime_error("d9d gemm_comm: all-gather GEMM stores bf16");
       dispatch_layout<COMM_AG_A, EPI_BF16>(a, bn, stream);
       break;
+    case COMM_WAIT_A:
+      if (a.epi != EPI_BF16) throw std::runtime_error("d9d gemm_comm: all-gather GEMM stores bf16");
+      dispatch_layout<COMM_WAIT_A, EPI_BF16>(a, bn, stream);
+      break;
     case COMM_RS_D:
       if (a.epi != EPI_BF16_ACC) throw std::runtime_error("d9d gemm_comm: reduce-scatter GEMM reduce-adds bf16");
       dispatch_layout<COMM_RS_D, EPI_BF16_ACC>(a, bn, stream);

@@ -85,7 +85,10 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   // ---- tensor maps ----
   CUtensorMap ta, tb;
   typename PeerArg<COMM>::type peers{};
-  if constexpr (COMM != COMM_NONE) {
+  if constexpr (COMM == COMM_WAIT_A) {
+    if (a.comm_flags == nullptr || a.comm_block_rows <= 0 || a.comm_block_rows % BLOCK_M != 0)
+      throw std::runtime_error("d9d gemm: flag-gated all-gather GEMM needs arrival flags and tile-aligned shard blocks");
+  } else if constexpr (COMM != COMM_NONE) {
     if (a.comm_world < 1 || a.comm_world > MAX_PEERS || a.comm_peer_ptrs == nullptr)
       throw std::runtime_error("d9d gemm: fused communication needs 1..8 peer pointers");
     const int unit = (COMM == COMM_AG_A) ? BLOCK_M : (COMM == COMM_RS_D ? 32 : BLOCK_K);
@@ -143,6 +146,8 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   }
   p.M = a.M; p.N = a.N; p.K = a.K; p.num_groups = a.num_groups;
   p.comm_world = a.comm_world; p.comm_block_rows = a.comm_block_rows;
+  p.comm_rank = a.comm_rank; p.comm_flags = a.comm_flags;
+  p.comm_m_rot = (COMM == COMM_WAIT_A) ? (a.comm_rank * a.comm_block_rows / BLOCK_M) % static_cast<int>((a.M + BLOCK_M - 1) / BLOCK_M) : 0;
   p.D = a.D; p.ldd = a.ldd; p.d_group_stride = a.d_group_stride;
   p.tile_group = a.tile_group; p.group_offsets = a.group_offsets;
   p.ce_target = a.ce_target; p.ce_lse = a.ce_lse; p.ce_grad = a.ce_grad;

@@ -50,12 +50,17 @@ enum Epi : int {
 // Row index -> (owner, local row):  blk = idx / comm_block_rows; owner = blk % comm_world;
 //                                   local = (blk / comm_world) * comm_block_rows + idx % comm_block_rows
 // (covers both "tokens sharded as one contiguous block per rank" and "[batch, seq/W] per rank, batch-major").
-enum Comm : int { COMM_NONE = 0, COMM_AG_A = 1, COMM_RS_D = 2, COMM_AG_KA = 3, COMM_AG_KB = 4 };
+//   COMM_WAIT_A A is a *local* gathered buffer that is being filled shard by shard (peer copies running concurrently on
+//               the copy engines / another stream); the producer waits on the owner's arrival flag before the first
+//               load of an m-tile and tiles are visited starting with the local shard  => all-gather overlapped with
+//               the GEMM tile by tile while every remote byte crosses NVLink exactly once
+enum Comm : int { COMM_NONE = 0, COMM_AG_A = 1, COMM_RS_D = 2, COMM_AG_KA = 3, COMM_AG_KB = 4, COMM_WAIT_A = 5 };
 constexpr int MAX_PEERS = 8;
 struct PeerMaps { CUtensorMap m[MAX_PEERS]; };
 struct NoPeerMaps {};
 template <int COMM> struct PeerArg { using type = PeerMaps; };
 template <> struct PeerArg<COMM_NONE> { using type = NoPeerMaps; };
+template <> struct PeerArg<COMM_WAIT_A> { using type = NoPeerMaps; };
 
 struct Params {
   int M, N, K;            // DENSE: problem dims. GROUPED_M: M = padded row capacity. GROUPED_K: M,N = per-expert out dims
@@ -64,6 +69,9 @@ struct Params {
   int tma_epilogue;       // 1: output through the tmap_d TMA store/reduce path, 0: direct global stores
   int comm_world;         // COMM_*: number of peers
   int comm_block_rows;    // COMM_*: rows per (rank, block) of the sharded dim
+  int comm_rank;          // COMM_WAIT_A: this rank (its shard needs no wait)
+  int comm_m_rot;         // COMM_WAIT_A: m-blocks are visited starting at this block (the local shard first)
+  const int* comm_flags;  // COMM_WAIT_A: [comm_world] arrival flags of the shards (non-zero = landed)
   void* D;                // output
   long long ldd;          // leading dim of D (elements)
   long long d_group_stride;  // GROUPED_K: elements between per-expert outputs
@@ -144,6 +152,7 @@ __device__ __forceinline__ TileCoord get_tile(const Params& p, int tile) {
   const int r = tile - gid * group_span;
   t.m_blk = first_m + (r % gm);
   t.n_blk = r / gm;
+  if (MODE == DENSE && p.comm_m_rot != 0) t.m_blk = (t.m_blk + p.comm_m_rot) % m_tiles;
   t.k_begin = 0;
   t.k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   if (MODE == DENSE && p.k_splits > 1) {
@@ -173,7 +182,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const __grid_constant__ CUtensorMap tmap_d, const Params p,
             const __grid_constant__ typename PeerArg<COMM>::type peers) {
   static_assert(COMM == COMM_NONE || MODE == DENSE, "fused communication is implemented for dense GEMMs");
-  static_assert(COMM != COMM_AG_A || !A_MN, "COMM_AG_A gathers a K-major A");
+  static_assert((COMM != COMM_AG_A && COMM != COMM_WAIT_A) || !A_MN, "COMM_AG_A / COMM_WAIT_A work on a K-major A");
   static_assert(COMM != COMM_AG_KA || A_MN, "COMM_AG_KA gathers an MN-major A along K");
   static_assert(COMM != COMM_AG_KB || B_MN, "COMM_AG_KB gathers an MN-major B along K");
   static_assert(COMM != COMM_RS_D || EPI == EPI_F32_ACC || EPI == EPI_BF16_ACC, "COMM_RS_D needs a reduce-add epilogue");
@@ -198,7 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (p.tma_epilogue) tma_prefetch_desc(&tmap_d);
-    if constexpr (COMM != COMM_NONE)
+    if constexpr (COMM != COMM_NONE && COMM != COMM_WAIT_A)
       for (int r = 0; r < p.comm_world; ++r) tma_prefetch_desc(&peers.m[r]);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -225,6 +234,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
         if (!t.valid) continue;
         const int m_idx = t.m_blk * BLOCK_M, n_idx = t.n_blk * BLOCK_N;
+        if constexpr (COMM == COMM_WAIT_A) {  // the shard holding this m-tile may still be in flight
+          int owner, unused;
+          comm_locate(p, m_idx, owner, unused);
+          if (owner != p.comm_rank) {
+            const int* flag = p.comm_flags + owner;
+            int landed;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(landed) : "l"(flag) : "memory");
+              if (!landed) __nanosleep(200);
+            } while (!landed);
+            fence_proxy_async_all();  // the copy's generic-proxy writes are ordered before our async-proxy (TMA) reads
+          }
+        }
         for (int kb = 0; kb < t.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
