@@ -61,8 +61,8 @@ class TensorParallelWorkspace:
         tile by tile, waiting on a shard's flag only when it reaches it; ``join()`` must be called before the
         buffer is used by anything else.
         """
-        arena, _ = self.stage(name, local)
         rows_local, cols = local.shape
+        arena = self.arena(name, local.numel(), local.device)
         batch = rows_local // block_rows
         gathered = torch.empty(self.world * rows_local, cols, device=local.device, dtype=local.dtype)
         view = gathered.view(batch, self.world, block_rows, cols)
@@ -71,9 +71,14 @@ class TensorParallelWorkspace:
             self._side = torch.cuda.Stream(device=local.device)
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)
-        gathered.record_stream(self._side)
-        flags.record_stream(self._side)
+        for t in (gathered, flags, local):
+            t.record_stream(self._side)
         with torch.cuda.stream(self._side):
+            # publish + pull entirely off the critical path: the main stream only copies the local shard and launches
+            # the GEMM, which works on local tiles until the remote shards' flags are raised
+            arena.barrier()  # peers finished pulling the previous contents of my staging buffer
+            arena.buffer[: local.numel()].copy_(local.reshape(-1))
+            arena.barrier()  # every rank's shard is published
             for step in range(1, self.world):
                 r = (self.rank + step) % self.world
                 view[:, r].copy_(arena.peer_view(r, (rows_local * cols,))[: rows_local * cols].view(batch, block_rows, cols))
