@@ -62,13 +62,30 @@ def main() -> None:
     y = torch.empty(T, Fl, **bf)
     gathered = torch.empty(T, H, **bf)
 
+    ones = torch.ones(world, dtype=torch.int32, device=dev)
+
     def ag_gemm_fused():
         _, ptrs = ws.stage("ag_in", x_shard)
         ops.gemm_ag_a(ptrs, Tl, H, Tl, w_up, y, False)
 
-    def ag_gemm_pipelined():
+    def ag_gemm_pipelined(spare=0):
         g2, flags = ws.gather_async("ag_in", x_shard, Tl)
-        ops.gemm_wait_a(g2, flags, rank, Tl, w_up, y, False)
+        ops.gemm_wait_a(g2, flags, rank, Tl, w_up, y, False, spare)
+        ws.join()
+
+    def concurrent_independent():  # gather chain and an ungated GEMM at the same time (no data dependency)
+        ws.gather_async("ag_in", x_shard, Tl)
+        ops.gemm_wait_a(gathered, ones, rank, Tl, w_up, y, False, 0)
+        ws.join()
+
+    def wait_gemm_only():  # flag-gated kernel with every flag already raised
+        ops.gemm_wait_a(gathered, ones, rank, Tl, w_up, y, False)
+
+    def _unused():
+        pass
+
+    def gather_only():
+        ws.gather_async("ag_in", x_shard, Tl)
         ws.join()
 
     def ag_gemm_nccl():
@@ -95,7 +112,9 @@ def main() -> None:
         ops.gemm(h, w_down, partial, False, False, False)
 
     res = {"world": world, "tokens": T, "hidden": H, "ffn": F,
-           "ag_gemm_fused_ms": timed(ag_gemm_fused), "ag_gemm_pipelined_ms": timed(ag_gemm_pipelined), "ag_gemm_nccl_ms": timed(ag_gemm_nccl), "gemm_up_only_ms": timed(gemm_only_up),
+           "ag_gemm_fused_ms": timed(ag_gemm_fused), "ag_gemm_pipelined_ms": timed(ag_gemm_pipelined), "ag_gemm_pipelined_spare8_ms": timed(lambda: ag_gemm_pipelined(8)),
+           "ag_gemm_pipelined_spare16_ms": timed(lambda: ag_gemm_pipelined(16)),
+           "wait_gemm_only_ms": timed(wait_gemm_only), "gather_only_ms": timed(gather_only), "concurrent_independent_ms": timed(concurrent_independent), "ag_gemm_nccl_ms": timed(ag_gemm_nccl), "gemm_up_only_ms": timed(gemm_only_up),
            "gemm_rs_fused_ms": timed(gemm_rs_fused), "gemm_rs_nccl_ms": timed(gemm_rs_nccl), "gemm_down_only_ms": timed(gemm_only_down)}
     flops = 2.0 * T * H * Fl
     for k in ("ag_gemm_pipelined_ms", "ag_gemm_fused_ms", "ag_gemm_nccl_ms", "gemm_up_only_ms", "gemm_rs_fused_ms", "gemm_rs_nccl_ms", "gemm_down_only_ms"):

@@ -367,7 +367,8 @@ void gemm_ag_a(at::IntArrayRef a_peer_ptrs, int64_t rows_local, int64_t lda, int
 
 // d[M,N] = a[M,K] · B where a is a local buffer whose shards (owner(row) per the block mapping) arrive asynchronously:
 // the GEMM starts with this rank's shard and waits on flags[owner] (int32, non-zero = landed) before touching another one
-void gemm_wait_a(const Tensor& a, const Tensor& flags, int64_t rank, int64_t block_rows, const Tensor& b, Tensor d, bool b_mn) {
+void gemm_wait_a(const Tensor& a, const Tensor& flags, int64_t rank, int64_t block_rows, const Tensor& b, Tensor d, bool b_mn,
+                 int64_t spare_sms) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda() && a.dim() == 2 && b.dim() == 2 && d.dim() == 2);
   TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1 && d.stride(1) == 1);
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && d.scalar_type() == at::kBFloat16);
@@ -382,6 +383,7 @@ void gemm_wait_a(const Tensor& a, const Tensor& flags, int64_t rank, int64_t blo
   g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
   g.comm = 5; g.comm_world = static_cast<int>(flags.numel()); g.comm_block_rows = static_cast<int>(block_rows);
   g.comm_rank = static_cast<int>(rank); g.comm_flags = flags.data_ptr<int>();
+  g.comm_spare_sms = static_cast<int>(spare_sms);
   d9d::gemm_comm(g, cur_stream());
 }
 
@@ -484,7 +486,7 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
   m.def("gemm_ag_a(int[] a_peer_ptrs, int rows_local, int lda, int block_rows, Tensor b, Tensor(a!) d, bool b_mn) -> ()");
-  m.def("gemm_wait_a(Tensor a, Tensor flags, int rank, int block_rows, Tensor b, Tensor(a!) d, bool b_mn) -> ()");
+  m.def("gemm_wait_a(Tensor a, Tensor flags, int rank, int block_rows, Tensor b, Tensor(a!) d, bool b_mn, int spare_sms=0) -> ()");
   m.def("gemm_rs_d(Tensor a, Tensor b, int[] d_peer_ptrs, int rows_local, int ldd, int block_rows, bool b_mn) -> ()");
   m.def("gemm_ag_k(Tensor local, int[] peer_ptrs, bool peer_is_a, int rows_local, int peer_ld, int block_rows, Tensor(a!) d, "
         "bool accumulate) -> ()");

@@ -35,6 +35,7 @@ struct GemmArgs {
   long long comm_ld = 0;                       // leading dim (elements) of the shards
   int comm_rank = 0;                           // COMM_WAIT_A: this rank
   const int* comm_flags = nullptr;             // COMM_WAIT_A: device array [comm_world] of shard arrival flags
+  int comm_spare_sms = 0;                      // COMM_WAIT_A: SMs left free for the concurrent copy kernels
   // fused linear cross entropy
   const long long* ce_target = nullptr;
   const float* ce_lse = nullptr;

@@ -157,7 +157,9 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   const long long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   long long tiles = m_tiles * n_tiles * (MODE == GROUPED_K ? a.num_groups : 1) * p.k_splits;
   if (tiles <= 0) return;
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  // COMM_WAIT_A runs next to copy / flag kernels of another stream: leave `comm_spare_sms` SMs to them
+  const int usable = sm_count() - ((COMM == COMM_WAIT_A) ? a.comm_spare_sms : 0);
+  const int grid = static_cast<int>(tiles < usable ? tiles : usable);
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, td, p, peers);
 }
 
