@@ -1,5 +1,6 @@
 from __future__ import annotations
 
+from collections.abc import Callable
 from typing import Any
 
 import torch
@@ -52,14 +53,17 @@ class TensorParallelWorkspace:
         arena.barrier()
         return arena, [int(p) for p in arena.handle.buffer_ptrs]
 
-    def gather_async(self, name: str, local: torch.Tensor, block_rows: int) -> tuple[torch.Tensor, torch.Tensor]:
-        """Start an all-gather of ``local [rows_local, C]`` into a *local* buffer ``[world * rows_local, C]`` (rows in
-        ``(batch, rank, row-in-block)`` order) and return ``(gathered, flags)`` immediately.
+    def gather_async(self, name: str, local: torch.Tensor, block_rows: int,
+                     consumer: "Callable[[torch.Tensor, torch.Tensor], None] | None" = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """All-gather ``local [rows_local, C]`` into a *local* buffer ``[world * rows_local, C]`` (rows in
+        ``(batch, rank, row-in-block)`` order) without blocking the current stream; returns ``(gathered, flags)``.
 
-        The local shard is copied on the current stream; every remote shard is pulled over NVLink exactly once on a
-        side stream (peer-to-peer copies, no SMs), followed by ``flags[r] = 1``.  ``gemm_wait_a`` consumes the buffer
-        tile by tile, waiting on a shard's flag only when it reaches it; ``join()`` must be called before the
-        buffer is used by anything else.
+        The local shard is copied on the current stream, then ``consumer(gathered, flags)`` (typically the flag-gated
+        GEMM) is launched, and only then the publish / pull chain is enqueued on a side stream: barrier → copy my shard
+        to the symmetric staging buffer → barrier → pull every remote shard over NVLink exactly once → ``flags[r] = 1``.
+        Enqueueing the consumer first matters when all streams share one hardware queue
+        (``CUDA_DEVICE_MAX_CONNECTIONS=1``): work can only overlap with work submitted *earlier*.
+        ``join()`` must be called before the buffer is used by anything that does not look at the flags.
         """
         rows_local, cols = local.shape
         arena = self.arena(name, local.numel(), local.device)
@@ -70,12 +74,15 @@ class TensorParallelWorkspace:
         if self._side is None:
             self._side = torch.cuda.Stream(device=local.device)
         main = torch.cuda.current_stream()
-        self._side.wait_stream(main)
+        view[:, self.rank].copy_(local.view(batch, block_rows, cols))
+        ready = torch.cuda.Event()
+        ready.record(main)
+        if consumer is not None:
+            consumer(gathered, flags)
+        self._side.wait_event(ready)
         for t in (gathered, flags, local):
             t.record_stream(self._side)
         with torch.cuda.stream(self._side):
-            # publish + pull entirely off the critical path: the main stream only copies the local shard and launches
-            # the GEMM, which works on local tiles until the remote shards' flags are raised
             arena.barrier()  # peers finished pulling the previous contents of my staging buffer
             arena.buffer[: local.numel()].copy_(local.reshape(-1))
             arena.barrier()  # every rank's shard is published
@@ -83,7 +90,6 @@ class TensorParallelWorkspace:
                 r = (self.rank + step) % self.world
                 view[:, r].copy_(arena.peer_view(r, (rows_local * cols,))[: rows_local * cols].view(batch, block_rows, cols))
                 flags[r : r + 1].fill_(1)
-        view[:, self.rank].copy_(local.view(batch, block_rows, cols))
         return gathered, flags
 
     def join(self) -> None:
@@ -121,8 +127,8 @@ class _AllGatherLinear(Function):
         else:
             # many n-tiles re-read A: pull every remote shard once (copy engines) while the GEMM already runs on the
             # local shard; tiles of a remote shard wait for its arrival flag
-            gathered, flags = ws.gather_async("ag_in", x2, block_rows)
-            ops.gemm_wait_a(gathered, flags, ws.rank, block_rows, weight, y, False)
+            ws.gather_async("ag_in", x2, block_rows,
+                            consumer=lambda g, f: ops.gemm_wait_a(g, f, ws.rank, block_rows, weight, y, False, 0))
             ws.join()
         ctx.save_for_backward(x2, weight)
         ctx.ws, ctx.owner, ctx.block_rows, ctx.x_shape = ws, owner, block_rows, x.shape
@@ -188,12 +194,13 @@ class _LinearReduceScatter(Function):
         dx = dw = None
         need_dx = ctx.needs_input_grad[0] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.inputs)
         need_dw = GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight) and (ctx.needs_input_grad[1] or ctx.needs_input_grad[3])
-        if need_dx or need_dw:
-            gathered, flags = ws.gather_async("ag_in", dy, ctx.block_rows)
         if need_dx:  # dx[M, K_local] = all_gather(dy) @ W, consuming the shards as they land
             dx = torch.empty_like(x2)
-            ops.gemm_wait_a(gathered, flags, ws.rank, ctx.block_rows, weight, dx, True)
+            gathered, _ = ws.gather_async("ag_in", dy, ctx.block_rows,
+                                          consumer=lambda g, f: ops.gemm_wait_a(g, f, ws.rank, ctx.block_rows, weight, dx, True, 0))
             dx = dx.view(ctx.x_shape)
+        elif need_dw:
+            gathered, _ = ws.gather_async("ag_in", dy, ctx.block_rows)
         if need_dx or need_dw:
             ws.join()
         if need_dw:  # dW[N, K_local] = all_gather(dy)^T @ x
