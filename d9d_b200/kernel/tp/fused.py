@@ -13,6 +13,9 @@ from d9d_b200.internals.nvlink import SymmetricArena
 from .._native import fused_wgrad_buffer, fused_wgrad_owner, grad_dtype_of, native_ops
 
 
+# the flag-gated GEMM is persistent (one CTA per SM, ~226 KiB of shared memory each): the copy / flag / barrier kernels
+# of the concurrent pull chain need SMs of their own or the two would dead-lock
+_PIPELINE_SPARE_SMS = 8
 _DIRECT_PEER_LOAD_MAX_N = 512  # output width up to which A tiles are loaded directly from the peers (few re-reads)
 
 
@@ -128,7 +131,7 @@ class _AllGatherLinear(Function):
             # many n-tiles re-read A: pull every remote shard once (copy engines) while the GEMM already runs on the
             # local shard; tiles of a remote shard wait for its arrival flag
             ws.gather_async("ag_in", x2, block_rows,
-                            consumer=lambda g, f: ops.gemm_wait_a(g, f, ws.rank, block_rows, weight, y, False, 0))
+                            consumer=lambda g, f: ops.gemm_wait_a(g, f, ws.rank, block_rows, weight, y, False, _PIPELINE_SPARE_SMS))
             ws.join()
         ctx.save_for_backward(x2, weight)
         ctx.ws, ctx.owner, ctx.block_rows, ctx.x_shape = ws, owner, block_rows, x.shape
@@ -197,7 +200,7 @@ class _LinearReduceScatter(Function):
         if need_dx:  # dx[M, K_local] = all_gather(dy) @ W, consuming the shards as they land
             dx = torch.empty_like(x2)
             gathered, _ = ws.gather_async("ag_in", dy, ctx.block_rows,
-                                          consumer=lambda g, f: ops.gemm_wait_a(g, f, ws.rank, ctx.block_rows, weight, dx, True, 0))
+                                          consumer=lambda g, f: ops.gemm_wait_a(g, f, ws.rank, ctx.block_rows, weight, dx, True, _PIPELINE_SPARE_SMS))
             dx = dx.view(ctx.x_shape)
         elif need_dw:
             gathered, _ = ws.gather_async("ag_in", dy, ctx.block_rows)

@@ -240,9 +240,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (owner != p.comm_rank) {
             const int* flag = p.comm_flags + owner;
             int landed;
+            long long spins = 0;
             do {
               asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(landed) : "l"(flag) : "memory");
-              if (!landed) __nanosleep(200);
+              if (!landed) {
+                __nanosleep(500);
+                if (++spins > 8000000LL) {  // ~4 s: the producer of the flag never ran (would otherwise hang the GPU)
+                  printf("d9d gemm: shard arrival flag %d never raised\n", owner);
+                  __trap();
+                }
+              }
             } while (!landed);
             fence_proxy_async_all();  // the copy's generic-proxy writes are ordered before our async-proxy (TMA) reads
           }
