@@ -68,12 +68,12 @@ def main() -> None:
         _, ptrs = ws.stage("ag_in", x_shard)
         ops.gemm_ag_a(ptrs, Tl, H, Tl, w_up, y, False)
 
-    def ag_gemm_pipelined(spare=8):
+    def ag_gemm_pipelined(spare=0):
         ws.gather_async("ag_in", x_shard, Tl, consumer=lambda g2, flags: ops.gemm_wait_a(g2, flags, rank, Tl, w_up, y, False, spare))
         ws.join()
 
     def concurrent_independent():  # gather chain and an ungated GEMM at the same time (no data dependency)
-        ws.gather_async("ag_in", x_shard, Tl, consumer=lambda g2, flags: ops.gemm_wait_a(gathered, ones, rank, Tl, w_up, y, False, 8))
+        ws.gather_async("ag_in", x_shard, Tl, consumer=lambda g2, flags: ops.gemm_wait_a(gathered, ones, rank, Tl, w_up, y, False, 0))
         ws.join()
 
     def wait_gemm_only():  # flag-gated kernel with every flag already raised
@@ -110,7 +110,7 @@ def main() -> None:
         ops.gemm(h, w_down, partial, False, False, False)
 
     res = {"world": world, "tokens": T, "hidden": H, "ffn": F,
-           "ag_gemm_fused_ms": timed(ag_gemm_fused), "ag_gemm_pipelined_ms": timed(ag_gemm_pipelined), "ag_gemm_pipelined_spare16_ms": timed(lambda: ag_gemm_pipelined(16)),
+           "ag_gemm_fused_ms": timed(ag_gemm_fused), "ag_gemm_pipelined_ms": timed(ag_gemm_pipelined), "ag_gemm_pipelined_spare8_ms": timed(lambda: ag_gemm_pipelined(8)),
            "max_connections_env": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
            "wait_gemm_only_ms": timed(wait_gemm_only), "gather_only_ms": timed(gather_only), "concurrent_independent_ms": timed(concurrent_independent), "ag_gemm_nccl_ms": timed(ag_gemm_nccl), "gemm_up_only_ms": timed(gemm_only_up),
            "gemm_rs_fused_ms": timed(gemm_rs_fused), "gemm_rs_nccl_ms": timed(gemm_rs_nccl), "gemm_down_only_ms": timed(gemm_only_down)}

@@ -13,9 +13,9 @@ from d9d_b200.internals.nvlink import SymmetricArena
 from .._native import fused_wgrad_buffer, fused_wgrad_owner, grad_dtype_of, native_ops
 
 
-# the flag-gated GEMM is persistent (one CTA per SM, ~226 KiB of shared memory each): the copy / flag / barrier kernels
-# of the concurrent pull chain need SMs of their own or the two would dead-lock
-_PIPELINE_SPARE_SMS = 8
+# SMs the flag-gated GEMM leaves to the concurrent pull chain (measured: the small copy / flag / barrier kernels co-reside
+# with the persistent GEMM CTAs, no SMs need to be set aside)
+_PIPELINE_SPARE_SMS = 0
 _DIRECT_PEER_LOAD_MAX_N = 512  # output width up to which A tiles are loaded directly from the peers (few re-reads)
 
 
@@ -31,6 +31,7 @@ class TensorParallelWorkspace:
         self.rank = group.rank()
         self._arenas: dict[str, SymmetricArena] = {}
         self._side: torch.cuda.Stream | None = None
+        self._warmed: set[tuple] = set()
 
     @classmethod
     def for_group(cls, group: dist.ProcessGroup) -> "TensorParallelWorkspace":
@@ -80,7 +81,12 @@ class TensorParallelWorkspace:
         view[:, self.rank].copy_(local.view(batch, block_rows, cols))
         ready = torch.cuda.Event()
         ready.record(main)
-        if consumer is not None:
+        # CUDA loads kernels lazily and a first-time load waits for the device to drain: if the consumer is already
+        # spinning on a flag that one of the not-yet-loaded side kernels must raise, that dead-locks.  The first call of
+        # every kernel combination therefore runs the pull chain to completion before launching the consumer.
+        warm_key = (name, batch > 1, local.dtype)
+        warmed = warm_key in self._warmed
+        if consumer is not None and warmed:
             consumer(gathered, flags)
         self._side.wait_event(ready)
         for t in (gathered, flags, local):
@@ -93,6 +99,11 @@ class TensorParallelWorkspace:
                 r = (self.rank + step) % self.world
                 view[:, r].copy_(arena.peer_view(r, (rows_local * cols,))[: rows_local * cols].view(batch, block_rows, cols))
                 flags[r : r + 1].fill_(1)
+        if not warmed:
+            self._warmed.add(warm_key)
+            main.wait_stream(self._side)
+            if consumer is not None:
+                consumer(gathered, flags)
         return gathered, flags
 
     def join(self) -> None:
