@@ -37,12 +37,14 @@ def _local_norm_pow(params: list[nn.Parameter], norm_type: float, device: torch.
 
 
 def clip_grad_norm_distributed_(parameter_groups: ParametersForNorm, max_norm: float | None, norm_type: float,
-                                pp_mesh: DeviceMesh | None) -> torch.Tensor:
+                                pp_mesh: DeviceMesh | None, pending_scale: torch.Tensor | None = None) -> torch.Tensor:
     """Global gradient norm over every parallel dimension, then in-place clipping (tensor coefficient, no host sync).
 
     Sharded groups all-reduce their ``||g||^p`` over the mesh they are sharded on (async, launched first);
     replicated groups contribute locally; finally one scalar all-reduce over the pipeline dimension.
-    ``max_norm=None`` only measures.  Parity: reference ``d9d/internals/grad_norm/norm.py:99-139``.
+    ``max_norm=None`` only measures.  ``pending_scale`` (device scalar) is a factor that has not been applied to the
+    gradients yet: the norm is reported for the scaled gradients and the clip coefficient is multiplied into it instead
+    of rewriting every gradient.  Parity: reference ``d9d/internals/grad_norm/norm.py:99-139``.
     """
     with record_function("Gradient Clipping"):
         device = _device_of(parameter_groups)
@@ -65,8 +67,13 @@ def clip_grad_norm_distributed_(parameter_groups: ParametersForNorm, max_norm: f
         if pp_mesh is not None:
             dist.all_reduce(total_pow, op=_reduce_op(norm_type), group=pp_mesh.get_group())
         total = total_pow if math.isinf(norm_type) else total_pow ** (1.0 / norm_type)
+        if pending_scale is not None:
+            total = total * pending_scale.reshape(()).abs()
         if max_norm:
             coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
-            for params in parameter_groups.values():
-                torch._foreach_mul_([_local_grad(p) for p in params], coef)  # noqa: SLF001
+            if pending_scale is not None:
+                pending_scale.mul_(coef)
+            else:
+                for params in parameter_groups.values():
+                    torch._foreach_mul_([_local_grad(p) for p in params], coef)  # noqa: SLF001
         return total

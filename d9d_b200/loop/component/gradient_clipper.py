@@ -21,6 +21,11 @@ class GradientClipper:
         self._ctx, self._modules, self._config, self._stepper = dist_context, tracked_modules, config, stepper
         self._groups: ParametersForNorm | None = None
         self._external_owners: list = []
+        self._gradient_manager = None
+
+    def bind_gradient_manager(self, gradient_manager: object) -> None:
+        """Lets the clipper see (and extend) a gradient scale the manager has deferred to the optimizer."""
+        self._gradient_manager = gradient_manager
         self.last_norm = None  # device tensor of the most recent global norm
 
     @contextmanager
@@ -53,7 +58,9 @@ class GradientClipper:
                 run.scalar(name="l2_grad_norm_total", value=norm.item())
             return
         pp_mesh = self._ctx.mesh_for(REGULAR_DOMAIN)["pp"] if self._ctx.mesh_params.is_distributed else None
-        norm = clip_grad_norm_distributed_(parameter_groups=self._groups, max_norm=self._config.max_norm, norm_type=2.0, pp_mesh=pp_mesh)
+        pending = self._gradient_manager.pending_scale if self._gradient_manager is not None else None
+        norm = clip_grad_norm_distributed_(parameter_groups=self._groups, max_norm=self._config.max_norm, norm_type=2.0, pp_mesh=pp_mesh,
+                                           pending_scale=pending)
         self.last_norm = norm
         if should_log:
             run.scalar(name="l2_grad_norm_total", value=norm.item())

@@ -38,6 +38,22 @@ class GradientManager:
                                           require_accumulations=batch_maths.num_backward_calls)
         self._installed = False
         self._external_owners: list = []
+        self._scale_sinks: list = []  # optimizers whose update kernel multiplies gradients by a device scalar
+        self._pending_scale: torch.Tensor | None = None
+
+    def bind_optimizer(self, optimizer: object) -> None:
+        """Let the manager hand its gradient scale to the optimizer(s) instead of rewriting the gradients."""
+        leaves = list(getattr(optimizer, "optimizers", [optimizer]))
+        if self._config.fold_scaling_into_optimizer and leaves and all(hasattr(o, "grad_scale") and not hasattr(o, "set_grad_scale") for o in leaves):
+            self._scale_sinks = leaves
+            self._pending_scale = torch.ones(1, dtype=torch.float32, device=self._ctx.current_device)
+            for o in leaves:
+                o.grad_scale = self._pending_scale
+
+    @property
+    def pending_scale(self) -> torch.Tensor | None:
+        """Device scalar that still has to be applied to every gradient (None: gradients are already scaled)."""
+        return self._pending_scale
 
     def _apply_grad_dtype(self) -> None:
         if self._config.grad_dtype is None:
@@ -93,7 +109,9 @@ class GradientManager:
             self._loss.sync(self._ctx)
         grads = self._local_grads()
         inv = 1.0 / self._loss.accumulated_weight
-        if grads:
+        if self._pending_scale is not None:
+            self._pending_scale.copy_(inv.reshape(-1)[:1])  # consumed by the optimizer kernel (and the clipper)
+        elif grads:
             torch._foreach_mul_(grads, inv)  # noqa: SLF001  tensor scalar: no host sync
         for owner in self._external_owners:
             owner.set_grad_scale(inv)  # applied inside the NVLink update kernel after the cross-replica reduction

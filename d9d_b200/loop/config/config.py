@@ -63,6 +63,9 @@ class JobLoggerConfig(BaseModel):
 class GradientManagerConfig(BaseModel):
     grad_dtype: str | None  # None => parameter dtype
     bucket_size_mb: int
+    # fold the 1/sum(weights) scaling and the clip coefficient into the optimizer's gradient-scale input instead of
+    # rewriting every gradient twice (only when every optimizer accepts a device ``grad_scale``, e.g. StochasticAdamW)
+    fold_scaling_into_optimizer: bool = True
 
 
 class TimeoutConfig(BaseModel):

@@ -123,6 +123,8 @@ class TrainingConfigurator:
         profiler = JobProfiler(dist_context=ctx, stepper=stepper, config=cfg.profiling)
         exporter = ModelStageExporter(model_provider=self._model_provider, dist_context=ctx, modules=modules)
         grad_manager = GradientManager(dist_context=ctx, tracked_modules=modules, batch_maths=maths, config=cfg.gradient_manager)
+        grad_manager.bind_optimizer(optimizer)
+        clipper.bind_gradient_manager(grad_manager)
         logger = JobLogger(dist_context=ctx, config=cfg.logging, metrics=metrics, stepper=stepper, run_config=cfg.run,
                            additional_hparams={"task": task.dump_hparams(), "model": self._model_provider.dump_hparams()})
         return TrainJobState(dist_context=ctx, data_loader=loader, stepper=stepper, tracked_modules=modules, garbage_collector=gc,

@@ -9,7 +9,8 @@ from tests.dist_utils import run_distributed
 from tests.helpers_train import LMProvider, SFTTask, SyntheticDataProvider, dense_params, moe_params, trainer_config
 
 
-def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable", total_batch=8, micro=4, log=True, samples=64):
+def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable", total_batch=8, micro=4, log=True, samples=64,
+                  optimizer=None, fold_scaling=True, dtype=torch.float32):
     from d9d_b200.core.dist_context import DeviceMeshParameters
     from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
     from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
@@ -22,13 +23,21 @@ def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable
     return TrainingConfigurator(
         mesh=mesh or DeviceMeshParameters(),
         parameters=trainer_config(tmp, total_batch=total_batch, micro=micro, schedule=schedule, ckpt_period=ckpt_period,
-                                  log_dir=(tmp / "logs") if log else None),
+                                  log_dir=(tmp / "logs") if log else None).model_copy(update={}, deep=True)
+        if fold_scaling else _without_folding(trainer_config(tmp, total_batch=total_batch, micro=micro, schedule=schedule,
+                                                             ckpt_period=ckpt_period, log_dir=(tmp / "logs") if log else None)),
         task_provider=lambda ctx: SFTTask(),
-        model_provider=LMProvider(moe_params() if moe else dense_params(), moe=moe),
+        model_provider=LMProvider(moe_params() if moe else dense_params(), moe=moe, dtype=dtype),
         data_provider=SyntheticDataProvider(num_samples=samples),
-        optimizer_provider=AutoOptimizerProvider(AdamWOptimizerConfig(lr=3e-3, weight_decay=0.0)),
+        optimizer_provider=AutoOptimizerProvider(optimizer or AdamWOptimizerConfig(lr=3e-3, weight_decay=0.0)),
         lr_scheduler_provider=AutoLRSchedulerProvider(sched),
     ).configure()
+
+
+def _without_folding(cfg):
+    cfg = cfg.model_copy(deep=True)
+    cfg.gradient_manager.fold_scaling_into_optimizer = False
+    return cfg
 
 
 def _read_losses(tmp):
@@ -129,3 +138,21 @@ def test_dp_matches_single_process(tmp_path):
     # samples are distributed differently (round-robin sharding) so per-step batches differ; the totals must be close
     # and the first step (same init, different but same-sized batch) must be within noise
     assert abs(ref[0] - got[0]) < 0.2
+
+
+def test_folding_the_gradient_scale_into_the_optimizer_changes_nothing(tmp_path):
+    """1/sum(w) and the clip coefficient handed to StochasticAdamW as a device scalar == rewriting the gradients."""
+    from d9d_b200.loop.auto.auto_optimizer import StochasticAdamWOptimizerConfig
+
+    finals = []
+    for fold in (True, False):
+        opt = StochasticAdamWOptimizerConfig(lr=3e-3, weight_decay=0.0, state_dtype="float32")
+        trainer = _make_trainer(tmp_path / f"fold{fold}", optimizer=opt, fold_scaling=fold, log=False, dtype=torch.bfloat16)
+        assert (trainer.state.gradient_manager.pending_scale is not None) == fold
+        trainer.train()
+        finals.append({k: v.detach().clone() for k, v in trainer.state.tracked_modules.modules[0].state_dict().items()})
+    # identical maths up to fp32 association order; a handful of stochastic-rounding decisions may flip by one bf16 ulp
+    a = torch.cat([v.float().flatten() for v in finals[0].values()])
+    b = torch.cat([finals[1][k].float().flatten() for k in finals[0]])
+    assert float((a != b).float().mean()) < 0.02
+    torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2)
