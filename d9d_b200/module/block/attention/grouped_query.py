@@ -3,6 +3,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from d9d_b200.kernel.rope.fused_qk import fused_qk_norm_rope_supported, qk_norm_rope
 from d9d_b200.module.base import ModuleLateInit
 from d9d_b200.module.block.attention.sdpa import FlashSdpa
 from d9d_b200.module.block.linear import Linear
@@ -61,15 +62,20 @@ class GroupedQueryAttention(nn.Module, ModuleLateInit):
         q = self.q_proj(hidden_states).view(per_head)
         k = self.k_proj(hidden_states).view(per_head)
         v = self.v_proj(hidden_states).view(per_head)
-        if self.q_norm is not None:
-            q = self.q_norm(q)
-        if self.k_norm is not None:
-            k = self.k_norm(k)
-
         cos, sin = position_embeddings
-        # the rope kernel rotates the first cos.shape[-1] dims of each head and passes the rest through,
-        # so partial RoPE needs no split/cat
-        q, k = self.rope(q, k, cos, sin)
+        if (self.q_norm is not None and self.k_norm is not None
+                and fused_qk_norm_rope_supported(q, k, self.q_norm.weight, self.k_norm.weight, cos.shape[-1])):
+            # per-head RMSNorm of q and k + rotary embedding in one kernel
+            q, k = qk_norm_rope(q, k, self.q_norm.weight, self.k_norm.weight, cos, sin, self.q_norm.eps,
+                                self.q_norm.zero_centered, self.rope.style_code)
+        else:
+            if self.q_norm is not None:
+                q = self.q_norm(q)
+            if self.k_norm is not None:
+                k = self.k_norm(k)
+            # the rope kernel rotates the first cos.shape[-1] dims of each head and passes the rest through,
+            # so partial RoPE needs no split/cat
+            q, k = self.rope(q, k, cos, sin)
 
         out = self.kernel(q, k, v, attention_mask=attention_mask, is_causal=self._is_causal, scale=self._scaling)
         out = out.reshape(*lead, -1)

@@ -3,9 +3,9 @@ from __future__ import annotations
 import dataclasses
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
+from d9d_b200.kernel.router import route_topk
 from d9d_b200.module.base import ModuleLateInit
 from d9d_b200.module.block.linear import Linear
 
@@ -17,7 +17,8 @@ class RoutingResult:
 
 
 class TopKRouter(nn.Module, ModuleLateInit):
-    """Linear gate -> fp32 softmax over all experts -> top-k (optionally biased selection) -> optional renorm.
+    """Linear gate -> fp32 softmax over all experts -> top-k (optionally biased selection) -> optional renorm
+    (softmax / selection / renormalisation are one fused kernel on CUDA, ``ops/csrc/router.cu``).
 
     Parity: reference ``d9d/module/block/moe/router.py:24-107``.
     """
@@ -34,14 +35,7 @@ class TopKRouter(nn.Module, ModuleLateInit):
         self._renormalize = renormalize_probabilities
 
     def forward(self, hidden_states: torch.Tensor) -> RoutingResult:
-        probs = F.softmax(self.gate(hidden_states), dim=-1, dtype=torch.float32)
-        if self.expert_bias is None:
-            chosen_p, chosen = torch.topk(probs, k=self._top_k, dim=-1)
-        else:
-            chosen = torch.topk(probs + self.expert_bias, k=self._top_k, dim=-1).indices
-            chosen_p = probs.gather(-1, chosen)
-        if self._renormalize:
-            chosen_p = chosen_p / (chosen_p.sum(dim=-1, keepdim=True) + 1e-20)
+        chosen, chosen_p = route_topk(self.gate(hidden_states), self._top_k, self._renormalize, self.expert_bias)
         return RoutingResult(selected_expert_indices=chosen, selected_probabilities=chosen_p)
 
     def reset_parameters(self) -> None:

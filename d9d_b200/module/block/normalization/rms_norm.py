@@ -19,6 +19,14 @@ class RMSNorm(nn.Module, ModuleLateInit):
         self._zero_centered = zero_centered
         self.weight = nn.Parameter(torch.empty(hidden_size))
 
+    @property
+    def eps(self) -> float:
+        return self._eps
+
+    @property
+    def zero_centered(self) -> bool:
+        return self._zero_centered
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return rms_norm(x, self.weight, eps=self._eps, zero_centered=self._zero_centered)
 

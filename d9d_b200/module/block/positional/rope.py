@@ -90,6 +90,10 @@ class RotaryEmbeddingApplicator(nn.Module):
         self._style = style
         self._code = _style_code(style)
 
+    @property
+    def style_code(self) -> int:
+        return self._code
+
     def _rotate(self, x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
         if on_gpu(x) and x.dtype == torch.bfloat16 and x.shape[-1] % 64 == 0:
             rope_dim = cos.shape[-1]

@@ -337,6 +337,82 @@ void scale_inplace_(Tensor x, const Tensor& scale) {
 
 }  // namespace
 
+// ------------------------------------------------------------------ fused q/k RMSNorm + RoPE
+static void check_qk(const Tensor& q, const Tensor& k) {
+  TORCH_CHECK(q.is_cuda() && k.is_cuda() && q.dim() == 3 && k.dim() == 3 && q.scalar_type() == at::kBFloat16 &&
+              k.scalar_type() == at::kBFloat16, "qk_norm_rope: q/k must be bf16 [T, H, D]");
+  TORCH_CHECK(q.stride(2) == 1 && k.stride(2) == 1 && q.stride(1) == q.size(2) && k.stride(1) == k.size(2) &&
+              q.size(0) == k.size(0) && q.size(2) == k.size(2), "qk_norm_rope: heads must be densely packed");
+}
+
+std::tuple<Tensor, Tensor, Tensor> qk_norm_rope_fwd(const Tensor& q, const Tensor& k, const Tensor& wq, const Tensor& wk,
+                                                    const Tensor& cos_t, const Tensor& sin_t, double eps, bool zero_centered,
+                                                    int64_t style) {
+  check_qk(q, k);
+  CHECK_CUDA_CONTIG(wq); CHECK_CUDA_CONTIG(wk); CHECK_CUDA_CONTIG(cos_t); CHECK_CUDA_CONTIG(sin_t);
+  TORCH_CHECK(wq.scalar_type() == at::kBFloat16 && wk.scalar_type() == at::kBFloat16 && cos_t.scalar_type() == at::kFloat &&
+              sin_t.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(q.device());
+  const int64_t T = q.size(0), Hq = q.size(1), Hk = k.size(1), D = q.size(2), rope_dim = cos_t.size(-1);
+  TORCH_CHECK(cos_t.numel() == T * rope_dim && sin_t.numel() == T * rope_dim && wq.numel() == D && wk.numel() == D);
+  Tensor qo = at::empty({T, Hq, D}, q.options()), ko = at::empty({T, Hk, D}, k.options());
+  Tensor inv = at::empty({T, Hq + Hk}, q.options().dtype(at::kFloat));
+  d9d::qk_norm_rope_fwd(q.data_ptr(), k.data_ptr(), wq.data_ptr(), wk.data_ptr(), cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), T,
+                        static_cast<int>(Hq), static_cast<int>(Hk), static_cast<int>(D), static_cast<int>(rope_dim), q.stride(0),
+                        k.stride(0), static_cast<float>(eps), zero_centered, static_cast<int>(style), qo.data_ptr(), ko.data_ptr(),
+                        inv.data_ptr<float>(), cur_stream());
+  return {qo, ko, inv};
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor> qk_norm_rope_bwd(const Tensor& dq_out, const Tensor& dk_out, const Tensor& q, const Tensor& k,
+                                                            const Tensor& wq, const Tensor& wk, const Tensor& cos_t,
+                                                            const Tensor& sin_t, const Tensor& inv_rms, bool zero_centered,
+                                                            int64_t style) {
+  check_qk(q, k);
+  CHECK_CUDA_CONTIG(dq_out); CHECK_CUDA_CONTIG(dk_out); CHECK_CUDA_CONTIG(inv_rms);
+  c10::cuda::CUDAGuard guard(q.device());
+  const int64_t T = q.size(0), Hq = q.size(1), Hk = k.size(1), D = q.size(2), rope_dim = cos_t.size(-1);
+  Tensor dq = at::empty({T, Hq, D}, q.options()), dk = at::empty({T, Hk, D}, k.options());
+  const int grid = d9d::qk_norm_rope_grid(T, static_cast<int>(Hq + Hk));
+  auto fopt = q.options().dtype(at::kFloat);
+  Tensor partial = at::empty({grid, 2, D}, fopt), dwq = at::empty({D}, fopt), dwk = at::empty({D}, fopt);
+  d9d::qk_norm_rope_bwd(dq_out.data_ptr(), dk_out.data_ptr(), q.data_ptr(), k.data_ptr(), wq.data_ptr(), wk.data_ptr(),
+                        cos_t.data_ptr<float>(), sin_t.data_ptr<float>(), inv_rms.data_ptr<float>(), T, static_cast<int>(Hq),
+                        static_cast<int>(Hk), static_cast<int>(D), static_cast<int>(rope_dim), q.stride(0), k.stride(0), zero_centered,
+                        static_cast<int>(style), dq.data_ptr(), dk.data_ptr(), partial.data_ptr<float>(), dwq.data_ptr<float>(),
+                        dwk.data_ptr<float>(), cur_stream());
+  return {dq, dk, dwq, dwk};
+}
+
+// ------------------------------------------------------------------ MoE router
+std::tuple<Tensor, Tensor> router_topk_fwd(const Tensor& logits, const c10::optional<Tensor>& bias, int64_t k, bool renorm) {
+  CHECK_CUDA_CONTIG(logits);
+  TORCH_CHECK(logits.scalar_type() == at::kBFloat16 && logits.dim() == 2);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int64_t T = logits.size(0), E = logits.size(1);
+  const float* b = nullptr;
+  if (bias.has_value()) {
+    TORCH_CHECK(bias->is_cuda() && bias->is_contiguous() && bias->scalar_type() == at::kFloat && bias->numel() == E);
+    b = bias->data_ptr<float>();
+  }
+  Tensor idx = at::empty({T, k}, logits.options().dtype(at::kLong));
+  Tensor probs = at::empty({T, k}, logits.options().dtype(at::kFloat));
+  d9d::router_topk_fwd(logits.data_ptr(), b, T, static_cast<int>(E), static_cast<int>(k), renorm,
+                       reinterpret_cast<long long*>(idx.data_ptr<int64_t>()), probs.data_ptr<float>(), cur_stream());
+  return {idx, probs};
+}
+
+Tensor router_topk_bwd(const Tensor& logits, const Tensor& idx, const Tensor& dprobs, bool renorm) {
+  CHECK_CUDA_CONTIG(logits); CHECK_CUDA_CONTIG(idx); CHECK_CUDA_CONTIG(dprobs);
+  TORCH_CHECK(logits.scalar_type() == at::kBFloat16 && idx.scalar_type() == at::kLong && dprobs.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard guard(logits.device());
+  const int64_t T = logits.size(0), E = logits.size(1), k = idx.size(1);
+  Tensor out = at::empty_like(logits);
+  d9d::router_topk_bwd(logits.data_ptr(), reinterpret_cast<const long long*>(idx.data_ptr<int64_t>()), dprobs.data_ptr<float>(), T,
+                       static_cast<int>(E), static_cast<int>(k), renorm, out.data_ptr(), cur_stream());
+  return out;
+}
+
 // ------------------------------------------------------------------ tensor-parallel GEMMs with fused communication
 // peer pointer lists come from torch.distributed._symmetric_memory (handle.buffer_ptrs) plus a byte offset.
 static std::vector<const void*> to_ptrs(at::IntArrayRef v) {
@@ -485,6 +561,12 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_permute(Tensor x, Tensor? probs, Tensor row_map, Tensor counts, Tensor seg_offsets, int capacity) -> (Tensor, Tensor)");
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
+  m.def("qk_norm_rope_fwd(Tensor q, Tensor k, Tensor wq, Tensor wk, Tensor cos_t, Tensor sin_t, float eps, bool zero_centered, "
+        "int style) -> (Tensor, Tensor, Tensor)");
+  m.def("qk_norm_rope_bwd(Tensor dq_out, Tensor dk_out, Tensor q, Tensor k, Tensor wq, Tensor wk, Tensor cos_t, Tensor sin_t, "
+        "Tensor inv_rms, bool zero_centered, int style) -> (Tensor, Tensor, Tensor, Tensor)");
+  m.def("router_topk_fwd(Tensor logits, Tensor? bias, int k, bool renorm) -> (Tensor, Tensor)");
+  m.def("router_topk_bwd(Tensor logits, Tensor idx, Tensor dprobs, bool renorm) -> Tensor");
   m.def("gemm_ag_a(int[] a_peer_ptrs, int rows_local, int lda, int block_rows, Tensor b, Tensor(a!) d, bool b_mn) -> ()");
   m.def("gemm_wait_a(Tensor a, Tensor flags, int rank, int block_rows, Tensor b, Tensor(a!) d, bool b_mn, int spare_sms=0) -> ()");
   m.def("gemm_rs_d(Tensor a, Tensor b, int[] d_peer_ptrs, int rows_local, int ldd, int block_rows, bool b_mn) -> ()");
@@ -517,6 +599,10 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("moe_permute", &moe_permute);
   m.impl("moe_gather", &moe_gather);
   m.impl("sumsq_accumulate_", &sumsq_accumulate_);
+  m.impl("qk_norm_rope_fwd", &qk_norm_rope_fwd);
+  m.impl("qk_norm_rope_bwd", &qk_norm_rope_bwd);
+  m.impl("router_topk_fwd", &router_topk_fwd);
+  m.impl("router_topk_bwd", &router_topk_bwd);
   m.impl("gemm_ag_a", &gemm_ag_a);
   m.impl("gemm_wait_a", &gemm_wait_a);
   m.impl("gemm_rs_d", &gemm_rs_d);

@@ -125,6 +125,24 @@ void sumsq_accumulate(const void* x, long long n, int dtype, float* out, cudaStr
 // x *= *scale (device scalar)
 void scale_inplace(void* x, long long n, int dtype, const float* scale, cudaStream_t stream);
 
+// ------------------------------------------------------------------ fused q/k RMSNorm + RoPE -------------
+// q [T, Hq, D] (row stride ldq), k [T, Hk, D] (row stride ldk), cos/sin [T, rope_dim] fp32 (already gathered per token)
+int qk_norm_rope_grid(long long T, int Ht);  // number of blocks == rows of dw_partial
+void qk_norm_rope_fwd(const void* q, const void* k, const void* wq, const void* wk, const float* cos_t, const float* sin_t,
+                      long long T, int Hq, int Hk, int D, int rope_dim, long long ldq, long long ldk, float eps,
+                      bool zero_centered, int style, void* q_out, void* k_out, float* inv_rms, cudaStream_t s);
+void qk_norm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, const void* k, const void* wq, const void* wk,
+                      const float* cos_t, const float* sin_t, const float* inv_rms, long long T, int Hq, int Hk, int D,
+                      int rope_dim, long long ldq, long long ldk, bool zero_centered, int style, void* dq, void* dk,
+                      float* dw_partial, float* dwq, float* dwk, cudaStream_t s);
+
+// ------------------------------------------------------------------ MoE router -----------------------------
+// logits [T, E] bf16 -> softmax (fp32) -> top-k by (prob + bias) -> idx [T, k] int64, probs [T, k] fp32 (renormalised)
+void router_topk_fwd(const void* logits, const float* bias, long long T, int E, int k, bool renorm, long long* idx,
+                     float* probs, cudaStream_t stream);
+void router_topk_bwd(const void* logits, const long long* idx, const float* dprobs, long long T, int E, int k,
+                     bool renorm, void* dlogits, cudaStream_t stream);
+
 // ------------------------------------------------------------------ NVLink data-parallel optimizer -----------
 // peer_* : device array [world] of per-replica base pointers of the symmetric arena; mc_* : multicast (NVLS) mapping
 // of the same arena or nullptr.  [begin, end) is this rank's shard (multiples of 8 elements).

@@ -377,3 +377,66 @@ def test_gemm_split_k_accumulate(ops, M, N, K):
     d = d0.clone()
     ops.gemm(a, b, d, True, True, True)
     assert _rel_err(d, a.float().t() @ b.float() + d0) < 1e-4
+
+
+@pytest.mark.parametrize("E,k", [(128, 8), (8, 2), (64, 6), (200, 4), (1024, 32)])
+@pytest.mark.parametrize("renorm", [True, False])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_router_topk_matches_reference(ops, E, k, renorm, with_bias):
+    from d9d_b200.kernel.router import route_topk, route_topk_reference
+
+    torch.manual_seed(E + k)
+    T = 777
+    logits = (torch.randn(T, E, device="cuda") * 2).bfloat16()
+    bias = torch.randn(E, device="cuda") * 0.05 if with_bias else None
+    a = logits.clone().requires_grad_()
+    b = logits.clone().float().requires_grad_()
+    idx, probs = route_topk(a, k, renorm, bias)
+    ridx, rprobs = route_topk_reference(b, k, renorm, bias)
+    # compare as sets ordered by expert id (the order among the k selections is not part of the contract)
+    order, rorder = idx.argsort(-1), ridx.argsort(-1)
+    assert torch.equal(idx.gather(-1, order), ridx.gather(-1, rorder))
+    torch.testing.assert_close(probs.gather(-1, order), rprobs.gather(-1, rorder), rtol=1e-4, atol=1e-6)
+    w = torch.randn(T, k, device="cuda")
+    (probs.gather(-1, order) * w).sum().backward()
+    (rprobs.gather(-1, rorder) * w).sum().backward()
+    torch.testing.assert_close(a.grad.float(), b.grad, rtol=2e-2, atol=2e-3 * float(b.grad.abs().max()))
+
+
+@pytest.mark.parametrize("D,rope_dim", [(128, 128), (64, 64), (128, 64), (256, 256)])
+@pytest.mark.parametrize("style", [0, 1])
+@pytest.mark.parametrize("zero_centered", [False, True])
+def test_fused_qk_norm_rope_matches_unfused_reference(ops, D, rope_dim, style, zero_centered):
+    from d9d_b200.kernel.rope import rotate_reference
+    from d9d_b200.kernel.rope.fused_qk import qk_norm_rope
+
+    torch.manual_seed(D + style)
+    B, S, Hq, Hk = 2, 75, 6, 2
+    fused = torch.randn(B, S, (Hq + 2 * Hk) * D, device="cuda").bfloat16()  # q|k|v packed: exercises strided heads
+    q = fused[..., : Hq * D].reshape(B, S, Hq, D)
+    k = fused[..., Hq * D : (Hq + Hk) * D].reshape(B, S, Hk, D)
+    wq = (torch.randn(D, device="cuda") * 0.1 + (0.0 if zero_centered else 1.0)).bfloat16()
+    wk = (torch.randn(D, device="cuda") * 0.1 + (0.0 if zero_centered else 1.0)).bfloat16()
+    ang = torch.rand(B, S, rope_dim // 2, device="cuda") * 6.28
+    ang = torch.cat([ang, ang], -1) if style == 0 else ang.repeat_interleave(2, -1)
+    cos, sin = ang.cos(), ang.sin()
+
+    def reference(qf, kf, wqf, wkf):
+        def norm(x, w):
+            x = x.float()
+            r = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6)
+            return x * r * (w.float() + (1.0 if zero_centered else 0.0))
+        return (rotate_reference(norm(qf, wqf), cos, sin, style), rotate_reference(norm(kf, wkf), cos, sin, style))
+
+    leaves = [t.clone().requires_grad_() for t in (q, k, wq, wk)]
+    ref_leaves = [t.float().clone().requires_grad_() for t in (q, k, wq, wk)]
+    qo, ko = qk_norm_rope(*leaves, cos, sin, 1e-6, zero_centered, style)
+    rq, rk = reference(*ref_leaves)
+    torch.testing.assert_close(qo.float(), rq, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(ko.float(), rk, rtol=2e-2, atol=2e-2)
+    gq, gk = torch.randn_like(rq), torch.randn_like(rk)
+    torch.autograd.backward([qo, ko], [gq.bfloat16(), gk.bfloat16()])
+    torch.autograd.backward([rq, rk], [gq.bfloat16().float(), gk.bfloat16().float()])
+    for a, b, name in zip(leaves, ref_leaves, ("dq", "dk", "dwq", "dwk")):
+        scale = float(b.grad.abs().max())
+        torch.testing.assert_close(a.grad.float(), b.grad, rtol=3e-2, atol=3e-2 * scale, msg=lambda m: f"{name}: {m}")  # noqa: B023
