@@ -32,7 +32,7 @@ def fused_qk_norm_rope_supported(q: torch.Tensor, k: torch.Tensor, wq: torch.Ten
     d = q.shape[-1]
     return (on_gpu(q) and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and wq.dtype == torch.bfloat16
             and wk.dtype == torch.bfloat16 and d in (64, 128, 256) and k.shape[-1] == d and rope_dim <= d
-            and rope_dim % 2 == 0 and (rope_dim // 2) % (d // 32) == 0)
+            and rope_dim % 16 == 0)
 
 
 def qk_norm_rope(q: torch.Tensor, k: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,

@@ -9,151 +9,215 @@
 namespace d9d {
 namespace {
 
-template <int VEC>
-__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float (&v)[VEC]) {
+// Thread mapping: a head of D elements is owned by LPH = D / 8 consecutive lanes, 8 contiguous elements (16 bytes) per
+// lane, so one warp works on 32 / LPH heads at once; all reductions / exchanges are segmented xor-shuffles.
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int i = 0; i < VEC; i += 2) {
-    const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p + i));
-    v[i] = f.x; v[i + 1] = f.y;
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack_bf16x2(w[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
 
-template <int VEC>
-__device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&v)[VEC]) {
-#pragma unroll
-  for (int i = 0; i < VEC; i += 2) *reinterpret_cast<uint32_t*>(p + i) = pack_bf16x2(v[i], v[i + 1]);
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
 }
 
-// out = R(theta) v for the first rope_dim dims (inverse: R(-theta)); HALF pairs (e, e + rope_dim/2), INTERLEAVED (2i, 2i+1)
-template <int VEC>
-__device__ __forceinline__ void rotate(const float (&v)[VEC], float (&o)[VEC], const float* __restrict__ cp,
-                                       const float* __restrict__ sp, int lane, int rope_dim, int style, bool inverse) {
-  if (style == 0) {
+template <int LPH>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int off = LPH / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// out = R(theta) v on the first rope_dim dims (inverse: R(-theta)); `sub` = lane index inside the head group
+template <int LPH>
+__device__ __forceinline__ void rotate8(const float (&v)[8], float (&o)[8], const float* __restrict__ cp,
+                                        const float* __restrict__ sp, int sub, int rope_dim, int style, bool inverse) {
+  const int e0 = sub * 8;
+  if (style == 0) {  // HALF: element e pairs with e +/- rope_dim/2, i.e. the lane `half/8` further up / down
     const int half = rope_dim >> 1;
-    const int lane_shift = half / VEC;
+    const int lane_shift = half >> 3;
+    const bool low = e0 < half;
+    const int lane = threadIdx.x & 31;
+    const int src = low ? lane + lane_shift : lane - lane_shift;
+    float partner[8];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int e = lane * VEC + i;
-      const int src_lane = (e < half) ? lane + lane_shift : lane - lane_shift;
-      const float partner = __shfl_sync(0xffffffffu, v[i], src_lane & 31);
-      if (e < rope_dim) {
-        float s = sp[e];
-        if (inverse) s = -s;
-        o[i] = v[i] * cp[e] + ((e < half) ? -partner : partner) * s;
-      } else {
-        o[i] = v[i];
+    for (int i = 0; i < 8; ++i) partner[i] = __shfl_sync(0xffffffffu, v[i], src & 31);
+    if (e0 < rope_dim) {
+      const float4 c0 = *reinterpret_cast<const float4*>(cp + e0), c1 = *reinterpret_cast<const float4*>(cp + e0 + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(sp + e0), s1 = *reinterpret_cast<const float4*>(sp + e0 + 4);
+      const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float s = inverse ? -sn[i] : sn[i];
+        o[i] = v[i] * c[i] + (low ? -partner[i] : partner[i]) * s;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = v[i];
     }
-  } else {
+  } else {  // INTERLEAVED: pairs (2i, 2i+1) live in the same lane
+    if (e0 < rope_dim) {
 #pragma unroll
-    for (int i = 0; i < VEC; i += 2) {
-      const int e = lane * VEC + i;
-      if (e < rope_dim) {
-        float s0 = sp[e], s1 = sp[e + 1];
+      for (int i = 0; i < 8; i += 2) {
+        float s0 = sp[e0 + i], s1 = sp[e0 + i + 1];
         if (inverse) { s0 = -s0; s1 = -s1; }
-        o[i] = v[i] * cp[e] - v[i + 1] * s0;
-        o[i + 1] = v[i + 1] * cp[e + 1] + v[i] * s1;
-      } else {
-        o[i] = v[i]; o[i + 1] = v[i + 1];
+        o[i] = v[i] * cp[e0 + i] - v[i + 1] * s0;
+        o[i + 1] = v[i + 1] * cp[e0 + i + 1] + v[i] * s1;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = v[i];
     }
   }
 }
 
-template <int VEC>
+constexpr int ROWS_IN_FLIGHT = 2;  // independent (token, head) rows per head group per iteration (memory-level parallelism)
+
+template <int LPH>
 __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ wq,
     const __nv_bfloat16* __restrict__ wk, const float* __restrict__ cos_t, const float* __restrict__ sin_t, long long T,
     int Hq, int Hk, int rope_dim, long long ldq, long long ldk, float eps, bool zero_centered, int style,
     __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out, float* __restrict__ inv_rms) {
-  constexpr int D = VEC * 32;
-  const int lane = threadIdx.x & 31;
+  constexpr int D = LPH * 8;
+  constexpr int GROUPS = 32 / LPH;
+  const int lane = threadIdx.x & 31, sub = lane % LPH, grp = lane / LPH;
   const int Ht = Hq + Hk;
   const long long total = T * Ht;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float wqv[VEC], wkv[VEC];
-  load_vec<VEC>(wq + lane * VEC, wqv);
-  load_vec<VEC>(wk + lane * VEC, wkv);
+  const long long slot = ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * GROUPS + grp;
+  const long long slots = ((static_cast<long long>(gridDim.x) * blockDim.x) >> 5) * GROUPS;
+  float wqv[8], wkv[8];
+  load8(wq + sub * 8, wqv);
+  load8(wk + sub * 8, wkv);
   if (zero_centered) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { wqv[i] += 1.f; wkv[i] += 1.f; }
+    for (int i = 0; i < 8; ++i) { wqv[i] += 1.f; wkv[i] += 1.f; }
   }
-  for (long long idx = warp; idx < total; idx += warps) {
-    const long long t = idx / Ht;
-    const int h = static_cast<int>(idx - t * Ht);
-    const bool is_k = h >= Hq;
-    const __nv_bfloat16* src = is_k ? k + t * ldk + static_cast<long long>(h - Hq) * D : q + t * ldq + static_cast<long long>(h) * D;
-    __nv_bfloat16* dst = is_k ? k_out + (t * Hk + (h - Hq)) * D : q_out + (t * Hq + h) * D;
-    float v[VEC], y[VEC], o[VEC];
-    load_vec<VEC>(src + lane * VEC, v);
-    float ss = 0.f;
+  // all lanes of a warp run the same number of iterations (shuffles are warp-wide); out-of-range rows are predicated
+  const long long iters = (total + slots * ROWS_IN_FLIGHT - 1) / (slots * ROWS_IN_FLIGHT);
+  for (long long it = 0; it < iters; ++it) {
+    float v[ROWS_IN_FLIGHT][8];
+    long long idx[ROWS_IN_FLIGHT];
+    bool ok[ROWS_IN_FLIGHT], isk[ROWS_IN_FLIGHT];
+    long long tt[ROWS_IN_FLIGHT];
+    int hh[ROWS_IN_FLIGHT];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) ss += v[i] * v[i];
-    ss = warp_sum(ss);
-    const float r = rsqrtf(ss / D + eps);
+    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+      idx[u] = (it * ROWS_IN_FLIGHT + u) * slots + slot;
+      ok[u] = idx[u] < total;
+      const long long id = ok[u] ? idx[u] : 0;
+      tt[u] = id / Ht;
+      hh[u] = static_cast<int>(id - tt[u] * Ht);
+      isk[u] = hh[u] >= Hq;
+      const __nv_bfloat16* src = isk[u] ? k + tt[u] * ldk + static_cast<long long>(hh[u] - Hq) * D
+                                        : q + tt[u] * ldq + static_cast<long long>(hh[u]) * D;
+      load8(src + sub * 8, v[u]);
+    }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) y[i] = v[i] * r * (is_k ? wkv[i] : wqv[i]);
-    rotate<VEC>(y, o, cos_t + t * rope_dim, sin_t + t * rope_dim, lane, rope_dim, style, false);
-    store_vec<VEC>(dst + lane * VEC, o);
-    if (lane == 0) inv_rms[idx] = r;
+    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += v[u][i] * v[u][i];
+      ss = group_sum<LPH>(ss);
+      const float r = rsqrtf(ss / D + eps);
+      float y[8], o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = v[u][i] * r * (isk[u] ? wkv[i] : wqv[i]);
+      rotate8<LPH>(y, o, cos_t + tt[u] * rope_dim, sin_t + tt[u] * rope_dim, sub, rope_dim, style, false);
+      if (ok[u]) {
+        __nv_bfloat16* dst = isk[u] ? k_out + (tt[u] * Hk + (hh[u] - Hq)) * D : q_out + (tt[u] * Hq + hh[u]) * D;
+        store8(dst + sub * 8, o);
+        if (sub == 0) inv_rms[idx[u]] = r;
+      }
+    }
   }
 }
 
-template <int VEC>
+template <int LPH>
 __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(
     const __nv_bfloat16* __restrict__ dq_out, const __nv_bfloat16* __restrict__ dk_out, const __nv_bfloat16* __restrict__ q,
     const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
     const float* __restrict__ cos_t, const float* __restrict__ sin_t, const float* __restrict__ inv_rms, long long T, int Hq,
     int Hk, int rope_dim, long long ldq, long long ldk, bool zero_centered, int style, __nv_bfloat16* __restrict__ dq,
     __nv_bfloat16* __restrict__ dk, float* __restrict__ dw_partial /* [grid, 2, D] */) {
-  constexpr int D = VEC * 32;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int D = LPH * 8;
+  constexpr int GROUPS = 32 / LPH;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane % LPH, grp = lane / LPH;
   const int Ht = Hq + Hk;
   const long long total = T * Ht;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float wqv[VEC], wkv[VEC], accq[VEC], acck[VEC];
-  load_vec<VEC>(wq + lane * VEC, wqv);
-  load_vec<VEC>(wk + lane * VEC, wkv);
+  const long long slot = ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * GROUPS + grp;
+  const long long slots = ((static_cast<long long>(gridDim.x) * blockDim.x) >> 5) * GROUPS;
+  float wqv[8], wkv[8], accq[8], acck[8];
+  load8(wq + sub * 8, wqv);
+  load8(wk + sub * 8, wkv);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
+  for (int i = 0; i < 8; ++i) {
     if (zero_centered) { wqv[i] += 1.f; wkv[i] += 1.f; }
     accq[i] = 0.f; acck[i] = 0.f;
   }
-  for (long long idx = warp; idx < total; idx += warps) {
-    const long long t = idx / Ht;
-    const int h = static_cast<int>(idx - t * Ht);
-    const bool is_k = h >= Hq;
-    const __nv_bfloat16* xs = is_k ? k + t * ldk + static_cast<long long>(h - Hq) * D : q + t * ldq + static_cast<long long>(h) * D;
-    const long long off = is_k ? (t * Hk + (h - Hq)) * D : (t * Hq + h) * D;
-    const __nv_bfloat16* gs = (is_k ? dk_out : dq_out) + off;
-    float g[VEC], dy[VEC], x[VEC], dx[VEC];
-    load_vec<VEC>(gs + lane * VEC, g);
-    load_vec<VEC>(xs + lane * VEC, x);
-    rotate<VEC>(g, dy, cos_t + t * rope_dim, sin_t + t * rope_dim, lane, rope_dim, style, true);
-    const float r = inv_rms[idx];
-    float dot = 0.f;
+  const long long iters = (total + slots * ROWS_IN_FLIGHT - 1) / (slots * ROWS_IN_FLIGHT);
+  for (long long it = 0; it < iters; ++it) {
+    float g[ROWS_IN_FLIGHT][8], x[ROWS_IN_FLIGHT][8], rr[ROWS_IN_FLIGHT];
+    long long off[ROWS_IN_FLIGHT], tt[ROWS_IN_FLIGHT];
+    bool ok[ROWS_IN_FLIGHT], isk[ROWS_IN_FLIGHT];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float xhat = x[i] * r;
-      const float gw = dy[i] * (is_k ? wkv[i] : wqv[i]);
-      dot += gw * xhat;
-      if (is_k) acck[i] += dy[i] * xhat; else accq[i] += dy[i] * xhat;
-      dx[i] = gw;   // finished below once the row mean is known
-      x[i] = xhat;
+    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+      const long long idx = (it * ROWS_IN_FLIGHT + u) * slots + slot;
+      ok[u] = idx < total;
+      const long long id = ok[u] ? idx : 0;
+      tt[u] = id / Ht;
+      const int h = static_cast<int>(id - tt[u] * Ht);
+      isk[u] = h >= Hq;
+      const __nv_bfloat16* xs = isk[u] ? k + tt[u] * ldk + static_cast<long long>(h - Hq) * D : q + tt[u] * ldq + static_cast<long long>(h) * D;
+      off[u] = isk[u] ? (tt[u] * Hk + (h - Hq)) * D : (tt[u] * Hq + h) * D;
+      load8((isk[u] ? dk_out : dq_out) + off[u] + sub * 8, g[u]);
+      load8(xs + sub * 8, x[u]);
+      rr[u] = inv_rms[id];
     }
-    dot = warp_sum(dot) / D;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) dx[i] = r * (dx[i] - x[i] * dot);
-    store_vec<VEC>((is_k ? dk : dq) + off + lane * VEC, dx);
+    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+      float dy[8], dx[8];
+      rotate8<LPH>(g[u], dy, cos_t + tt[u] * rope_dim, sin_t + tt[u] * rope_dim, sub, rope_dim, style, true);
+      const float r = rr[u];
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xhat = x[u][i] * r;
+        const float gw = dy[i] * (isk[u] ? wkv[i] : wqv[i]);
+        dot += gw * xhat;
+        if (ok[u]) { if (isk[u]) acck[i] += dy[i] * xhat; else accq[i] += dy[i] * xhat; }
+        dx[i] = gw;
+        x[u][i] = xhat;
+      }
+      dot = group_sum<LPH>(dot) / D;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dx[i] = r * (dx[i] - x[u][i] * dot);
+      if (ok[u]) store8((isk[u] ? dk : dq) + off[u] + sub * 8, dx);
+    }
   }
-  // block-level reduction of the weight gradients: [8 warps][2][D] in shared memory -> one partial row per block
-  __shared__ float red[8][2][D];
+  // weight gradients: fold the head groups of a warp, then the 8 warps of the block, into one partial row per block
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    red[wid][0][lane * VEC + i] = accq[i];
-    red[wid][1][lane * VEC + i] = acck[i];
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int offl = LPH; offl < 32; offl <<= 1) {
+      accq[i] += __shfl_xor_sync(0xffffffffu, accq[i], offl);
+      acck[i] += __shfl_xor_sync(0xffffffffu, acck[i], offl);
+    }
+  }
+  __shared__ float red[8][2][D];
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[wid][0][sub * 8 + i] = accq[i];
+      red[wid][1][sub * 8 + i] = acck[i];
+    }
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 2 * D; e += blockDim.x) {
@@ -165,14 +229,23 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(
   }
 }
 
+// partial [blocks, 2, D] -> dwq[D], dwk[D]; one block per 32 columns, 8 row-lanes x 32 columns of threads
 __global__ void __launch_bounds__(256) qk_dw_reduce_kernel(const float* __restrict__ partial, int blocks, int D,
                                                            float* __restrict__ dwq, float* __restrict__ dwk) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= 2 * D) return;
-  const int which = e / D, d = e - which * D;
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);  // column in [0, 2D)
+  const int rl = threadIdx.x >> 5;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[(static_cast<long long>(b) * 2 + which) * D + d];
-  (which ? dwk : dwq)[d] = s;
+  if (col < 2 * D)
+    for (int b = rl; b < blocks; b += 8) s += partial[static_cast<long long>(b) * 2 * D + col];
+  __shared__ float sm[8][32];
+  sm[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && col < 2 * D) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+    if (col < D) dwq[col] = t; else dwk[col - D] = t;
+  }
 }
 
 inline int sms() {
@@ -182,16 +255,15 @@ inline int sms() {
 }
 
 inline void check_dims(int D, int rope_dim) {
-  const int vec = D / 32;
-  if ((D != 64 && D != 128 && D != 256) || rope_dim > D || rope_dim % 2 != 0 || (rope_dim / 2) % vec != 0)
-    throw std::runtime_error("d9d qk_norm_rope: head_dim must be 64/128/256 and rope_dim/2 a multiple of head_dim/32");
+  if ((D != 64 && D != 128 && D != 256) || rope_dim > D || rope_dim % 16 != 0)
+    throw std::runtime_error("d9d qk_norm_rope: head_dim must be 64/128/256 and rope_dim a multiple of 16");
 }
 
 }  // namespace
 
 int qk_norm_rope_grid(long long T, int Ht) {
-  long long blocks = (T * Ht + 7) / 8;
-  const long long cap = static_cast<long long>(sms()) * 8;
+  long long blocks = (T * Ht + 15) / 16;
+  const long long cap = static_cast<long long>(sms()) * 4;
   if (blocks > cap) blocks = cap;
   return static_cast<int>(blocks > 0 ? blocks : 1);
 }
@@ -206,7 +278,7 @@ void qk_norm_rope_fwd(const void* q, const void* k, const void* wq, const void* 
   qk_norm_rope_fwd_kernel<V><<<grid, 256, 0, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)wq, \
       (const __nv_bfloat16*)wk, cos_t, sin_t, T, Hq, Hk, rope_dim, ldq, ldk, eps, zero_centered, style,                 \
       (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_out, inv_rms)
-  if (D == 64) D9D_QKF(2); else if (D == 128) D9D_QKF(4); else D9D_QKF(8);
+  if (D == 64) D9D_QKF(8); else if (D == 128) D9D_QKF(16); else D9D_QKF(32);
 #undef D9D_QKF
 }
 
@@ -221,9 +293,9 @@ void qk_norm_rope_bwd(const void* dq_out, const void* dk_out, const void* q, con
   qk_norm_rope_bwd_kernel<V><<<grid, 256, 0, s>>>((const __nv_bfloat16*)dq_out, (const __nv_bfloat16*)dk_out,        \
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)wq, (const __nv_bfloat16*)wk, cos_t, sin_t, \
       inv_rms, T, Hq, Hk, rope_dim, ldq, ldk, zero_centered, style, (__nv_bfloat16*)dq, (__nv_bfloat16*)dk, dw_partial)
-  if (D == 64) D9D_QKB(2); else if (D == 128) D9D_QKB(4); else D9D_QKB(8);
+  if (D == 64) D9D_QKB(8); else if (D == 128) D9D_QKB(16); else D9D_QKB(32);
 #undef D9D_QKB
-  qk_dw_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, s>>>(dw_partial, grid, D, dwq, dwk);
+  qk_dw_reduce_kernel<<<(2 * D + 31) / 32, 256, 0, s>>>(dw_partial, grid, D, dwq, dwk);
 }
 
 }  // namespace d9d
