@@ -34,10 +34,11 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-// out = R(theta) v on the first rope_dim dims (inverse: R(-theta)); `sub` = lane index inside the head group
+// out = R(theta) v on the first rope_dim dims (inverse: R(-theta)); `sub` = lane index inside the head group.
+// c / sn hold cos / sin of this lane's 8 elements (loaded once per token and reused for every head).
 template <int LPH>
-__device__ __forceinline__ void rotate8(const float (&v)[8], float (&o)[8], const float* __restrict__ cp,
-                                        const float* __restrict__ sp, int sub, int rope_dim, int style, bool inverse) {
+__device__ __forceinline__ void rotate8(const float (&v)[8], float (&o)[8], const float (&c)[8], const float (&sn)[8], int sub,
+                                        int rope_dim, int style, bool inverse) {
   const int e0 = sub * 8;
   if (style == 0) {  // HALF: element e pairs with e +/- rope_dim/2, i.e. the lane `half/8` further up / down
     const int half = rope_dim >> 1;
@@ -48,38 +49,41 @@ __device__ __forceinline__ void rotate8(const float (&v)[8], float (&o)[8], cons
     float partner[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) partner[i] = __shfl_sync(0xffffffffu, v[i], src & 31);
-    if (e0 < rope_dim) {
-      const float4 c0 = *reinterpret_cast<const float4*>(cp + e0), c1 = *reinterpret_cast<const float4*>(cp + e0 + 4);
-      const float4 s0 = *reinterpret_cast<const float4*>(sp + e0), s1 = *reinterpret_cast<const float4*>(sp + e0 + 4);
-      const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float s = inverse ? -sn[i] : sn[i];
-        o[i] = v[i] * c[i] + (low ? -partner[i] : partner[i]) * s;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = v[i];
+    for (int i = 0; i < 8; ++i) {
+      const float s = inverse ? -sn[i] : sn[i];
+      o[i] = (e0 < rope_dim) ? v[i] * c[i] + (low ? -partner[i] : partner[i]) * s : v[i];
     }
   } else {  // INTERLEAVED: pairs (2i, 2i+1) live in the same lane
-    if (e0 < rope_dim) {
 #pragma unroll
-      for (int i = 0; i < 8; i += 2) {
-        float s0 = sp[e0 + i], s1 = sp[e0 + i + 1];
-        if (inverse) { s0 = -s0; s1 = -s1; }
-        o[i] = v[i] * cp[e0 + i] - v[i + 1] * s0;
-        o[i + 1] = v[i + 1] * cp[e0 + i + 1] + v[i] * s1;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = v[i];
+    for (int i = 0; i < 8; i += 2) {
+      const float s0 = inverse ? -sn[i] : sn[i], s1 = inverse ? -sn[i + 1] : sn[i + 1];
+      o[i] = (e0 < rope_dim) ? v[i] * c[i] - v[i + 1] * s0 : v[i];
+      o[i + 1] = (e0 < rope_dim) ? v[i + 1] * c[i + 1] + v[i] * s1 : v[i + 1];
     }
+  }
+}
+
+__device__ __forceinline__ void load_angles(const float* __restrict__ cos_t, const float* __restrict__ sin_t, long long t,
+                                            int rope_dim, int sub, float (&c)[8], float (&sn)[8]) {
+  const int e0 = sub * 8;
+  if (e0 < rope_dim) {
+    const float4 c0 = *reinterpret_cast<const float4*>(cos_t + t * rope_dim + e0);
+    const float4 c1 = *reinterpret_cast<const float4*>(cos_t + t * rope_dim + e0 + 4);
+    const float4 s0 = *reinterpret_cast<const float4*>(sin_t + t * rope_dim + e0);
+    const float4 s1 = *reinterpret_cast<const float4*>(sin_t + t * rope_dim + e0 + 4);
+    c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+    sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i] = 1.f; sn[i] = 0.f; }
   }
 }
 
 constexpr int ROWS_IN_FLIGHT = 2;  // independent (token, head) rows per head group per iteration (memory-level parallelism)
 
+// One warp per token: cos / sin of the token are loaded once and reused for all of its q and k heads; the head groups of
+// the warp walk the heads ROWS_IN_FLIGHT at a time.
 template <int LPH>
 __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ wq,
@@ -90,9 +94,8 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(
   constexpr int GROUPS = 32 / LPH;
   const int lane = threadIdx.x & 31, sub = lane % LPH, grp = lane / LPH;
   const int Ht = Hq + Hk;
-  const long long total = T * Ht;
-  const long long slot = ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * GROUPS + grp;
-  const long long slots = ((static_cast<long long>(gridDim.x) * blockDim.x) >> 5) * GROUPS;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   float wqv[8], wkv[8];
   load8(wq + sub * 8, wqv);
   load8(wk + sub * 8, wkv);
@@ -100,41 +103,39 @@ __global__ void __launch_bounds__(256) qk_norm_rope_fwd_kernel(
 #pragma unroll
     for (int i = 0; i < 8; ++i) { wqv[i] += 1.f; wkv[i] += 1.f; }
   }
-  // all lanes of a warp run the same number of iterations (shuffles are warp-wide); out-of-range rows are predicated
-  const long long iters = (total + slots * ROWS_IN_FLIGHT - 1) / (slots * ROWS_IN_FLIGHT);
-  for (long long it = 0; it < iters; ++it) {
-    float v[ROWS_IN_FLIGHT][8];
-    long long idx[ROWS_IN_FLIGHT];
-    bool ok[ROWS_IN_FLIGHT], isk[ROWS_IN_FLIGHT];
-    long long tt[ROWS_IN_FLIGHT];
-    int hh[ROWS_IN_FLIGHT];
+  const int head_iters = (Ht + GROUPS * ROWS_IN_FLIGHT - 1) / (GROUPS * ROWS_IN_FLIGHT);  // warp-uniform trip count
+  for (long long t = warp; t < T; t += warps) {
+    float c[8], sn[8];
+    load_angles(cos_t, sin_t, t, rope_dim, sub, c, sn);
+    for (int hi = 0; hi < head_iters; ++hi) {
+      float v[ROWS_IN_FLIGHT][8];
+      int hh[ROWS_IN_FLIGHT];
+      bool ok[ROWS_IN_FLIGHT], isk[ROWS_IN_FLIGHT];
 #pragma unroll
-    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
-      idx[u] = (it * ROWS_IN_FLIGHT + u) * slots + slot;
-      ok[u] = idx[u] < total;
-      const long long id = ok[u] ? idx[u] : 0;
-      tt[u] = id / Ht;
-      hh[u] = static_cast<int>(id - tt[u] * Ht);
-      isk[u] = hh[u] >= Hq;
-      const __nv_bfloat16* src = isk[u] ? k + tt[u] * ldk + static_cast<long long>(hh[u] - Hq) * D
-                                        : q + tt[u] * ldq + static_cast<long long>(hh[u]) * D;
-      load8(src + sub * 8, v[u]);
-    }
+      for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+        hh[u] = (hi * ROWS_IN_FLIGHT + u) * GROUPS + grp;
+        ok[u] = hh[u] < Ht;
+        const int h = ok[u] ? hh[u] : 0;
+        isk[u] = h >= Hq;
+        const __nv_bfloat16* src = isk[u] ? k + t * ldk + static_cast<long long>(h - Hq) * D : q + t * ldq + static_cast<long long>(h) * D;
+        load8(src + sub * 8, v[u]);
+      }
 #pragma unroll
-    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
-      float ss = 0.f;
+      for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+        float ss = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ss += v[u][i] * v[u][i];
-      ss = group_sum<LPH>(ss);
-      const float r = rsqrtf(ss / D + eps);
-      float y[8], o[8];
+        for (int i = 0; i < 8; ++i) ss += v[u][i] * v[u][i];
+        ss = group_sum<LPH>(ss);
+        const float r = rsqrtf(ss / D + eps);
+        float y[8], o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = v[u][i] * r * (isk[u] ? wkv[i] : wqv[i]);
-      rotate8<LPH>(y, o, cos_t + tt[u] * rope_dim, sin_t + tt[u] * rope_dim, sub, rope_dim, style, false);
-      if (ok[u]) {
-        __nv_bfloat16* dst = isk[u] ? k_out + (tt[u] * Hk + (hh[u] - Hq)) * D : q_out + (tt[u] * Hq + hh[u]) * D;
-        store8(dst + sub * 8, o);
-        if (sub == 0) inv_rms[idx[u]] = r;
+        for (int i = 0; i < 8; ++i) y[i] = v[u][i] * r * (isk[u] ? wkv[i] : wqv[i]);
+        rotate8<LPH>(y, o, c, sn, sub, rope_dim, style, false);
+        if (ok[u]) {
+          __nv_bfloat16* dst = isk[u] ? k_out + (t * Hk + (hh[u] - Hq)) * D : q_out + (t * Hq + hh[u]) * D;
+          store8(dst + sub * 8, o);
+          if (sub == 0) inv_rms[t * Ht + hh[u]] = r;
+        }
       }
     }
   }
@@ -151,9 +152,8 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(
   constexpr int GROUPS = 32 / LPH;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, sub = lane % LPH, grp = lane / LPH;
   const int Ht = Hq + Hk;
-  const long long total = T * Ht;
-  const long long slot = ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * GROUPS + grp;
-  const long long slots = ((static_cast<long long>(gridDim.x) * blockDim.x) >> 5) * GROUPS;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   float wqv[8], wkv[8], accq[8], acck[8];
   load8(wq + sub * 8, wqv);
   load8(wk + sub * 8, wkv);
@@ -162,44 +162,46 @@ __global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(
     if (zero_centered) { wqv[i] += 1.f; wkv[i] += 1.f; }
     accq[i] = 0.f; acck[i] = 0.f;
   }
-  const long long iters = (total + slots * ROWS_IN_FLIGHT - 1) / (slots * ROWS_IN_FLIGHT);
-  for (long long it = 0; it < iters; ++it) {
-    float g[ROWS_IN_FLIGHT][8], x[ROWS_IN_FLIGHT][8], rr[ROWS_IN_FLIGHT];
-    long long off[ROWS_IN_FLIGHT], tt[ROWS_IN_FLIGHT];
-    bool ok[ROWS_IN_FLIGHT], isk[ROWS_IN_FLIGHT];
+  const int head_iters = (Ht + GROUPS * ROWS_IN_FLIGHT - 1) / (GROUPS * ROWS_IN_FLIGHT);
+  for (long long t = warp; t < T; t += warps) {
+    float c[8], sn[8];
+    load_angles(cos_t, sin_t, t, rope_dim, sub, c, sn);
+    for (int hi = 0; hi < head_iters; ++hi) {
+      float g[ROWS_IN_FLIGHT][8], x[ROWS_IN_FLIGHT][8], rr[ROWS_IN_FLIGHT];
+      long long off[ROWS_IN_FLIGHT];
+      bool ok[ROWS_IN_FLIGHT], isk[ROWS_IN_FLIGHT];
 #pragma unroll
-    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
-      const long long idx = (it * ROWS_IN_FLIGHT + u) * slots + slot;
-      ok[u] = idx < total;
-      const long long id = ok[u] ? idx : 0;
-      tt[u] = id / Ht;
-      const int h = static_cast<int>(id - tt[u] * Ht);
-      isk[u] = h >= Hq;
-      const __nv_bfloat16* xs = isk[u] ? k + tt[u] * ldk + static_cast<long long>(h - Hq) * D : q + tt[u] * ldq + static_cast<long long>(h) * D;
-      off[u] = isk[u] ? (tt[u] * Hk + (h - Hq)) * D : (tt[u] * Hq + h) * D;
-      load8((isk[u] ? dk_out : dq_out) + off[u] + sub * 8, g[u]);
-      load8(xs + sub * 8, x[u]);
-      rr[u] = inv_rms[id];
-    }
-#pragma unroll
-    for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
-      float dy[8], dx[8];
-      rotate8<LPH>(g[u], dy, cos_t + tt[u] * rope_dim, sin_t + tt[u] * rope_dim, sub, rope_dim, style, true);
-      const float r = rr[u];
-      float dot = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xhat = x[u][i] * r;
-        const float gw = dy[i] * (isk[u] ? wkv[i] : wqv[i]);
-        dot += gw * xhat;
-        if (ok[u]) { if (isk[u]) acck[i] += dy[i] * xhat; else accq[i] += dy[i] * xhat; }
-        dx[i] = gw;
-        x[u][i] = xhat;
+      for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+        const int hraw = (hi * ROWS_IN_FLIGHT + u) * GROUPS + grp;
+        ok[u] = hraw < Ht;
+        const int h = ok[u] ? hraw : 0;
+        isk[u] = h >= Hq;
+        const __nv_bfloat16* xs = isk[u] ? k + t * ldk + static_cast<long long>(h - Hq) * D : q + t * ldq + static_cast<long long>(h) * D;
+        off[u] = isk[u] ? (t * Hk + (h - Hq)) * D : (t * Hq + h) * D;
+        load8((isk[u] ? dk_out : dq_out) + off[u] + sub * 8, g[u]);
+        load8(xs + sub * 8, x[u]);
+        rr[u] = inv_rms[t * Ht + h];
       }
-      dot = group_sum<LPH>(dot) / D;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dx[i] = r * (dx[i] - x[u][i] * dot);
-      if (ok[u]) store8((isk[u] ? dk : dq) + off[u] + sub * 8, dx);
+      for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+        float dy[8], dx[8];
+        rotate8<LPH>(g[u], dy, c, sn, sub, rope_dim, style, true);
+        const float r = rr[u];
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xhat = x[u][i] * r;
+          const float gw = dy[i] * (isk[u] ? wkv[i] : wqv[i]);
+          dot += gw * xhat;
+          if (ok[u]) { if (isk[u]) acck[i] += dy[i] * xhat; else accq[i] += dy[i] * xhat; }
+          dx[i] = gw;
+          x[u][i] = xhat;
+        }
+        dot = group_sum<LPH>(dot) / D;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dx[i] = r * (dx[i] - x[u][i] * dot);
+        if (ok[u]) store8((isk[u] ? dk : dq) + off[u] + sub * 8, dx);
+      }
     }
   }
   // weight gradients: fold the head groups of a warp, then the 8 warps of the block, into one partial row per block
@@ -262,8 +264,9 @@ inline void check_dims(int D, int rope_dim) {
 }  // namespace
 
 int qk_norm_rope_grid(long long T, int Ht) {
-  long long blocks = (T * Ht + 15) / 16;
-  const long long cap = static_cast<long long>(sms()) * 4;
+  (void)Ht;
+  long long blocks = (T + 7) / 8;  // one warp per token
+  const long long cap = static_cast<long long>(sms()) * 8;
   if (blocks > cap) blocks = cap;
   return static_cast<int>(blocks > 0 ? blocks : 1);
 }
