@@ -1,5 +1,8 @@
+"""LR-scheduler provider driven by a discriminated pydantic config (``name`` selects the family)."""
+
 from __future__ import annotations
 
+from collections.abc import Callable
 from typing import Annotated, Literal
 
 from pydantic import BaseModel, Field
@@ -16,12 +19,16 @@ class PiecewiseConfig(BaseModel):
 
 AutoLRSchedulerConfig = Annotated[PiecewiseConfig, Field(discriminator="name")]
 
+_BUILDERS: dict[type, Callable[[BaseModel, InitializeLRSchedulerContext], LRSchedulerProtocol]] = {
+    PiecewiseConfig: lambda cfg, ctx: piecewise_scheduler_from_config(cfg.scheduler, optimizer=ctx.optimizer, total_steps=ctx.total_steps),
+}
+
 
 class AutoLRSchedulerProvider(LRSchedulerProvider):
     def __init__(self, config: PiecewiseConfig):
+        if type(config) not in _BUILDERS:
+            raise ValueError(f"Unsupported LR scheduler type: {config}")
         self._config = config
 
     def __call__(self, context: InitializeLRSchedulerContext) -> LRSchedulerProtocol:
-        if isinstance(self._config, PiecewiseConfig):
-            return piecewise_scheduler_from_config(self._config.scheduler, optimizer=context.optimizer, total_steps=context.total_steps)
-        raise ValueError(f"Unsupported LR scheduler type: {self._config}")
+        return _BUILDERS[type(self._config)](self._config, context)

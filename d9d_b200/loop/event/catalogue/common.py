@@ -1,32 +1,34 @@
+"""Payloads shared by both loops (defined in ``contexts.py``) and the helper that mints namespaced events."""
+
 from __future__ import annotations
 
-import dataclasses
-from typing import TYPE_CHECKING
+from typing import TypeVar
 
-from torch import nn
-from torch.utils.data import DataLoader
+from d9d_b200.loop.event import Event
 
-from d9d_b200.core.dist_context import DistributedContext
+from .contexts import (
+    EventConfigurationStartedContext,
+    EventDataLoaderReadyContext,
+    EventModelStagesReadyContext,
+    EventStepContext,
+)
 
-if TYPE_CHECKING:
-    from d9d_b200.loop.component import Stepper
-
-
-@dataclasses.dataclass(kw_only=True)
-class EventStepContext:
-    stepper: "Stepper"
+T = TypeVar("T")
 
 
-@dataclasses.dataclass(kw_only=True)
-class EventConfigurationStartedContext:
-    dist_context: DistributedContext
+def namespaced(namespace: str):
+    """``make = namespaced("train"); make("step.pre", EventStepContext)`` -> ``Event[EventStepContext]("train.step.pre")``."""
+
+    def make(name: str, payload: type[T]) -> Event[T]:
+        return Event[payload](id=f"{namespace}.{name}")  # type: ignore[valid-type]
+
+    return make
 
 
-@dataclasses.dataclass(kw_only=True)
-class EventDataLoaderReadyContext:
-    data_loader: DataLoader
-
-
-@dataclasses.dataclass(kw_only=True)
-class EventModelStagesReadyContext:
-    modules: list[nn.Module]
+__all__ = [
+    "EventConfigurationStartedContext",
+    "EventDataLoaderReadyContext",
+    "EventModelStagesReadyContext",
+    "EventStepContext",
+    "namespaced",
+]

@@ -1,33 +1,26 @@
+"""Events of ``Inference``: three configuration events, ``ready``, per batch ``step.pre`` → ``forward.pre/post`` →
+``step.post``, and ``finished``."""
+
 from __future__ import annotations
 
-import dataclasses
-
-from d9d_b200.loop.event import Event
-
-from .common import (
+from .common import namespaced
+from .contexts import (
     EventConfigurationStartedContext,
     EventDataLoaderReadyContext,
+    EventInferenceFinishedContext,
+    EventInferenceReadyContext,
     EventModelStagesReadyContext,
     EventStepContext,
 )
 
+_infer = namespaced("inference")
 
-@dataclasses.dataclass(kw_only=True)
-class EventInferenceReadyContext:
-    pass
+EVENT_INFERENCE_CONFIG_STARTED = _infer("configuration.start", EventConfigurationStartedContext)
+EVENT_INFERENCE_DATA_LOADER_READY = _infer("configuration.data_loader", EventDataLoaderReadyContext)
+EVENT_INFERENCE_MODEL_STAGES_READY = _infer("configuration.model_stages", EventModelStagesReadyContext)
+EVENT_INFERENCE_READY = _infer("ready", EventInferenceReadyContext)
+EVENT_INFERENCE_STEP_PRE, EVENT_INFERENCE_STEP_POST = (_infer(f"step.{edge}", EventStepContext) for edge in ("pre", "post"))
+EVENT_INFERENCE_FORWARD_PRE, EVENT_INFERENCE_FORWARD_POST = (_infer(f"forward.{edge}", EventStepContext) for edge in ("pre", "post"))
+EVENT_INFERENCE_FINISHED = _infer("finished", EventInferenceFinishedContext)
 
-
-@dataclasses.dataclass(kw_only=True)
-class EventInferenceFinishedContext:
-    pass
-
-
-EVENT_INFERENCE_CONFIG_STARTED = Event[EventConfigurationStartedContext](id="inference.configuration.start")
-EVENT_INFERENCE_DATA_LOADER_READY = Event[EventDataLoaderReadyContext](id="inference.configuration.data_loader")
-EVENT_INFERENCE_MODEL_STAGES_READY = Event[EventModelStagesReadyContext](id="inference.configuration.model_stages")
-EVENT_INFERENCE_READY = Event[EventInferenceReadyContext](id="inference.ready")
-EVENT_INFERENCE_STEP_PRE = Event[EventStepContext](id="inference.step.pre")
-EVENT_INFERENCE_STEP_POST = Event[EventStepContext](id="inference.step.post")
-EVENT_INFERENCE_FORWARD_PRE = Event[EventStepContext](id="inference.forward.pre")
-EVENT_INFERENCE_FORWARD_POST = Event[EventStepContext](id="inference.forward.post")
-EVENT_INFERENCE_FINISHED = Event[EventInferenceFinishedContext](id="inference.finished")
+__all__ = [name for name in dir() if name.startswith(("EVENT_INFERENCE_", "Event"))]

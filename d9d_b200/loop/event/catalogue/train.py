@@ -1,51 +1,34 @@
+"""Events of ``Trainer`` in firing order: five configuration events, then per step ``step.pre`` →
+``forward_backward.pre/post`` → ``optimizer_step.pre/post`` → ``step.post``, finally ``finished``."""
+
 from __future__ import annotations
 
-import dataclasses
-
-from d9d_b200.core.protocol import LRSchedulerProtocol, OptimizerProtocol
-from d9d_b200.loop.event import Event
-from d9d_b200.tracker import BaseTrackerRun
-
-from .common import (
+from .common import namespaced
+from .contexts import (
     EventConfigurationStartedContext,
     EventDataLoaderReadyContext,
+    EventLRSchedulerReadyContext,
     EventModelStagesReadyContext,
+    EventOptimizerReadyContext,
     EventStepContext,
+    EventTrainFinishedContext,
+    EventTrainReadyContext,
 )
 
+_train = namespaced("train")
 
-@dataclasses.dataclass(kw_only=True)
-class EventOptimizerReadyContext:
-    optimizer: OptimizerProtocol
+EVENT_TRAIN_CONFIG_STARTED = _train("configuration.start", EventConfigurationStartedContext)
+EVENT_TRAIN_DATA_LOADER_READY = _train("configuration.data_loader", EventDataLoaderReadyContext)
+EVENT_TRAIN_MODEL_STAGES_READY = _train("configuration.model_stages", EventModelStagesReadyContext)
+EVENT_TRAIN_OPTIMIZER_READY = _train("configuration.optimizer", EventOptimizerReadyContext)
+EVENT_TRAIN_LR_SCHEDULER_READY = _train("configuration.lr_scheduler", EventLRSchedulerReadyContext)
 
+EVENT_TRAIN_READY = _train("ready", EventTrainReadyContext)
+EVENT_TRAIN_STEP_PRE, EVENT_TRAIN_STEP_POST = (_train(f"step.{edge}", EventStepContext) for edge in ("pre", "post"))
+EVENT_TRAIN_FORWARD_BACKWARD_PRE, EVENT_TRAIN_FORWARD_BACKWARD_POST = (
+    _train(f"forward_backward.{edge}", EventStepContext) for edge in ("pre", "post"))
+EVENT_TRAIN_OPTIMIZER_STEP_PRE, EVENT_TRAIN_OPTIMIZER_STEP_POST = (
+    _train(f"optimizer_step.{edge}", EventStepContext) for edge in ("pre", "post"))
+EVENT_TRAIN_FINISHED = _train("finished", EventTrainFinishedContext)
 
-@dataclasses.dataclass(kw_only=True)
-class EventLRSchedulerReadyContext:
-    lr_scheduler: LRSchedulerProtocol
-
-
-@dataclasses.dataclass(kw_only=True)
-class EventTrainReadyContext:
-    run: BaseTrackerRun
-
-
-@dataclasses.dataclass(kw_only=True)
-class EventTrainFinishedContext:
-    pass
-
-
-# configuration
-EVENT_TRAIN_CONFIG_STARTED = Event[EventConfigurationStartedContext](id="train.configuration.start")
-EVENT_TRAIN_DATA_LOADER_READY = Event[EventDataLoaderReadyContext](id="train.configuration.data_loader")
-EVENT_TRAIN_MODEL_STAGES_READY = Event[EventModelStagesReadyContext](id="train.configuration.model_stages")
-EVENT_TRAIN_OPTIMIZER_READY = Event[EventOptimizerReadyContext](id="train.configuration.optimizer")
-EVENT_TRAIN_LR_SCHEDULER_READY = Event[EventLRSchedulerReadyContext](id="train.configuration.lr_scheduler")
-# runtime
-EVENT_TRAIN_READY = Event[EventTrainReadyContext](id="train.ready")
-EVENT_TRAIN_STEP_PRE = Event[EventStepContext](id="train.step.pre")
-EVENT_TRAIN_STEP_POST = Event[EventStepContext](id="train.step.post")
-EVENT_TRAIN_FORWARD_BACKWARD_PRE = Event[EventStepContext](id="train.forward_backward.pre")
-EVENT_TRAIN_FORWARD_BACKWARD_POST = Event[EventStepContext](id="train.forward_backward.post")
-EVENT_TRAIN_OPTIMIZER_STEP_PRE = Event[EventStepContext](id="train.optimizer_step.pre")
-EVENT_TRAIN_OPTIMIZER_STEP_POST = Event[EventStepContext](id="train.optimizer_step.post")
-EVENT_TRAIN_FINISHED = Event[EventTrainFinishedContext](id="train.finished")
+__all__ = [name for name in dir() if name.startswith(("EVENT_TRAIN_", "Event"))]

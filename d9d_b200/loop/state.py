@@ -34,72 +34,56 @@ from d9d_b200.loop.event import EventBus
 from d9d_b200.metric.impl.container import ComposeMetric
 
 
-@dataclasses.dataclass(kw_only=True)
-class JobState(Stateful):
-    dist_context: DistributedContext
-    stepper: Stepper
-    garbage_collector: ManualGarbageCollector
-    checkpointer: StateCheckpointer
-    profiler: JobProfiler
-    tracked_modules: TrackedModules
-    batch_maths: BatchMaths
-    data_loader: StatefulDataLoader
-    timeout_manager: TimeoutManager
+class _CheckpointedFields(Stateful):
+    """``state_dict`` / ``load_state_dict`` derived from ``CHECKPOINTED``: the names of the fields that are Stateful and
+    belong in a job checkpoint (subclasses extend the tuple)."""
+
+    CHECKPOINTED: tuple[str, ...] = ()
 
     def state_dict(self) -> dict[str, Any]:
-        return {
-            "stepper": self.stepper.state_dict(),
-            "tracked_modules": self.tracked_modules.state_dict(),
-            "data_loader": self.data_loader.state_dict(),
-        }
+        return {name: getattr(self, name).state_dict() for name in self.CHECKPOINTED}
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        self.stepper.load_state_dict(state_dict["stepper"])
-        self.tracked_modules.load_state_dict(state_dict["tracked_modules"])
-        self.data_loader.load_state_dict(state_dict["data_loader"])
+        for name in self.CHECKPOINTED:
+            getattr(self, name).load_state_dict(state_dict[name])
+
+
+@dataclasses.dataclass(kw_only=True)
+class JobState(_CheckpointedFields):
+    """What training and inference jobs share."""
+
+    CHECKPOINTED = ("stepper", "tracked_modules", "data_loader")
+
+    dist_context: DistributedContext
+    event_bus: EventBus
+    stepper: Stepper
+    tracked_modules: TrackedModules
+    data_loader: StatefulDataLoader
+    batch_maths: BatchMaths
+    checkpointer: StateCheckpointer
+    garbage_collector: ManualGarbageCollector
+    profiler: JobProfiler
+    timeout_manager: TimeoutManager
 
 
 @dataclasses.dataclass(kw_only=True)
 class TrainJobState(JobState):
+    CHECKPOINTED = (*JobState.CHECKPOINTED, "logger", "task", "metrics", "optimizer", "lr_scheduler")
+
     task: TrainTask
-    gradient_manager: GradientManager
-    metrics: ComposeMetric
     task_operator: TrainTaskOperator
+    metrics: ComposeMetric
     logger: JobLogger
     optimizer: OptimizerProtocol
     lr_scheduler: LRSchedulerProtocol
+    gradient_manager: GradientManager
     gradient_clipper: GradientClipper
     exporter: ModelStageExporter
-    event_bus: EventBus
-
-    def state_dict(self) -> dict[str, Any]:
-        return {
-            **super().state_dict(),
-            "logger": self.logger.state_dict(),
-            "task": self.task.state_dict(),
-            "metrics": self.metrics.state_dict(),
-            "optimizer": self.optimizer.state_dict(),
-            "lr_scheduler": self.lr_scheduler.state_dict(),
-        }
-
-    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        super().load_state_dict(state_dict)
-        self.logger.load_state_dict(state_dict["logger"])
-        self.task.load_state_dict(state_dict["task"])
-        self.metrics.load_state_dict(state_dict["metrics"])
-        self.optimizer.load_state_dict(state_dict["optimizer"])
-        self.lr_scheduler.load_state_dict(state_dict["lr_scheduler"])
 
 
 @dataclasses.dataclass(kw_only=True)
 class InferenceJobState(JobState):
+    CHECKPOINTED = (*JobState.CHECKPOINTED, "task")
+
     task: InferenceTask
     task_operator: InferenceTaskOperator
-    event_bus: EventBus
-
-    def state_dict(self) -> dict[str, Any]:
-        return {**super().state_dict(), "task": self.task.state_dict()}
-
-    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        super().load_state_dict(state_dict)
-        self.task.load_state_dict(state_dict["task"])

@@ -1,39 +1,13 @@
-"""Pydantic parameters of the Llama3 family."""
+"""Hyper-parameters of the Llama3 family (classes generated from the shared field sets in ``module/model/_params.py``)."""
 
-from pydantic import BaseModel
+from d9d_b200.module.model._params import DenseLayerFields, family_parameters
 
+_generated = family_parameters("Llama3", DenseLayerFields, __name__)
 
-class Llama3LayerParameters(BaseModel):
-    hidden_size: int
-    intermediate_size: int
-    num_attention_heads: int
-    num_key_value_heads: int
-    rms_norm_eps: float
-    head_dim: int
+Llama3LayerParameters = _generated["Llama3LayerParameters"]
+Llama3Parameters = _generated["Llama3Parameters"]
+Llama3ForCausalLMParameters = _generated["Llama3ForCausalLMParameters"]
+Llama3ForClassificationParameters = _generated["Llama3ForClassificationParameters"]
+Llama3ForEmbeddingParameters = _generated["Llama3ForEmbeddingParameters"]
 
-
-class Llama3Parameters(BaseModel):
-    layer: Llama3LayerParameters
-    num_hidden_layers: int
-    rope_base: int
-    max_position_ids: int
-    split_vocab_size: dict[str, int]
-    split_vocab_order: list[str]
-    pipeline_num_virtual_layers_pre: int = 0
-    pipeline_num_virtual_layers_post: int = 0
-
-
-class Llama3ForCausalLMParameters(BaseModel):
-    model: Llama3Parameters
-
-
-class Llama3ForClassificationParameters(BaseModel):
-    model: Llama3Parameters
-    num_labels: int
-    classifier_dropout: float
-
-
-class Llama3ForEmbeddingParameters(BaseModel):
-    model: Llama3Parameters
-    embedding_dim: int | None = None
-    normalize: bool = False
+__all__ = list(_generated)

@@ -1,41 +1,13 @@
-"""Pydantic parameters of the Mixtral family."""
+"""Hyper-parameters of the Mixtral family (classes generated from the shared field sets in ``module/model/_params.py``)."""
 
-from pydantic import BaseModel
+from d9d_b200.module.model._params import MoELayerFields, family_parameters
 
+_generated = family_parameters("Mixtral", MoELayerFields, __name__)
 
-class MixtralLayerParameters(BaseModel):
-    hidden_size: int
-    intermediate_size: int
-    num_experts: int
-    experts_top_k: int
-    num_attention_heads: int
-    num_key_value_heads: int
-    rms_norm_eps: float
-    head_dim: int
+MixtralLayerParameters = _generated["MixtralLayerParameters"]
+MixtralParameters = _generated["MixtralParameters"]
+MixtralForCausalLMParameters = _generated["MixtralForCausalLMParameters"]
+MixtralForClassificationParameters = _generated["MixtralForClassificationParameters"]
+MixtralForEmbeddingParameters = _generated["MixtralForEmbeddingParameters"]
 
-
-class MixtralParameters(BaseModel):
-    layer: MixtralLayerParameters
-    num_hidden_layers: int
-    rope_base: int
-    max_position_ids: int
-    split_vocab_size: dict[str, int]
-    split_vocab_order: list[str]
-    pipeline_num_virtual_layers_pre: int = 0
-    pipeline_num_virtual_layers_post: int = 0
-
-
-class MixtralForCausalLMParameters(BaseModel):
-    model: MixtralParameters
-
-
-class MixtralForClassificationParameters(BaseModel):
-    model: MixtralParameters
-    num_labels: int
-    classifier_dropout: float
-
-
-class MixtralForEmbeddingParameters(BaseModel):
-    model: MixtralParameters
-    embedding_dim: int | None = None
-    normalize: bool = False
+__all__ = list(_generated)

@@ -1,39 +1,13 @@
-"""Pydantic parameters of the Qwen3Dense family."""
+"""Hyper-parameters of the Qwen3Dense family (classes generated from the shared field sets in ``module/model/_params.py``)."""
 
-from pydantic import BaseModel
+from d9d_b200.module.model._params import DenseLayerFields, family_parameters
 
+_generated = family_parameters("Qwen3Dense", DenseLayerFields, __name__)
 
-class Qwen3DenseLayerParameters(BaseModel):
-    hidden_size: int
-    intermediate_size: int
-    num_attention_heads: int
-    num_key_value_heads: int
-    rms_norm_eps: float
-    head_dim: int
+Qwen3DenseLayerParameters = _generated["Qwen3DenseLayerParameters"]
+Qwen3DenseParameters = _generated["Qwen3DenseParameters"]
+Qwen3DenseForCausalLMParameters = _generated["Qwen3DenseForCausalLMParameters"]
+Qwen3DenseForClassificationParameters = _generated["Qwen3DenseForClassificationParameters"]
+Qwen3DenseForEmbeddingParameters = _generated["Qwen3DenseForEmbeddingParameters"]
 
-
-class Qwen3DenseParameters(BaseModel):
-    layer: Qwen3DenseLayerParameters
-    num_hidden_layers: int
-    rope_base: int
-    max_position_ids: int
-    split_vocab_size: dict[str, int]
-    split_vocab_order: list[str]
-    pipeline_num_virtual_layers_pre: int = 0
-    pipeline_num_virtual_layers_post: int = 0
-
-
-class Qwen3DenseForCausalLMParameters(BaseModel):
-    model: Qwen3DenseParameters
-
-
-class Qwen3DenseForClassificationParameters(BaseModel):
-    model: Qwen3DenseParameters
-    num_labels: int
-    classifier_dropout: float
-
-
-class Qwen3DenseForEmbeddingParameters(BaseModel):
-    model: Qwen3DenseParameters
-    embedding_dim: int | None = None
-    normalize: bool = False
+__all__ = list(_generated)

@@ -1,41 +1,13 @@
-"""Pydantic parameters of the Qwen3MoE family."""
+"""Hyper-parameters of the Qwen3MoE family (classes generated from the shared field sets in ``module/model/_params.py``)."""
 
-from pydantic import BaseModel
+from d9d_b200.module.model._params import MoELayerFields, family_parameters
 
+_generated = family_parameters("Qwen3MoE", MoELayerFields, __name__)
 
-class Qwen3MoELayerParameters(BaseModel):
-    hidden_size: int
-    intermediate_size: int
-    num_experts: int
-    experts_top_k: int
-    num_attention_heads: int
-    num_key_value_heads: int
-    rms_norm_eps: float
-    head_dim: int
+Qwen3MoELayerParameters = _generated["Qwen3MoELayerParameters"]
+Qwen3MoEParameters = _generated["Qwen3MoEParameters"]
+Qwen3MoEForCausalLMParameters = _generated["Qwen3MoEForCausalLMParameters"]
+Qwen3MoEForClassificationParameters = _generated["Qwen3MoEForClassificationParameters"]
+Qwen3MoEForEmbeddingParameters = _generated["Qwen3MoEForEmbeddingParameters"]
 
-
-class Qwen3MoEParameters(BaseModel):
-    layer: Qwen3MoELayerParameters
-    num_hidden_layers: int
-    rope_base: int
-    max_position_ids: int
-    split_vocab_size: dict[str, int]
-    split_vocab_order: list[str]
-    pipeline_num_virtual_layers_pre: int = 0
-    pipeline_num_virtual_layers_post: int = 0
-
-
-class Qwen3MoEForCausalLMParameters(BaseModel):
-    model: Qwen3MoEParameters
-
-
-class Qwen3MoEForClassificationParameters(BaseModel):
-    model: Qwen3MoEParameters
-    num_labels: int
-    classifier_dropout: float
-
-
-class Qwen3MoEForEmbeddingParameters(BaseModel):
-    model: Qwen3MoEParameters
-    embedding_dim: int | None = None
-    normalize: bool = False
+__all__ = list(_generated)

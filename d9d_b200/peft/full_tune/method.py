@@ -9,21 +9,24 @@ from .config import FullTuneConfig
 
 
 class FullTune(PeftMethod[FullTuneConfig]):
-    """Marks every parameter of the modules whose name full-matches the pattern as trainable; no structural change."""
+    """No structural change: the parameters of every module whose qualified name full-matches the pattern become the
+    trainable set (each parameter once, even if several matching modules share it)."""
 
     def __init__(self, config: FullTuneConfig):
-        self._config = config
-
-    def inject(self, module: nn.Module) -> PeftInjectionResult:
-        train: list[nn.Parameter] = []
-        for name, mod in module.named_modules():
-            if self._config.module_name_pattern.fullmatch(name):
-                train.extend(mod.parameters())
-        return PeftInjectionResult(parameters_to_train=train, load_state_mappers=[])
-
-    def merge(self, module: nn.Module) -> None:
-        return None
+        self._pattern = config.module_name_pattern
 
     @classmethod
     def from_config(cls, config: FullTuneConfig) -> Self:
         return cls(config)
+
+    def inject(self, module: nn.Module) -> PeftInjectionResult:
+        selected: dict[int, nn.Parameter] = {}
+        for name, sub in module.named_modules():
+            if self._pattern.fullmatch(name) is None:
+                continue
+            for p in sub.parameters():
+                selected.setdefault(id(p), p)
+        return PeftInjectionResult(parameters_to_train=list(selected.values()), load_state_mappers=[])
+
+    def merge(self, module: nn.Module) -> None:
+        """Nothing was injected, so there is nothing to fold back."""

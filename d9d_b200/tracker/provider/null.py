@@ -1,10 +1,11 @@
+"""Tracker that drops everything (non-main ranks, unit tests, benchmarks)."""
+
 from __future__ import annotations
 
-from collections.abc import Generator
+from collections.abc import Iterator
 from contextlib import contextmanager
 from typing import Any, Literal, Self
 
-import torch
 from pydantic import BaseModel
 
 from d9d_b200.tracker.base import BaseTracker, BaseTrackerRun, RunConfig
@@ -15,28 +16,26 @@ class NullTrackerConfig(BaseModel):
 
 
 class NullRun(BaseTrackerRun):
-    def set_step(self, step: int) -> None: ...
+    def _discard(self, *args: Any, **kwargs: Any) -> None:
+        return None
 
-    def set_context(self, context: dict[str, str]) -> None: ...
+    set_step = set_context = scalar = bins = _discard  # type: ignore[assignment]
 
-    def scalar(self, name: str, value: float, context: dict[str, str] | None = None) -> None: ...
 
-    def bins(self, name: str, values: torch.Tensor, context: dict[str, str] | None = None) -> None: ...
+_THE_RUN = NullRun()
 
 
 class NullTracker(BaseTracker[NullTrackerConfig]):
-    """Discards everything (non-main ranks, tests)."""
-
-    @contextmanager
-    def open(self, properties: RunConfig) -> Generator[BaseTrackerRun, None, None]:
-        yield NullRun()
-
     @classmethod
     def from_config(cls, config: NullTrackerConfig) -> Self:
         return cls()
 
-    def state_dict(self) -> dict[str, Any]:
-        return {}
+    @contextmanager
+    def open(self, properties: RunConfig) -> Iterator[BaseTrackerRun]:
+        yield _THE_RUN
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        return None
+        del state_dict
+
+    def state_dict(self) -> dict[str, Any]:
+        return {}
