@@ -1,5 +1,7 @@
 from __future__ import annotations
 
+import math
+
 import torch
 import torch.distributed as dist
 
@@ -32,9 +34,9 @@ def _exchange_shapes(tensor: torch.Tensor, group: dist.ProcessGroup) -> list[tup
     for i, s in enumerate(tensor.shape):
         desc[i + 1] = s
     desc = desc.to(tensor.device)
-    everyone = torch.empty(group.size(), _MAX_NDIM + 1, dtype=torch.long, device=tensor.device)
+    everyone = torch.empty(group.size() * (_MAX_NDIM + 1), dtype=torch.long, device=tensor.device)
     dist.all_gather_into_tensor(everyone, desc, group=group)
-    rows = everyone.cpu().tolist()
+    rows = everyone.view(group.size(), _MAX_NDIM + 1).cpu().tolist()
     return [tuple(int(v) for v in row[1 : 1 + int(row[0])]) for row in rows]
 
 
@@ -43,8 +45,15 @@ def all_gather_variadic_shape(
 ) -> list[torch.Tensor] | tuple[list[torch.Tensor], dist.Work]:
     """All-gather of tensors whose shapes differ per rank (the shape exchange itself is synchronous)."""
     shapes = _exchange_shapes(tensor, group)
-    sink = [torch.empty(shape, dtype=tensor.dtype, device=tensor.device) for shape in shapes]
-    work = dist.all_gather(sink, tensor, group=group, async_op=async_op)
+    # one equal-size collective on a buffer padded to the largest shard (uneven list all-gathers are not portable
+    # across backends); the results are views into the gathered buffer
+    sizes = [math.prod(shape) for shape in shapes]
+    width = max(max(sizes), 1)
+    padded = tensor.new_zeros(width)
+    padded[: tensor.numel()] = tensor.reshape(-1)
+    gathered = tensor.new_empty(group.size() * width)
+    work = dist.all_gather_into_tensor(gathered, padded, group=group, async_op=async_op)
+    sink = [gathered[r * width : r * width + n].view(shape) for r, (n, shape) in enumerate(zip(sizes, shapes, strict=True))]
     return (sink, work) if async_op else sink
 
 
