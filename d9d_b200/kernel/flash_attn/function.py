@@ -96,10 +96,14 @@ def flash_attn_func(
 ) -> tuple[torch.Tensor, torch.Tensor | None]:
     """Returns ``(output [B,S,H,Dv], lse [B,H,S] or None)``."""
     del num_splits, pack_gqa, deterministic
-    if not return_lse and _fast_path_ok(q, k, causal, window_size, learnable_sink, softcap):
-        from .native import flash_attention
+    if _fast_path_ok(q, k, causal, window_size, learnable_sink, softcap):
+        from .native import flash_attention, flash_attention_forward, native_forward_supported
 
-        return flash_attention(q, k, v, softmax_scale, causal), None
+        needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+        if return_lse and not needs_grad and native_forward_supported(q, k, v):
+            return flash_attention_forward(q, k, v, softmax_scale, causal)
+        if not return_lse:
+            return flash_attention(q, k, v, softmax_scale, causal), None
     out, lse = attention_reference(q, k, v, softmax_scale, causal, window_size, learnable_sink, softcap)
     return out, (lse if return_lse else None)
 

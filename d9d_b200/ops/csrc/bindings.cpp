@@ -337,6 +337,22 @@ void scale_inplace_(Tensor x, const Tensor& scale) {
 
 }  // namespace
 
+// ------------------------------------------------------------------ flash attention forward
+std::tuple<Tensor, Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal) {
+  CHECK_CUDA_CONTIG(q); CHECK_CUDA_CONTIG(k); CHECK_CUDA_CONTIG(v);
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "flash_attn_fwd: [B, S, H, D] tensors expected");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(k.sizes() == v.sizes() && q.size(0) == k.size(0) && q.size(3) == k.size(3));
+  c10::cuda::CUDAGuard guard(q.device());
+  const int B = static_cast<int>(q.size(0)), Sq = static_cast<int>(q.size(1)), Hq = static_cast<int>(q.size(2)), D = static_cast<int>(q.size(3));
+  const int Sk = static_cast<int>(k.size(1)), Hk = static_cast<int>(k.size(2));
+  Tensor out = at::empty_like(q);
+  Tensor lse = at::empty({B, Hq, Sq}, q.options().dtype(at::kFloat));
+  d9d::flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), B, Sq, Sk, Hq, Hk, D,
+                      static_cast<float>(scale), causal, cur_stream());
+  return {out, lse};
+}
+
 // ------------------------------------------------------------------ fused q/k RMSNorm + RoPE
 static void check_qk(const Tensor& q, const Tensor& k) {
   TORCH_CHECK(q.is_cuda() && k.is_cuda() && q.dim() == 3 && k.dim() == 3 && q.scalar_type() == at::kBFloat16 &&
@@ -561,6 +577,7 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_permute(Tensor x, Tensor? probs, Tensor row_map, Tensor counts, Tensor seg_offsets, int capacity) -> (Tensor, Tensor)");
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
+  m.def("flash_attn_fwd(Tensor q, Tensor k, Tensor v, float scale, bool causal) -> (Tensor, Tensor)");
   m.def("qk_norm_rope_fwd(Tensor q, Tensor k, Tensor wq, Tensor wk, Tensor cos_t, Tensor sin_t, float eps, bool zero_centered, "
         "int style) -> (Tensor, Tensor, Tensor)");
   m.def("qk_norm_rope_bwd(Tensor dq_out, Tensor dk_out, Tensor q, Tensor k, Tensor wq, Tensor wk, Tensor cos_t, Tensor sin_t, "
@@ -599,6 +616,7 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("moe_permute", &moe_permute);
   m.impl("moe_gather", &moe_gather);
   m.impl("sumsq_accumulate_", &sumsq_accumulate_);
+  m.impl("flash_attn_fwd", &flash_attn_fwd);
   m.impl("qk_norm_rope_fwd", &qk_norm_rope_fwd);
   m.impl("qk_norm_rope_bwd", &qk_norm_rope_bwd);
   m.impl("router_topk_fwd", &router_topk_fwd);

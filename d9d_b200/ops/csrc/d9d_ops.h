@@ -125,6 +125,11 @@ void sumsq_accumulate(const void* x, long long n, int dtype, float* out, cudaStr
 // x *= *scale (device scalar)
 void scale_inplace(void* x, long long n, int dtype, const float* scale, cudaStream_t stream);
 
+// ------------------------------------------------------------------ flash attention (forward) -------------
+// q [B, Sq, Hq, D], k / v [B, Sk, Hk, D], out [B, Sq, Hq, D] bf16 (contiguous); lse [B, Hq, Sq] fp32 or null
+void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Sk, int Hq, int Hk,
+                    int D, float scale, bool causal, cudaStream_t stream);
+
 // ------------------------------------------------------------------ fused q/k RMSNorm + RoPE -------------
 // q [T, Hq, D] (row stride ldq), k [T, Hk, D] (row stride ldk), cos/sin [T, rope_dim] fp32 (already gathered per token)
 int qk_norm_rope_grid(long long T, int Ht);  // number of blocks == rows of dw_partial
