@@ -35,7 +35,8 @@ def main() -> None:
     p = torch.nn.Parameter(torch.randn(args.numel // 4096, 4096, device=dev).bfloat16())
     opt = NvlinkShardedAdamW([p], dist.group.WORLD, lr=1e-3, max_norm=1.0)
     n = opt._numel
-    begin, end = opt._begin, opt._begin + opt._shard
+    begin, end = opt._owned_range(0)
+    end = begin + opt._chunk  # one owned chunk
     p.grad.normal_()
 
     def timed(fn, sync_before=True):
@@ -69,6 +70,8 @@ def main() -> None:
     res["full_step_ms"] = timed(lambda: opt.step(), sync_before=False)
     flat = opt.grad_arena.buffer
     res["nccl_allreduce_fp32_ms"] = timed(lambda: dist.all_reduce(flat))
+    res["chunk_numel"] = opt._chunk
+    res["chunks_per_rank"] = opt._rows
     shard_bytes = (end - begin) * 4
     res["reduce_shard_GBps_in"] = shard_bytes / res["reduce_shard_ms"] / 1e6
     res["allreduce_busbw_GBps"] = 2 * (world - 1) / world * n * 4 / res["nccl_allreduce_fp32_ms"] / 1e6

@@ -37,6 +37,7 @@ class TrainStepRunner:
 
             self.opt = NvlinkShardedAdamW(self.params, dist.group.WORLD, lr=lr, state_dtype=torch.bfloat16, max_norm=max_norm)
             self.opt.grad_scale = self.grad_scale
+            self.opt.set_required_accumulations(args.accum)  # reduce finished chunks while backward is still running
             self.grad_arena = self.opt.grad_arena.buffer
         else:
             # flat fp32 gradient arena; every param.grad is a view (accumulated in place by autograd)

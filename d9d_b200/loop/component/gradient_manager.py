@@ -33,6 +33,7 @@ class GradientManager:
         self._config = config
         self._loss = WeightedMeanMetric()
         self._loss.to(dist_context.current_device)
+        self._num_backward_calls = batch_maths.num_backward_calls
         self._sync = GradientSynchronizer([list(m.parameters()) for m in tracked_modules.modules],
                                           bucket_size_mb=config.bucket_size_mb,
                                           require_accumulations=batch_maths.num_backward_calls)
@@ -80,6 +81,9 @@ class GradientManager:
                 if owner is not None:
                     owners[id(owner)] = owner
         self._external_owners = list(owners.values())  # optimizers that reduce / scale / zero their gradients themselves
+        for owner in self._external_owners:
+            if hasattr(owner, "set_required_accumulations"):  # lets them overlap their reduction with backward
+                owner.set_required_accumulations(self._num_backward_calls)
         self._installed = True
         try:
             yield

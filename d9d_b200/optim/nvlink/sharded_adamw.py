@@ -40,7 +40,7 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
 
     def __init__(self, params: Iterable[nn.Parameter], group: dist.ProcessGroup, lr: float, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-2, state_dtype: torch.dtype = torch.bfloat16,
-                 max_norm: float | None = None, seed: int = 0):
+                 max_norm: float | None = None, seed: int = 0, chunk_numel: int = 1 << 24, overlap_waves: int = 8):
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("NvlinkShardedAdamW needs at least one trainable parameter")
@@ -61,11 +61,16 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         for p in params:
             offsets.append(total)
             total += (_local(p).numel() + _ALIGN - 1) // _ALIGN * _ALIGN
-        quantum = self._world * 1024
-        total = (total + quantum - 1) // quantum * quantum
+        # Ownership is interleaved: the arena is cut into equal chunks and chunk c belongs to rank c % world, so every
+        # rank has something to reduce as soon as *any* region of the gradients is final (backward finishes the arena
+        # back to front).  A rank's moments for chunk c live in local slot c // world.
+        per_rank = -(-total // self._world)
+        self._chunk = max(1024, min(int(chunk_numel), -(-per_rank // 1024) * 1024))
+        row = self._chunk * self._world
+        total = -(-total // row) * row
         self._numel = total
-        self._shard = total // self._world
-        self._begin = self._rank * self._shard
+        self._rows = total // row  # chunks per rank
+        self._shard = self._rows * self._chunk
 
         self.param_arena = SymmetricArena(total, torch.bfloat16, device, group)
         self.grad_arena = SymmetricArena(total, torch.float32, device, group)
@@ -86,14 +91,99 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
                     p.grad = gview
                 setattr(p, FUSED_WGRAD_ATTR, True)
                 setattr(p, EXTERNAL_GRAD_OWNER_ATTR, self)
+        self._param_ranges = [(off, off + _local(p).numel()) for p, off in zip(params, offsets, strict=True)]
+        self._params_flat = params
         self.exp_avg = torch.zeros(self._shard, dtype=state_dtype, device=device)
         self.exp_avg_sq = torch.zeros(self._shard, dtype=state_dtype, device=device)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=device)
         self._scale = torch.ones(1, dtype=torch.float32, device=device)
         self.grad_scale: torch.Tensor | None = None  # optional device scalar multiplied into every gradient
         self.last_grad_norm: torch.Tensor | None = None
+        # ---- overlap of the gradient reduction with the tail of backward (enabled by set_required_accumulations)
+        self._num_waves = max(1, min(int(overlap_waves), self._rows))
+        self._required: int | None = None
+        self._hooks: list = []
+        self._side: torch.cuda.Stream | None = None
+        self._next_wave = 0
+        self._reduced_rows = 0  # rows [rows - reduced_rows, rows) of this step are already reduced
+        self._acc_counts: list[int] = []
+        self._wave_pending: list[int] = []
+        self._waves_of_param: list[list[int]] = []
         torch.cuda.synchronize(device)
         self.param_arena.barrier()
+
+    # ------------------------------------------------------------------ chunk / wave geometry
+    def _owned_range(self, row: int) -> tuple[int, int]:
+        begin = (row * self._world + self._rank) * self._chunk
+        return begin, begin + self._chunk
+
+    def _wave_rows(self, wave: int) -> range:
+        """Wave 0 covers the *last* rows of the arena (their gradients are final first)."""
+        per = -(-self._rows // self._num_waves)
+        hi = self._rows - wave * per
+        return range(max(hi - per, 0), max(hi, 0))
+
+    def set_required_accumulations(self, num_backward_calls: int | None) -> None:
+        """Enable (``n`` backward passes make a gradient final) or disable (``None``) the overlap of the cross-replica
+        reduction with backward.  With it, whenever all gradients of a wave of chunks are final the owner reduces them
+        on a side stream (after a device-side barrier among the replicas) while backward continues."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        self._required = num_backward_calls
+        if num_backward_calls is None:
+            return
+        row_span = self._chunk * self._world
+        per = -(-self._rows // self._num_waves)
+        self._waves_of_param = []
+        for lo, hi in self._param_ranges:
+            rows = range(lo // row_span, (max(hi, lo + 1) - 1) // row_span + 1)
+            self._waves_of_param.append(sorted({(self._rows - 1 - r) // per for r in rows}))
+        self._reset_readiness()
+        index = {id(p): i for i, p in enumerate(self._params_flat)}
+        self._hooks = [p.register_post_accumulate_grad_hook(lambda q, _i=index: self._on_grad_final(_i[id(q)])) for p in self._params_flat]
+
+    def _reset_readiness(self) -> None:
+        self._acc_counts = [0] * len(self._params_flat)
+        self._wave_pending = [0] * self._num_waves
+        for waves in self._waves_of_param:
+            for w in waves:
+                self._wave_pending[w] += 1
+        self._next_wave = 0
+        self._reduced_rows = 0
+
+    def _on_grad_final(self, idx: int) -> None:
+        self._acc_counts[idx] += 1
+        if self._acc_counts[idx] != self._required:
+            return
+        for w in self._waves_of_param[idx]:
+            self._wave_pending[w] -= 1
+        while self._next_wave < self._num_waves and self._wave_pending[self._next_wave] == 0:
+            self._launch_wave(self._next_wave)
+            self._next_wave += 1
+
+    def _reduce_rows(self, rows: range) -> None:
+        ops = native_ops()
+        mc = self.grad_arena.multicast_ptr if self.uses_multicast else 0
+        for row in rows:
+            begin, end = self._owned_range(row)
+            ops.nvl_reduce_shard_(self.grad_arena.buffer, self.grad_arena.peer_ptrs_dev, mc, begin, end, self._world, self._rank, self._sumsq)
+
+    def _launch_wave(self, wave: int) -> None:
+        """Reduce the owned chunks of ``wave`` on the side stream; everything enqueued on the current stream so far
+        (i.e. the kernels that produced these gradients) is ordered before it."""
+        rows = self._wave_rows(wave)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self._sumsq.device)
+        ready = torch.cuda.Event()
+        ready.record()
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            if self._reduced_rows == 0:
+                self._sumsq.zero_()
+            self.grad_arena.barrier()  # every replica finished the gradients of this wave
+            self._reduce_rows(rows)
+        self._reduced_rows += len(rows)
 
     @property
     def uses_multicast(self) -> bool:
@@ -133,13 +223,21 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         group = self.param_groups[0]
         beta1, beta2 = group["betas"]
         self._step_count += 1
-        begin, end = self._begin, self._begin + self._shard
-
-        self.grad_arena.barrier()  # every replica finished its backward; its gradients are visible
-        self._sumsq.zero_()
         multicast = self.uses_multicast
-        ops.nvl_reduce_shard_(self.grad_arena.buffer, self.grad_arena.peer_ptrs_dev,
-                              self.grad_arena.multicast_ptr if multicast else 0, begin, end, self._world, self._rank, self._sumsq)
+        remaining = range(0, self._rows - self._reduced_rows)
+        if self._reduced_rows > 0:
+            # part of the arena was reduced while backward was still running; finish the rest behind it
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                if len(remaining) > 0:
+                    self.grad_arena.barrier()
+                    self._reduce_rows(remaining)
+            main.wait_stream(self._side)
+        else:
+            self.grad_arena.barrier()  # every replica finished its backward; its gradients are visible
+            self._sumsq.zero_()
+            self._reduce_rows(remaining)
         scale = self.grad_scale if self.grad_scale is not None else None
         if self._max_norm is not None:
             dist.all_reduce(self._sumsq, group=self._group)
@@ -152,14 +250,19 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
             scale = self._scale
         self.grad_arena.barrier()  # all replicas have read my gradients: they may be overwritten / zeroed
         lr = group["lr"]
-        ops.nvl_adamw_shard_(self.param_arena.buffer, self.grad_arena.buffer, self.exp_avg, self.exp_avg_sq,
-                             self.param_arena.peer_ptrs_dev, self.param_arena.multicast_ptr if multicast else 0, begin, end,
-                             self._world, self._rank,
-                             float(lr), beta1, beta2, group["eps"], group["weight_decay"],
-                             1.0 - beta1**self._step_count, 1.0 - beta2**self._step_count,
-                             self._seed + 7919 * self._step_count, scale)
+        mc_param = self.param_arena.multicast_ptr if multicast else 0
+        for row in range(self._rows):
+            begin, end = self._owned_range(row)
+            slot = slice(row * self._chunk, (row + 1) * self._chunk)
+            ops.nvl_adamw_shard_(self.param_arena.buffer, self.grad_arena.buffer, self.exp_avg[slot], self.exp_avg_sq[slot],
+                                 self.param_arena.peer_ptrs_dev, mc_param, begin, end, self._world, self._rank,
+                                 float(lr), beta1, beta2, group["eps"], group["weight_decay"],
+                                 1.0 - beta1**self._step_count, 1.0 - beta2**self._step_count,
+                                 self._seed + 7919 * self._step_count, scale)
         self.grad_arena.buffer.zero_()
         self.param_arena.barrier()  # every shard owner's parameter writes have landed here before the next forward
+        if self._required is not None:
+            self._reset_readiness()
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # gradients are zeroed inside step()
         if set_to_none:
@@ -168,9 +271,12 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
 
     def state_dict(self) -> dict[str, Any]:
         return {f"shard_{self._rank}_of_{self._world}": {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq},
+                "chunk_numel": self._chunk,
                 "step": self._step_count, "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
+        if int(state_dict.get("chunk_numel", self._chunk)) != self._chunk:
+            raise ValueError("checkpoint was written with a different chunk size (ownership layout differs)")
         shard = state_dict[f"shard_{self._rank}_of_{self._world}"]
         self.exp_avg.copy_(shard["exp_avg"])
         self.exp_avg_sq.copy_(shard["exp_avg_sq"])

@@ -32,7 +32,7 @@ def _entry(rank, world, port, fn, args):
         dist.destroy_process_group()
 
 
-def _sharded_adamw_worker(rank, world, state_dtype, max_norm):
+def _sharded_adamw_worker(rank, world, state_dtype, max_norm, overlap=False):
     import torch.distributed as dist
 
     from d9d_b200.optim.nvlink import NvlinkShardedAdamW
@@ -42,7 +42,9 @@ def _sharded_adamw_worker(rank, world, state_dtype, max_norm):
     params = [torch.nn.Parameter(torch.randn(s, device="cuda").bfloat16()) for s in shapes]
     ref_p = [p.detach().float().clone() for p in params]
     opt = NvlinkShardedAdamW(params, dist.group.WORLD, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
-                             state_dtype=state_dtype, max_norm=max_norm, seed=5)
+                             state_dtype=state_dtype, max_norm=max_norm, seed=5, chunk_numel=2048, overlap_waves=3)
+    if overlap:
+        opt.set_required_accumulations(1)
     assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in params)
     for p, r in zip(params, ref_p):
         torch.testing.assert_close(p.detach().float(), r)  # moving into the arena kept the values
@@ -54,8 +56,10 @@ def _sharded_adamw_worker(rank, world, state_dtype, max_norm):
         for r in range(world):
             g = torch.Generator(device="cuda").manual_seed(100 * step + r)
             all_grads.append([torch.randn(s, device="cuda", generator=g) for s in shapes])
-        for p, g in zip(params, all_grads[rank]):
-            p.grad.add_(g)  # what backward would accumulate on this replica
+        for i in reversed(range(len(params))):  # backward produces gradients back to front
+            params[i].grad.add_(all_grads[rank][i])  # what backward would accumulate on this replica
+            if overlap:
+                opt._on_grad_final(i)  # the post-accumulate hook autograd would fire: finished waves reduce right away
         opt.grad_scale = torch.full((1,), 0.5, device="cuda")
         opt.step()
         # fp32 reference of: sum over replicas -> *0.5 -> clip -> AdamW
@@ -86,12 +90,12 @@ def _sharded_adamw_worker(rank, world, state_dtype, max_norm):
         ref_p = [p.detach().float().clone() for p in params]
 
 
-@pytest.mark.parametrize("state_dtype,max_norm,multimem", [(torch.bfloat16, 1.0, "0"), (torch.bfloat16, None, "1"),
-                                                           (torch.float32, 1.0, "1"), (torch.float32, None, "0")])
-def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm, multimem, monkeypatch):
+@pytest.mark.parametrize("state_dtype,max_norm,multimem,overlap", [
+    (torch.bfloat16, 1.0, "0", True), (torch.bfloat16, None, "1", False), (torch.float32, 1.0, "1", True), (torch.float32, None, "0", False)])
+def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm, multimem, overlap, monkeypatch):
     _need_gpus(2)
     monkeypatch.setenv("D9D_NVLINK_MULTIMEM", multimem)  # peer loads/stores vs NVSwitch multicast
-    _spawn(_sharded_adamw_worker, 2, state_dtype, max_norm)
+    _spawn(_sharded_adamw_worker, 2, state_dtype, max_norm, overlap)
 
 
 def _trainer_worker(rank, world, optimizer_name, tmp):
