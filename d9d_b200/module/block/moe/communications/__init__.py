@@ -3,5 +3,6 @@
 from .base import ExpertCommunicationHandler
 from .expert_parallel import ExpertParallelCommunicationHandler
 from .naive import NoCommunicationHandler
+from .nvlink import AutoExpertParallelCommunicationHandler, NvlinkExpertParallelCommunicationHandler
 
-__all__ = ["ExpertCommunicationHandler", "ExpertParallelCommunicationHandler", "NoCommunicationHandler"]
+__all__ = ["ExpertCommunicationHandler", "ExpertParallelCommunicationHandler", "AutoExpertParallelCommunicationHandler", "NoCommunicationHandler", "NvlinkExpertParallelCommunicationHandler"]

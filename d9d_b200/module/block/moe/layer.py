@@ -33,9 +33,9 @@ class MoELayer(nn.Module, ModuleLateInit):
 
     def enable_distributed_communicator(self, group: ProcessGroup) -> None:
         """Switch to expert-parallel dispatch/combine over ``group`` (NVLink peer memory / NCCL all-to-all)."""
-        from .communications.expert_parallel import ExpertParallelCommunicationHandler  # lazy: needs a process group
+        from .communications.nvlink import AutoExpertParallelCommunicationHandler  # lazy: needs a process group
 
-        handler = ExpertParallelCommunicationHandler(num_experts=self._num_grouped_experts)
+        handler = AutoExpertParallelCommunicationHandler(num_experts=self._num_grouped_experts)
         handler.setup(group, self._hidden_dim, self.router.gate.weight.dtype)
         self._communicator = handler
 

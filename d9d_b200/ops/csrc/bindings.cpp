@@ -519,6 +519,34 @@ void gemm_ag_k(const Tensor& local, at::IntArrayRef peer_ptrs, bool peer_is_a, i
   d9d::gemm_comm(g, cur_stream());
 }
 
+// ------------------------------------------------------------------ expert-parallel exchange over NVLink
+void ep_push(const Tensor& x, const c10::optional<Tensor>& probs, const Tensor& dest_rank, const Tensor& dest_row, int64_t peer_ptrs_dev,
+             int64_t off_x, int64_t off_p, int64_t k) {
+  CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(dest_rank); CHECK_CUDA_CONTIG(dest_row);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.dim() == 2 && dest_rank.scalar_type() == at::kInt && dest_row.scalar_type() == at::kInt);
+  TORCH_CHECK(dest_rank.numel() == x.size(0) * k && dest_row.numel() == x.size(0) * k, "ep_push: one destination per (token, slot) pair");
+  c10::cuda::CUDAGuard guard(x.device());
+  const float* pr = nullptr;
+  if (probs.has_value()) {
+    TORCH_CHECK(probs->is_cuda() && probs->is_contiguous() && probs->scalar_type() == at::kFloat && probs->numel() == dest_row.numel());
+    pr = probs->data_ptr<float>();
+  }
+  d9d::ep_push(x.data_ptr(), pr, dest_rank.data_ptr<int>(), dest_row.data_ptr<int>(), reinterpret_cast<void* const*>(peer_ptrs_dev), off_x,
+               off_p, dest_row.numel(), static_cast<int>(k), static_cast<int>(x.size(1)), cur_stream());
+}
+
+std::tuple<Tensor, Tensor> ep_pull_sum(int64_t peer_ptrs_dev, int64_t off_y, int64_t off_dp, const Tensor& dest_rank, const Tensor& dest_row,
+                                       int64_t T, int64_t k, int64_t H, bool with_dprobs) {
+  CHECK_CUDA_CONTIG(dest_rank); CHECK_CUDA_CONTIG(dest_row);
+  TORCH_CHECK(dest_rank.scalar_type() == at::kInt && dest_row.scalar_type() == at::kInt && dest_row.numel() == T * k);
+  c10::cuda::CUDAGuard guard(dest_row.device());
+  Tensor y = at::empty({T, H}, dest_row.options().dtype(at::kBFloat16));
+  Tensor dprobs = at::empty({with_dprobs ? T : 0, k}, dest_row.options().dtype(at::kFloat));
+  d9d::ep_pull_sum(reinterpret_cast<void* const*>(peer_ptrs_dev), off_y, off_dp, dest_rank.data_ptr<int>(), dest_row.data_ptr<int>(),
+                   y.data_ptr(), with_dprobs ? dprobs.data_ptr<float>() : nullptr, T, static_cast<int>(k), static_cast<int>(H), cur_stream());
+  return {y, dprobs};
+}
+
 // ------------------------------------------------------------------ NVLink data-parallel optimizer -----------
 // `peer_ptrs_dev` / `multicast_ptr` come from torch.distributed._symmetric_memory (buffer_ptrs_dev, multicast_ptr).
 void nvl_reduce_shard_(Tensor own_grad, int64_t peer_ptrs_dev, int64_t multicast_ptr, int64_t begin, int64_t end,
@@ -589,6 +617,9 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("gemm_rs_d(Tensor a, Tensor b, int[] d_peer_ptrs, int rows_local, int ldd, int block_rows, bool b_mn) -> ()");
   m.def("gemm_ag_k(Tensor local, int[] peer_ptrs, bool peer_is_a, int rows_local, int peer_ld, int block_rows, Tensor(a!) d, "
         "bool accumulate) -> ()");
+  m.def("ep_push(Tensor x, Tensor? probs, Tensor dest_rank, Tensor dest_row, int peer_ptrs_dev, int off_x, int off_p, int k) -> ()");
+  m.def("ep_pull_sum(int peer_ptrs_dev, int off_y, int off_dp, Tensor dest_rank, Tensor dest_row, int T, int k, int H, bool with_dprobs) "
+        "-> (Tensor, Tensor)");
   m.def("nvl_reduce_shard_(Tensor(a!) own_grad, int peer_ptrs_dev, int multicast_ptr, int begin, int end, int world, int rank, "
         "Tensor(b!) sumsq) -> ()");
   m.def("nvl_adamw_shard_(Tensor(a!) own_param, Tensor own_grad, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, int peer_ptrs_dev, "
@@ -625,6 +656,8 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("gemm_wait_a", &gemm_wait_a);
   m.impl("gemm_rs_d", &gemm_rs_d);
   m.impl("gemm_ag_k", &gemm_ag_k);
+  m.impl("ep_push", &ep_push);
+  m.impl("ep_pull_sum", &ep_pull_sum);
   m.impl("nvl_reduce_shard_", &nvl_reduce_shard_);
   m.impl("nvl_adamw_shard_", &nvl_adamw_shard_);
   m.impl("scale_inplace_", &scale_inplace_);

@@ -148,6 +148,14 @@ void router_topk_fwd(const void* logits, const float* bias, long long T, int E, 
 void router_topk_bwd(const void* logits, const long long* idx, const float* dprobs, long long T, int E, int k,
                      bool renorm, void* dlogits, cudaStream_t stream);
 
+// ------------------------------------------------------------------ expert-parallel exchange over NVLink ----
+// peer_base: device array [world] of symmetric-arena base pointers; off_* are byte offsets of regions inside the arena.
+// dest_rank / dest_row: per (token, slot) pair, the owner rank and the row in its buffer (row < 0: dropped pair).
+void ep_push(const void* x, const float* probs, const int* dest_rank, const int* dest_row, void* const* peer_base, long long off_x,
+             long long off_p, long long n_pairs, int k, int H, cudaStream_t stream);
+void ep_pull_sum(void* const* peer_base, long long off_y, long long off_dp, const int* dest_rank, const int* dest_row, void* y,
+                 float* dprobs, long long T, int k, int H, cudaStream_t stream);
+
 // ------------------------------------------------------------------ NVLink data-parallel optimizer -----------
 // peer_* : device array [world] of per-replica base pointers of the symmetric arena; mc_* : multicast (NVLS) mapping
 // of the same arena or nullptr.  [begin, end) is this rank's shard (multiples of 8 elements).

@@ -39,7 +39,7 @@ def _worker(rank, world_size):
     from d9d_b200.core.dist_context import DeviceMeshParameters
     from d9d_b200.internals.grad_sync import GradientSynchronizer
     from d9d_b200.module.block.moe import MoELayer
-    from d9d_b200.module.block.moe.communications import ExpertParallelCommunicationHandler
+    from d9d_b200.module.block.moe.communications import AutoExpertParallelCommunicationHandler
     from d9d_b200.module.parallelism.model.qwen3_moe import parallelize_qwen3_moe_for_causal_lm
     from d9d_b200.pipelining.api import PipelineStageInfo
 
@@ -47,7 +47,7 @@ def _worker(rank, world_size):
     model = _build()
     parallelize_qwen3_moe_for_causal_lm(ctx, model, PipelineStageInfo(0, 1))
     moe_layers = [m for m in model.modules() if isinstance(m, MoELayer)]
-    assert moe_layers and all(isinstance(m._communicator, ExpertParallelCommunicationHandler) for m in moe_layers)
+    assert moe_layers and all(isinstance(m._communicator, AutoExpertParallelCommunicationHandler) for m in moe_layers)
     w = moe_layers[0].grouped_experts.gate_proj.weight
     assert isinstance(w.data, DTensor) and w.to_local().shape[0] == 8 // world_size
 

@@ -274,3 +274,60 @@ def _tp_mlp_worker(rank, world):
 def test_sequence_parallel_mlp_uses_fused_tp_kernels():
     _need_gpus(2)
     _spawn(_tp_mlp_worker, 2)
+
+
+def _ep_worker(rank, world):
+    """EP=2 MoE layer on the NVLink exchange vs the same layer with all experts local (single-process reference)."""
+    import torch.distributed as dist
+    from torch.distributed.device_mesh import init_device_mesh
+
+    from d9d_b200.kernel._native import native_ops
+    from d9d_b200.module.block.moe import MoELayer
+    from d9d_b200.module.parallelism.api import parallelize_expert_parallel
+
+    E, k, H, F = 8, 2, 256, 192
+    torch.manual_seed(3)
+    ref = MoELayer(hidden_dim=H, intermediate_dim_grouped=F, num_grouped_experts=E, top_k=k, router_renormalize_probabilities=True)
+    ref.reset_parameters()
+    ref = ref.cuda().bfloat16()
+    ep = MoELayer(hidden_dim=H, intermediate_dim_grouped=F, num_grouped_experts=E, top_k=k, router_renormalize_probabilities=True)
+    ep = ep.cuda().bfloat16()
+    ep.load_state_dict(ref.state_dict())
+    ep.tokens_per_expert.zero_()
+    ref.tokens_per_expert.zero_()
+    mesh = init_device_mesh("cuda", (1, world), mesh_dim_names=("ep_replicate", "ep_shard"))
+    parallelize_expert_parallel(ep, mesh)
+
+    g = torch.Generator(device="cuda").manual_seed(50 + rank)  # every rank routes different tokens
+    x = torch.randn(2, 200, H, device="cuda", generator=g).bfloat16()
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    before = native_ops().launches
+    y = ep(xa)
+    y_ref = ref(xb)
+    torch.testing.assert_close(y.float(), y_ref.float(), rtol=3e-2, atol=3e-2)
+    w = torch.randn_like(y_ref)
+    (y.float() * w).sum().backward()
+    (y_ref.float() * w).sum().backward()
+    assert native_ops().launches > before
+
+    def close(a, b, name):
+        a, b = a.float().flatten(), b.float().flatten()
+        assert torch.nn.functional.cosine_similarity(a, b, dim=0) > 0.99, name
+        assert 0.9 < float(a.norm() / (b.norm() + 1e-12)) < 1.1, name
+
+    close(xa.grad, xb.grad, "dx")
+    # expert weights: this rank owns experts [rank * E/W, (rank + 1) * E/W); their gradients only see tokens routed to them
+    # from *all* ranks, so compare against the reference accumulated over every rank's tokens
+    local = E // world
+    for name in ("gate_proj", "up_proj", "down_proj"):
+        mine = getattr(ep.grouped_experts, name).weight.grad.to_local().float()
+        full = getattr(ref.grouped_experts, name).weight.grad.float().clone()
+        dist.all_reduce(full)  # sum of the per-rank references == gradient of the global batch
+        close(mine, full[rank * local : (rank + 1) * local], name)
+    gate = ep.router.gate.weight.grad
+    close(gate.to_local() if hasattr(gate, "to_local") else gate, ref.router.gate.weight.grad, "router")
+
+
+def test_expert_parallel_over_nvlink_matches_local_experts():
+    _need_gpus(2)
+    _spawn(_ep_worker, 2)
