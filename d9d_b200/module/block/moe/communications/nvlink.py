@@ -80,7 +80,10 @@ class _Dispatch(Function):
         ws, ops = plan.ws, native_ops()
         cap = plan.layout.capacity
         ws.x[:cap].copy_(dxp)
-        ws.p[:cap].copy_(dpp.float())
+        if dpp is None:
+            ws.p[:cap].zero_()
+        else:
+            ws.p[:cap].copy_(dpp.float())
         ws.arena.barrier()  # every owner published the gradients of the rows it received
         dx, dprobs = ops.ep_pull_sum(ws.arena.peer_ptrs_dev, ws.off_x, ws.off_p, plan.dest_rank, plan.dest_row, plan.num_tokens, plan.top_k,
                                      plan.hidden, True)
