@@ -98,7 +98,7 @@ def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm, multimem,
     _spawn(_sharded_adamw_worker, 2, state_dtype, max_norm, overlap)
 
 
-def _trainer_worker(rank, world, optimizer_name, tmp):
+def _trainer_worker(rank, world, optimizer_name, tmp, expert_parallel=1):
     from pathlib import Path
 
     import torch.distributed as dist
@@ -123,7 +123,7 @@ def _trainer_worker(rank, world, optimizer_name, tmp):
     lr_cfg = PiecewiseConfig.model_validate({"name": "piecewise", "scheduler": {"initial_multiplier": 1.0, "phases": [
         {"mode": "rest", "target_multiplier": 1.0, "curve": {"type": "linear"}}]}})
     trainer = TrainingConfigurator(
-        mesh=DeviceMeshParameters(data_parallel_replicate=world),
+        mesh=DeviceMeshParameters(data_parallel_replicate=world, expert_parallel=expert_parallel),
         parameters=trainer_config(Path(tmp) / f"r{rank}", total_batch=16, micro=4),
         task_provider=lambda ctx: CausalLMTask(),
         model_provider=Qwen3MoEModelProvider(Qwen3MoEModelProviderConfig(model=params)),
@@ -138,6 +138,15 @@ def _trainer_worker(rank, world, optimizer_name, tmp):
     state.event_bus.subscribe(EVENT_TRAIN_OPTIMIZER_STEP_POST, lambda ctx: losses.append(state.gradient_manager.compute_global_loss().item()))
     trainer.train()
     assert len(losses) == 12 and losses[-1] < losses[0] - 0.5, losses
+    if expert_parallel > 1:
+        from d9d_b200.module.block.moe import MoELayer
+        from d9d_b200.module.block.moe.communications.nvlink import NvlinkExpertParallelCommunicationHandler
+
+        layers = [m for stage in state.tracked_modules.modules for m in stage.modules() if isinstance(m, MoELayer)]
+        assert layers and all(isinstance(m._communicator._nvlink, NvlinkExpertParallelCommunicationHandler) for m in layers)
+        if rank == 0:
+            torch.save(torch.tensor(losses), Path(tmp) / f"losses_{optimizer_name}_ep.pt")
+        return
     flat = torch.cat([(p._local_tensor if hasattr(p, "_local_tensor") else p.data).float().flatten()
                       for m in state.tracked_modules.modules for p in m.parameters()])
     gathered = [torch.empty_like(flat) for _ in range(world)]
@@ -331,3 +340,13 @@ def _ep_worker(rank, world):
 def test_expert_parallel_over_nvlink_matches_local_experts():
     _need_gpus(2)
     _spawn(_ep_worker, 2)
+
+
+def test_trainer_with_expert_parallel_over_nvlink(tmp_path):
+    """DP=2 x EP=2 on two GPUs (experts sharded, tokens exchanged by the NVLink kernels) follows the pure-DP run."""
+    _need_gpus(2)
+    _spawn(_trainer_worker, 2, "nccl", str(tmp_path), 2)
+    _spawn(_trainer_worker, 2, "nccl", str(tmp_path), 1)
+    a = torch.load(tmp_path / "losses_nccl_ep.pt")
+    b = torch.load(tmp_path / "losses_nccl.pt")
+    assert abs(float(a[0] - b[0])) < 2e-2 and float((a - b).abs().max()) < 0.3, (a, b)
