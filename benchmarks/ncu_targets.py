@@ -54,6 +54,17 @@ def main() -> None:
     pitch = (V + 7) // 8 * 8
     dl = torch.empty(chunk, pitch, **bf)[:, :V]
     ops.ce_dlogits(x[:chunk], wv, tgt[:chunk], lse[:chunk], torch.ones(chunk, device=dev), dl, -100)
+    # 9) flash-attention forward (own tcgen05 kernel), flagship shape
+    B, S, Hq, Hk, D = 8, 2048, 16, 4, 128
+    q = torch.randn(B, S, Hq, D, **bf)
+    kk = torch.randn(B, S, Hk, D, **bf)
+    vv = torch.randn(B, S, Hk, D, **bf)
+    ops.flash_attn_fwd(q, kk, vv, D ** -0.5, True)
+    # 10) fused q/k RMSNorm + RoPE, 11) router
+    wqn = torch.ones(D, **bf)
+    ang = torch.rand(B * S, D, device=dev)
+    ops.qk_norm_rope_fwd(q.view(B * S, Hq, D), kk.view(B * S, Hk, D), wqn, wqn, ang.cos(), ang.sin(), 1e-6, False, 0)
+    ops.router_topk_fwd(torch.randn(T, E, **bf), None, k, True)
     torch.cuda.synchronize()
 
 
