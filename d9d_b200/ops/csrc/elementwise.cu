@@ -65,6 +65,42 @@ inline int num_sms() {
   return n;
 }
 
+// Rows are kept in registers in their *packed* storage type (16 bytes = 8 bf16/fp16 values; fp32: 32 bytes) and unpacked on
+// use — half the registers of an fp32 copy, which is what decides how many rows an SM keeps in flight.
+template <typename T> struct Raw8 { uint4 v; };
+template <> struct Raw8<float> { float4 a, b; };
+
+template <typename T>
+__device__ __forceinline__ Raw8<T> raw_load(const T* p) {
+  Raw8<T> r;
+  r.v = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+template <>
+__device__ __forceinline__ Raw8<float> raw_load<float>(const float* p) {
+  Raw8<float> r;
+  r.a = reinterpret_cast<const float4*>(p)[0];
+  r.b = reinterpret_cast<const float4*>(p)[1];
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void raw_unpack(const Raw8<T>& r, float (&f)[8]) {
+  Vec8<T>::load(&r.v, f);
+}
+template <>
+__device__ __forceinline__ void raw_unpack<float>(const Raw8<float>& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_weight(const T* w, int vi, bool zero_centered, float (&wf)[8]) {
+  Vec8<T>::load(w + vi * 8, wf);  // a few KiB shared by every row: stays in L1
+  if (zero_centered) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wf[i] += 1.f;
+  }
+}
+
 // ================================================================= RMSNorm ======================
 // A row is owned by G lanes (G in {8,16,32}) each holding VPL 8-wide vectors; N <= G*VPL*8, N % 8 == 0.
 // Rows are register-resident: one read of x, one write of out (HBM roofline = 2 B/elt r + 2 B/elt w for bf16).
@@ -73,49 +109,52 @@ __global__ void __launch_bounds__(256) rms_fwd_kernel(const T* __restrict__ x, c
                                                       T* __restrict__ out, float* __restrict__ inv_rms, long long M,
                                                       int N, float eps, bool zero_centered) {
   constexpr int ROWS_PER_WARP = 32 / G;
+  constexpr int U = (VPL <= 2) ? 2 : 1;  // short rows: two row groups in flight per warp
   const int lane = threadIdx.x & 31, sub = lane % G, rsub = lane / G;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int nvec = N >> 3;
-
-  float wf[VPL][8];
+  for (long long rb = warp_global * ROWS_PER_WARP * U; rb < M; rb += warps_total * ROWS_PER_WARP * U) {
+    Raw8<T> xr[U][VPL];
+    long long rows[U];
+    bool ok[U];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int vi = sub + v * G;
-    if (vi < nvec) {
-      Vec8<T>::load(w + vi * 8, wf[v]);
-      if (zero_centered) {
+    for (int u = 0; u < U; ++u) {
+      rows[u] = rb + u * ROWS_PER_WARP + rsub;
+      ok[u] = rows[u] < M;  // trip count is warp-uniform so the shuffles below stay convergent
 #pragma unroll
-        for (int i = 0; i < 8; ++i) wf[v][i] += 1.f;
-      }
-    }
-  }
-  for (long long rb = warp_global * ROWS_PER_WARP; rb < M; rb += warps_total * ROWS_PER_WARP) {
-    const long long row = rb + rsub;
-    const bool row_ok = row < M;  // trip count is warp-uniform so the shuffles below stay convergent
-    float xf[VPL][8];
-    float ss = 0.f;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int vi = sub + v * G;
-      if (vi < nvec && row_ok) {
-        Vec8<T>::load(x + row * N + vi * 8, xf[v]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ss += xf[v][i] * xf[v][i];
+      for (int v = 0; v < VPL; ++v) {
+        const int vi = sub + v * G;
+        if (vi < nvec && ok[u]) xr[u][v] = raw_load<T>(x + rows[u] * N + vi * 8);
       }
     }
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float ir = rsqrtf(ss / static_cast<float>(N) + eps);
-    if (sub == 0 && inv_rms && row_ok) inv_rms[row] = ir;
+    for (int u = 0; u < U; ++u) {
+      float ss = 0.f;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int vi = sub + v * G;
-      if (vi < nvec && row_ok) {
-        float o[8];
+      for (int v = 0; v < VPL; ++v) {
+        if (sub + v * G < nvec && ok[u]) {
+          float xf[8];
+          raw_unpack<T>(xr[u][v], xf);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = xf[v][i] * ir * wf[v][i];
-        Vec8<T>::store(out + row * N + vi * 8, o);
+          for (int i = 0; i < 8; ++i) ss += xf[i] * xf[i];
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float ir = rsqrtf(ss / static_cast<float>(N) + eps);
+      if (sub == 0 && inv_rms && ok[u]) inv_rms[rows[u]] = ir;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int vi = sub + v * G;
+        if (vi < nvec && ok[u]) {
+          float xf[8], wf[8], o[8];
+          raw_unpack<T>(xr[u][v], xf);
+          load_weight<T>(w, vi, zero_centered, wf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = xf[i] * ir * wf[i];
+          Vec8<T>::store(out + rows[u] * N + vi * 8, o);
+        }
       }
     }
   }
@@ -135,39 +174,38 @@ __global__ void __launch_bounds__(256) rms_bwd_kernel(const T* __restrict__ dout
   const int nvec = N >> 3;
   const int nwarps = blockDim.x >> 5;
 
-  float wf[VPL][8], dwf[VPL][8];
+  float dwf[VPL][8];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
+  for (int v = 0; v < VPL; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) dwf[v][i] = 0.f;
-    const int vi = sub + v * G;
-    if (vi < nvec) {
-      Vec8<T>::load(w + vi * 8, wf[v]);
-      if (zero_centered) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wf[v][i] += 1.f;
-      }
-    }
-  }
   for (long long rb = warp_global * ROWS_PER_WARP; rb < M; rb += warps_total * ROWS_PER_WARP) {
     const long long row = rb + rsub;
     const bool row_ok = row < M;  // trip count is warp-uniform so the shuffles below stay convergent
     const float ir = row_ok ? inv_rms[row] : 0.f;
-    float xh[VPL][8], dy[VPL][8];
+    Raw8<T> xr[VPL], gr[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int vi = sub + v * G;
+      if (vi < nvec && row_ok) {
+        xr[v] = raw_load<T>(x + row * N + vi * 8);
+        gr[v] = raw_load<T>(dout + row * N + vi * 8);
+      }
+    }
     float dot = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const int vi = sub + v * G;
       if (vi < nvec && row_ok) {
-        float xf[8], df[8];
-        Vec8<T>::load(x + row * N + vi * 8, xf);
-        Vec8<T>::load(dout + row * N + vi * 8, df);
+        float xf[8], df[8], wf[8];
+        raw_unpack<T>(xr[v], xf);
+        raw_unpack<T>(gr[v], df);
+        load_weight<T>(w, vi, zero_centered, wf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          xh[v][i] = xf[i] * ir;
-          dwf[v][i] += df[i] * xh[v][i];
-          dy[v][i] = df[i] * wf[v][i];
-          dot += dy[v][i] * xh[v][i];
+          const float xh = xf[i] * ir;
+          dwf[v][i] += df[i] * xh;
+          dot += df[i] * wf[i] * xh;
         }
       }
     }
@@ -178,9 +216,12 @@ __global__ void __launch_bounds__(256) rms_bwd_kernel(const T* __restrict__ dout
     for (int v = 0; v < VPL; ++v) {
       const int vi = sub + v * G;
       if (vi < nvec && row_ok) {
-        float o[8];
+        float xf[8], df[8], wf[8], o[8];
+        raw_unpack<T>(xr[v], xf);
+        raw_unpack<T>(gr[v], df);
+        load_weight<T>(w, vi, zero_centered, wf);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = ir * (dy[v][i] - xh[v][i] * mean_dot);
+        for (int i = 0; i < 8; ++i) o[i] = ir * (df[i] * wf[i] - xf[i] * ir * mean_dot);
         Vec8<T>::store(dx + row * N + vi * 8, o);
       }
     }
@@ -210,13 +251,24 @@ __global__ void __launch_bounds__(256) rms_bwd_kernel(const T* __restrict__ dout
   }
 }
 
+// partial [num_partials, N] -> dw[N]; one block per 32 columns, 8 row lanes x 32 columns of threads (fixed order: deterministic)
 template <typename T>
-__global__ void rms_dw_reduce_kernel(const float* __restrict__ partial, int num_partials, int N, T* __restrict__ dw) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
+__global__ void __launch_bounds__(256) rms_dw_reduce_kernel(const float* __restrict__ partial, int num_partials, int N,
+                                                            T* __restrict__ dw) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
   float s = 0.f;
-  for (int p = 0; p < num_partials; ++p) s += partial[static_cast<long long>(p) * N + c];
-  dw[c] = static_cast<T>(s);
+  if (c < N)
+    for (int p = rl; p < num_partials; p += 8) s += partial[static_cast<long long>(p) * N + c];
+  __shared__ float sm[8][32];
+  sm[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+    dw[c] = static_cast<T>(t);
+  }
 }
 
 template <typename T, int G, int VPL>
@@ -246,7 +298,7 @@ void rms_bwd_launch(const void* dout, const void* x, const void* w, const float*
   kern<<<static_cast<int>(blocks), 256, smem, s>>>(static_cast<const T*>(dout), static_cast<const T*>(x),
                                                    static_cast<const T*>(w), inv_rms, static_cast<T*>(dx), dw_partial,
                                                    M, N, zc);
-  rms_dw_reduce_kernel<T><<<(N + 255) / 256, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
+  rms_dw_reduce_kernel<T><<<(N + 31) / 32, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
 }
 
 
@@ -270,15 +322,20 @@ __global__ void __launch_bounds__(256) rms_fwd_block_kernel(const T* __restrict_
   __shared__ float sm[8];
   const int nvec = N >> 3;
   for (long long row = blockIdx.x; row < M; row += gridDim.x) {
-    float xf[VPL][8];
-    float ss = 0.f;
+    Raw8<T> xr[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const int vi = threadIdx.x + v * 256;
-      if (vi < nvec) {
-        Vec8<T>::load(x + row * N + vi * 8, xf[v]);
+      if (vi < nvec) xr[v] = raw_load<T>(x + row * N + vi * 8);
+    }
+    float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss += xf[v][i] * xf[v][i];
+    for (int v = 0; v < VPL; ++v) {
+      if (threadIdx.x + v * 256 < nvec) {
+        float xf[8];
+        raw_unpack<T>(xr[v], xf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += xf[i] * xf[i];
       }
     }
     ss = block_sum_256(ss, sm);
@@ -288,10 +345,11 @@ __global__ void __launch_bounds__(256) rms_fwd_block_kernel(const T* __restrict_
     for (int v = 0; v < VPL; ++v) {
       const int vi = threadIdx.x + v * 256;
       if (vi < nvec) {
-        float wf[8], o[8];
-        Vec8<T>::load(w + vi * 8, wf);
+        float xf[8], wf[8], o[8];
+        raw_unpack<T>(xr[v], xf);
+        load_weight<T>(w, vi, zero_centered, wf);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = xf[v][i] * ir * (zero_centered ? wf[i] + 1.f : wf[i]);
+        for (int i = 0; i < 8; ++i) o[i] = xf[i] * ir * wf[i];
         Vec8<T>::store(out + row * N + vi * 8, o);
       }
     }
@@ -305,37 +363,36 @@ __global__ void __launch_bounds__(256) rms_bwd_block_kernel(const T* __restrict_
                                                             long long M, int N, bool zero_centered) {
   __shared__ float sm[8];
   const int nvec = N >> 3;
-  float wf[VPL][8], dwf[VPL][8];
+  float dwf[VPL][8];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
+  for (int v = 0; v < VPL; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) dwf[v][i] = 0.f;
-    const int vi = threadIdx.x + v * 256;
-    if (vi < nvec) {
-      Vec8<T>::load(w + vi * 8, wf[v]);
-      if (zero_centered) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) wf[v][i] += 1.f;
-      }
-    }
-  }
   for (long long row = blockIdx.x; row < M; row += gridDim.x) {
     const float ir = inv_rms[row];
-    float xh[VPL][8], dy[VPL][8];
+    Raw8<T> xr[VPL], gr[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int vi = threadIdx.x + v * 256;
+      if (vi < nvec) {
+        xr[v] = raw_load<T>(x + row * N + vi * 8);
+        gr[v] = raw_load<T>(dout + row * N + vi * 8);
+      }
+    }
     float dot = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const int vi = threadIdx.x + v * 256;
       if (vi < nvec) {
-        float xf[8], df[8];
-        Vec8<T>::load(x + row * N + vi * 8, xf);
-        Vec8<T>::load(dout + row * N + vi * 8, df);
+        float xf[8], df[8], wf[8];
+        raw_unpack<T>(xr[v], xf);
+        raw_unpack<T>(gr[v], df);
+        load_weight<T>(w, vi, zero_centered, wf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          xh[v][i] = xf[i] * ir;
-          dwf[v][i] += df[i] * xh[v][i];
-          dy[v][i] = df[i] * wf[v][i];
-          dot += dy[v][i] * xh[v][i];
+          const float xh = xf[i] * ir;
+          dwf[v][i] += df[i] * xh;
+          dot += df[i] * wf[i] * xh;
         }
       }
     }
@@ -345,9 +402,12 @@ __global__ void __launch_bounds__(256) rms_bwd_block_kernel(const T* __restrict_
     for (int v = 0; v < VPL; ++v) {
       const int vi = threadIdx.x + v * 256;
       if (vi < nvec) {
-        float o[8];
+        float xf[8], df[8], wf[8], o[8];
+        raw_unpack<T>(xr[v], xf);
+        raw_unpack<T>(gr[v], df);
+        load_weight<T>(w, vi, zero_centered, wf);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = ir * (dy[v][i] - xh[v][i] * mean_dot);
+        for (int i = 0; i < 8; ++i) o[i] = ir * (df[i] * wf[i] - xf[i] * ir * mean_dot);
         Vec8<T>::store(dx + row * N + vi * 8, o);
       }
     }
@@ -382,7 +442,7 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
   rms_bwd_block_kernel<T, VPL><<<static_cast<int>(blocks), 256, 0, s>>>(
       static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms, static_cast<T*>(dx),
       dw_partial, M, N, zc);
-  rms_dw_reduce_kernel<T><<<(N + 255) / 256, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
+  rms_dw_reduce_kernel<T><<<(N + 31) / 32, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
 }
 
 #define D9D_RMS_FWD_DISPATCH(T, ...)                                                     \
@@ -414,7 +474,7 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
 
 }  // namespace
 
-int rms_norm_bwd_num_partials() { return num_sms() * 2; }
+int rms_norm_bwd_num_partials() { return num_sms() * 6; }
 
 void rms_norm_fwd(const void* x, const void* w, void* out, float* inv_rms, long long M, int N, float eps,
                   bool zero_centered, int dtype, cudaStream_t stream) {
