@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) rms_fwd_kernel(const T* __restrict__ x, c
                                                       T* __restrict__ out, float* __restrict__ inv_rms, long long M,
                                                       int N, float eps, bool zero_centered) {
   constexpr int ROWS_PER_WARP = 32 / G;
-  constexpr int U = (VPL <= 2) ? 2 : 1;  // short rows: two row groups in flight per warp
+  constexpr int U = (VPL <= 4) ? 2 : 1;  // short rows: two row groups in flight per warp
   const int lane = threadIdx.x & 31, sub = lane % G, rsub = lane / G;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) rms_fwd_block_kernel(const T* __restrict_
 }
 
 template <typename T, int VPL>
-__global__ void __launch_bounds__(256) rms_bwd_block_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+__global__ void __launch_bounds__(256, (VPL <= 2) ? 4 : 2) rms_bwd_block_kernel(const T* __restrict__ dout, const T* __restrict__ x,
                                                             const T* __restrict__ w, const float* __restrict__ inv_rms,
                                                             T* __restrict__ dx, float* __restrict__ dw_partial,
                                                             long long M, int N, bool zero_centered) {
@@ -453,7 +453,7 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
     else if (N <= 512) rms_fwd_launch<T, 32, 2>(__VA_ARGS__);                            \
     else if (N <= 1024) rms_fwd_launch<T, 32, 4>(__VA_ARGS__);                           \
     else if (N <= 2048) rms_fwd_launch<T, 32, 8>(__VA_ARGS__);                           \
-    else if (N <= 4096) rms_fwd_block_launch<T, 2>(__VA_ARGS__);                         \
+    else if (N <= 4096) rms_fwd_launch<T, 32, 16>(__VA_ARGS__);                          \
     else if (N <= 8192) rms_fwd_block_launch<T, 4>(__VA_ARGS__);                         \
     else if (N <= 16384) rms_fwd_block_launch<T, 8>(__VA_ARGS__);                        \
     else throw std::runtime_error("d9d rms_norm: N > 16384 not supported");              \
