@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) rms_fwd_kernel(const T* __restrict__ x, c
                                                       T* __restrict__ out, float* __restrict__ inv_rms, long long M,
                                                       int N, float eps, bool zero_centered) {
   constexpr int ROWS_PER_WARP = 32 / G;
-  constexpr int U = (VPL <= 4) ? 2 : 1;  // short rows: two row groups in flight per warp
+  constexpr int U = (VPL <= 2) ? 2 : 1;  // short rows: two row groups in flight per warp
   const int lane = threadIdx.x & 31, sub = lane % G, rsub = lane / G;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -319,6 +319,8 @@ template <typename T, int VPL>
 __global__ void __launch_bounds__(256) rms_fwd_block_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                             T* __restrict__ out, float* __restrict__ inv_rms,
                                                             long long M, int N, float eps, bool zero_centered) {
+  // 256 threads x VPL vectors cover a row; rows narrower than that simply leave the tail threads idle for the loads,
+  // which lets N <= 4096 run with VPL = 2 and therefore few registers / many resident blocks
   __shared__ float sm[8];
   const int nvec = N >> 3;
   for (long long row = blockIdx.x; row < M; row += gridDim.x) {
@@ -357,17 +359,17 @@ __global__ void __launch_bounds__(256) rms_fwd_block_kernel(const T* __restrict_
 }
 
 template <typename T, int VPL>
-__global__ void __launch_bounds__(256, (VPL <= 2) ? 4 : 2) rms_bwd_block_kernel(const T* __restrict__ dout, const T* __restrict__ x,
-                                                            const T* __restrict__ w, const float* __restrict__ inv_rms,
-                                                            T* __restrict__ dx, float* __restrict__ dw_partial,
-                                                            long long M, int N, bool zero_centered) {
+__global__ void __launch_bounds__(256, (VPL <= 2) ? 5 : 3) rms_bwd_block_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                                                                                const T* __restrict__ w,
+                                                                                const float* __restrict__ inv_rms, T* __restrict__ dx,
+                                                                                float* __restrict__ dw_partial, long long M, int N,
+                                                                                bool zero_centered) {
+  // dW accumulators live in shared memory (thread t owns the same columns for every row, so plain += is race free):
+  // registers only hold the packed x / dy vectors, which keeps five blocks resident per SM.
+  extern __shared__ float dw_acc[];  // [N]
   __shared__ float sm[8];
   const int nvec = N >> 3;
-  float dwf[VPL][8];
-#pragma unroll
-  for (int v = 0; v < VPL; ++v)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dwf[v][i] = 0.f;
+  for (int c = threadIdx.x; c < N; c += 256) dw_acc[c] = 0.f;
   for (long long row = blockIdx.x; row < M; row += gridDim.x) {
     const float ir = inv_rms[row];
     Raw8<T> xr[VPL], gr[VPL];
@@ -388,12 +390,15 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 4 : 2) rms_bwd_block_kernel(
         raw_unpack<T>(xr[v], xf);
         raw_unpack<T>(gr[v], df);
         load_weight<T>(w, vi, zero_centered, wf);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = xf[i] * ir;
-          dwf[v][i] += df[i] * xh;
-          dot += df[i] * wf[i] * xh;
-        }
+        float4* acc = reinterpret_cast<float4*>(dw_acc + vi * 8);
+        float4 a0 = acc[0], a1 = acc[1];
+        const float xh0 = xf[0] * ir, xh1 = xf[1] * ir, xh2 = xf[2] * ir, xh3 = xf[3] * ir;
+        const float xh4 = xf[4] * ir, xh5 = xf[5] * ir, xh6 = xf[6] * ir, xh7 = xf[7] * ir;
+        a0.x += df[0] * xh0; a0.y += df[1] * xh1; a0.z += df[2] * xh2; a0.w += df[3] * xh3;
+        a1.x += df[4] * xh4; a1.y += df[5] * xh5; a1.z += df[6] * xh6; a1.w += df[7] * xh7;
+        acc[0] = a0; acc[1] = a1;
+        dot += df[0] * wf[0] * xh0 + df[1] * wf[1] * xh1 + df[2] * wf[2] * xh2 + df[3] * wf[3] * xh3 +
+               df[4] * wf[4] * xh4 + df[5] * wf[5] * xh5 + df[6] * wf[6] * xh6 + df[7] * wf[7] * xh7;
       }
     }
     dot = block_sum_256(dot, sm);
@@ -412,21 +417,15 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 4 : 2) rms_bwd_block_kernel(
       }
     }
   }
-#pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int vi = threadIdx.x + v * 256;
-    if (vi < nvec) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dw_partial[static_cast<long long>(blockIdx.x) * N + vi * 8 + i] = dwf[v][i];
-    }
-  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += 256) dw_partial[static_cast<long long>(blockIdx.x) * N + c] = dw_acc[c];
 }
 
 template <typename T, int VPL>
 void rms_fwd_block_launch(const void* x, const void* w, void* out, float* inv_rms, long long M, int N, float eps,
                           bool zc, cudaStream_t s) {
   long long blocks = M;
-  const long long cap = static_cast<long long>(num_sms()) * 8;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   rms_fwd_block_kernel<T, VPL><<<static_cast<int>(blocks), 256, 0, s>>>(
       static_cast<const T*>(x), static_cast<const T*>(w), static_cast<T*>(out), inv_rms, M, N, eps, zc);
@@ -439,7 +438,10 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
   const long long cap = rms_norm_bwd_num_partials();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  rms_bwd_block_kernel<T, VPL><<<static_cast<int>(blocks), 256, 0, s>>>(
+  auto kern = rms_bwd_block_kernel<T, VPL>;
+  const size_t smem = static_cast<size_t>(N) * sizeof(float);
+  if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  kern<<<static_cast<int>(blocks), 256, smem, s>>>(
       static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms, static_cast<T*>(dx),
       dw_partial, M, N, zc);
   rms_dw_reduce_kernel<T><<<(N + 31) / 32, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
@@ -453,7 +455,7 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
     else if (N <= 512) rms_fwd_launch<T, 32, 2>(__VA_ARGS__);                            \
     else if (N <= 1024) rms_fwd_launch<T, 32, 4>(__VA_ARGS__);                           \
     else if (N <= 2048) rms_fwd_launch<T, 32, 8>(__VA_ARGS__);                           \
-    else if (N <= 4096) rms_fwd_launch<T, 32, 16>(__VA_ARGS__);                          \
+    else if (N <= 4096) rms_fwd_block_launch<T, 2>(__VA_ARGS__);                         \
     else if (N <= 8192) rms_fwd_block_launch<T, 4>(__VA_ARGS__);                         \
     else if (N <= 16384) rms_fwd_block_launch<T, 8>(__VA_ARGS__);                        \
     else throw std::runtime_error("d9d rms_norm: N > 16384 not supported");              \
