@@ -421,6 +421,73 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 5 : 3) rms_bwd_block_kernel(
   for (int c = threadIdx.x; c < N; c += 256) dw_partial[static_cast<long long>(blockIdx.x) * N + c] = dw_acc[c];
 }
 
+// register-accumulator variant (faster for rows of <= 4096 elements: two vectors per thread)
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 2) ? 4 : 2) rms_bwd_block_reg_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                                                            const T* __restrict__ w, const float* __restrict__ inv_rms,
+                                                            T* __restrict__ dx, float* __restrict__ dw_partial,
+                                                            long long M, int N, bool zero_centered) {
+  __shared__ float sm[8];
+  const int nvec = N >> 3;
+  float dwf[VPL][8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dwf[v][i] = 0.f;
+  for (long long row = blockIdx.x; row < M; row += gridDim.x) {
+    const float ir = inv_rms[row];
+    Raw8<T> xr[VPL], gr[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int vi = threadIdx.x + v * 256;
+      if (vi < nvec) {
+        xr[v] = raw_load<T>(x + row * N + vi * 8);
+        gr[v] = raw_load<T>(dout + row * N + vi * 8);
+      }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int vi = threadIdx.x + v * 256;
+      if (vi < nvec) {
+        float xf[8], df[8], wf[8];
+        raw_unpack<T>(xr[v], xf);
+        raw_unpack<T>(gr[v], df);
+        load_weight<T>(w, vi, zero_centered, wf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = xf[i] * ir;
+          dwf[v][i] += df[i] * xh;
+          dot += df[i] * wf[i] * xh;
+        }
+      }
+    }
+    dot = block_sum_256(dot, sm);
+    const float mean_dot = dot / static_cast<float>(N);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int vi = threadIdx.x + v * 256;
+      if (vi < nvec) {
+        float xf[8], df[8], wf[8], o[8];
+        raw_unpack<T>(xr[v], xf);
+        raw_unpack<T>(gr[v], df);
+        load_weight<T>(w, vi, zero_centered, wf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = ir * (df[i] * wf[i] - xf[i] * ir * mean_dot);
+        Vec8<T>::store(dx + row * N + vi * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int vi = threadIdx.x + v * 256;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dw_partial[static_cast<long long>(blockIdx.x) * N + vi * 8 + i] = dwf[v][i];
+    }
+  }
+}
+
 template <typename T, int VPL>
 void rms_fwd_block_launch(const void* x, const void* w, void* out, float* inv_rms, long long M, int N, float eps,
                           bool zc, cudaStream_t s) {
@@ -438,6 +505,13 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
   const long long cap = rms_norm_bwd_num_partials();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  if constexpr (VPL <= 2) {
+    rms_bwd_block_reg_kernel<T, VPL><<<static_cast<int>(blocks), 256, 0, s>>>(
+        static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms, static_cast<T*>(dx), dw_partial, M,
+        N, zc);
+    rms_dw_reduce_kernel<T><<<(N + 31) / 32, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
+    return;
+  }
   auto kern = rms_bwd_block_kernel<T, VPL>;
   const size_t smem = static_cast<size_t>(N) * sizeof(float);
   if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
