@@ -15,16 +15,14 @@ def fused_indices_to_multihot(indices: torch.Tensor, probs_indices: torch.Tensor
     """
     T = indices.shape[0]
     valid = (indices >= 0) & (indices < num_of_local_experts)
-    safe = indices.clamp(0, max(num_of_local_experts - 1, 0)).long()
-    routing = torch.zeros(T, num_of_local_experts, dtype=torch.bool, device=indices.device)
-    routing.scatter_(1, safe, valid)
-    # scatter may overwrite a valid hit with a clamped invalid one on the same column -> OR via scatter_add
+    # dropped ids are redirected to column 0 with a zero contribution; scatter_add makes that a no-op (a plain scatter
+    # could overwrite a genuine hit on column 0)
+    safe = torch.where(valid, indices, torch.zeros_like(indices)).long()
     hits = torch.zeros(T, num_of_local_experts, dtype=torch.int32, device=indices.device)
     hits.scatter_add_(1, safe, valid.int())
-    routing = hits > 0
     probs = torch.zeros(T, num_of_local_experts, dtype=probs_indices.dtype, device=indices.device)
-    probs = probs.scatter_add(1, safe, probs_indices * valid.to(probs_indices.dtype))
-    return routing, probs
+    probs.scatter_add_(1, safe, probs_indices * valid.to(probs_indices.dtype))
+    return hits > 0, probs
 
 
 def moe_permute_with_probs(inp: torch.Tensor, probs: torch.Tensor, routing_map: torch.Tensor, num_out_tokens: int = -1):

@@ -155,3 +155,19 @@ def test_moe_layer_matches_per_token_expert_sum_and_counts_tokens():
             want[t] += p * ((torch.nn.functional.silu(gate) * up) @ ge.down_proj.weight[e])
     torch.testing.assert_close(y.view(-1, 16), want, rtol=1e-4, atol=1e-5)
     assert int(moe.tokens_per_expert.sum()) == 21 * 2
+
+
+def test_reference_compatible_moe_routing_helpers():
+    from d9d_b200.kernel.moe import fused_indices_to_multihot, moe_permute_with_probs, moe_unpermute_mask
+
+    idx = torch.tensor([[0, 2], [1, -1], [3, 0]])
+    p = torch.tensor([[0.6, 0.4], [1.0, 0.5], [0.3, 0.7]])
+    routing, probs = fused_indices_to_multihot(idx, p, 4)
+    assert routing.tolist() == [[True, False, True, False], [False, True, False, False], [True, False, False, True]]
+    torch.testing.assert_close(probs, torch.tensor([[0.6, 0, 0.4, 0], [0, 1.0, 0, 0], [0.7, 0, 0, 0.3]]))
+    x = torch.arange(3, dtype=torch.float32)[:, None] * torch.ones(3, 4)
+    permuted, pp, row_map = moe_permute_with_probs(x, probs, routing)
+    assert permuted[:, 0].tolist() == [0.0, 2.0, 1.0, 0.0, 2.0]  # expert-major, token order kept inside an expert
+    torch.testing.assert_close(pp, torch.tensor([0.6, 0.7, 1.0, 0.4, 0.3]))
+    back = moe_unpermute_mask(permuted, row_map, merging_probs=probs, restore_shape=x.shape)
+    torch.testing.assert_close(back, x * probs.sum(-1, keepdim=True))
