@@ -35,7 +35,16 @@ class TrainStepRunner:
             # peer-memory kernels inside opt.step() (no NCCL all-reduce of the gradients)
             from d9d_b200.optim.nvlink import NvlinkShardedAdamW
 
-            self.opt = NvlinkShardedAdamW(self.params, dist.group.WORLD, lr=lr, state_dtype=torch.bfloat16, max_norm=max_norm)
+            try:
+                self.opt = NvlinkShardedAdamW(self.params, dist.group.WORLD, lr=lr, state_dtype=torch.bfloat16, max_norm=max_norm)
+            except Exception as exc:  # e.g. no peer access between the visible GPUs: every rank fails the same way
+                import sys
+
+                print(f"[bench] NVLink symmetric memory unavailable ({type(exc).__name__}: {exc}); falling back to NCCL all-reduce",
+                      file=sys.stderr, flush=True)
+                self.nvlink = False
+                args.dp_impl = "nccl"
+        if self.nvlink:
             self.opt.grad_scale = self.grad_scale
             self.opt.set_required_accumulations(args.accum)  # reduce finished chunks while backward is still running
             self.grad_arena = self.opt.grad_arena.buffer
