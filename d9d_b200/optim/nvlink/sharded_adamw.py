@@ -187,17 +187,15 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
 
     @property
     def uses_multicast(self) -> bool:
-        """NVSwitch multicast (``multimem``) path or explicit peer loads/stores.
+        """NVSwitch multicast (``multimem``) path or explicit peer loads/stores (default).
 
-        In-switch reduction divides the NVLink traffic of the reduce by ``world - 1`` and of the broadcast by the
-        same factor, which pays from 4 replicas on; with 2 replicas plain peer loads/stores are faster (measured on
-        2xB200: 8.6 ms vs 16.2 ms for the reduce of a 2.73 B-parameter arena).  ``D9D_NVLINK_MULTIMEM=0/1`` overrides.
+        ``multimem.ld_reduce`` / ``multimem.st`` move fewer bytes *into* a GPU, but both phases are bound by what every
+        GPU has to send / receive in total, and measured on B200 the plain peer loads / stores are faster at every
+        size tried (reduce of a 2.73 B-parameter arena: 8.1 vs 16.1 ms on 2 GPUs, 14.2 vs 15.0 ms on 8; update +
+        broadcast 4.3 vs 8.4 ms and 7.2 vs 7.7 ms).  ``D9D_NVLINK_MULTIMEM=1`` selects the multicast path.
         """
         available = self.param_arena.multicast_ptr != 0 and self.grad_arena.multicast_ptr != 0
-        override = os.environ.get("D9D_NVLINK_MULTIMEM")
-        if override is not None:
-            return available and override == "1"
-        return available and self._world >= 4
+        return available and os.environ.get("D9D_NVLINK_MULTIMEM", "0") == "1"
 
     state_is_materialized = True  # nothing is created lazily: checkpoint loading needs no warm-up step
 
