@@ -65,6 +65,16 @@ inline int num_sms() {
   return n;
 }
 
+// Persistent kernels (each block loops over rows and owns one partial-dW row) must be launched with exactly as many blocks
+// as fit on the device at once: a grid of 1.5 "waves" leaves the last half wave running at half occupancy.
+template <typename K>
+inline int resident_blocks(K kernel, int threads, size_t smem) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (per_sm < 1) per_sm = 1;
+  return per_sm * num_sms();
+}
+
 // Rows are kept in registers in their *packed* storage type (16 bytes = 8 bf16/fp16 values; fp32: 32 bytes) and unpacked on
 // use — half the registers of an fp32 copy, which is what decides how many rows an SM keeps in flight.
 template <typename T> struct Raw8 { uint4 v; };
@@ -289,12 +299,13 @@ void rms_bwd_launch(const void* dout, const void* x, const void* w, const float*
   constexpr int ROWS_PER_WARP = 32 / G;
   const long long warps_needed = (M + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
   long long blocks = (warps_needed + 7) / 8;
-  const long long max_blocks = rms_norm_bwd_num_partials();
-  if (blocks > max_blocks) blocks = max_blocks;
-  if (blocks < 1) blocks = 1;
   const size_t smem = static_cast<size_t>(8) * N * sizeof(float);
   auto kern = rms_bwd_kernel<T, G, VPL>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  long long max_blocks = resident_blocks(kern, 256, smem);
+  if (max_blocks > rms_norm_bwd_num_partials()) max_blocks = rms_norm_bwd_num_partials();
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
   kern<<<static_cast<int>(blocks), 256, smem, s>>>(static_cast<const T*>(dout), static_cast<const T*>(x),
                                                    static_cast<const T*>(w), inv_rms, static_cast<T*>(dx), dw_partial,
                                                    M, N, zc);
@@ -502,10 +513,11 @@ template <typename T, int VPL>
 void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const float* inv_rms, void* dx, void* dw,
                           float* dw_partial, long long M, int N, bool zc, cudaStream_t s) {
   long long blocks = M;
-  const long long cap = rms_norm_bwd_num_partials();
-  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if constexpr (VPL <= 2) {
+    long long cap = resident_blocks(rms_bwd_block_reg_kernel<T, VPL>, 256, 0);
+    if (cap > rms_norm_bwd_num_partials()) cap = rms_norm_bwd_num_partials();
+    if (blocks > cap) blocks = cap;
     rms_bwd_block_reg_kernel<T, VPL><<<static_cast<int>(blocks), 256, 0, s>>>(
         static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms, static_cast<T*>(dx), dw_partial, M,
         N, zc);
@@ -515,6 +527,9 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
   auto kern = rms_bwd_block_kernel<T, VPL>;
   const size_t smem = static_cast<size_t>(N) * sizeof(float);
   if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  long long cap = resident_blocks(kern, 256, smem);
+  if (cap > rms_norm_bwd_num_partials()) cap = rms_norm_bwd_num_partials();
+  if (blocks > cap) blocks = cap;
   kern<<<static_cast<int>(blocks), 256, smem, s>>>(
       static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms, static_cast<T*>(dx),
       dw_partial, M, N, zc);
@@ -550,7 +565,7 @@ void rms_bwd_block_launch(const void* dout, const void* x, const void* w, const 
 
 }  // namespace
 
-int rms_norm_bwd_num_partials() { return num_sms() * 6; }
+int rms_norm_bwd_num_partials() { return num_sms() * 8; }
 
 void rms_norm_fwd(const void* x, const void* w, void* out, float* inv_rms, long long M, int N, float eps,
                   bool zero_centered, int dtype, cudaStream_t stream) {
