@@ -10,6 +10,8 @@ Replaces the reference's dependency on the cut-cross-entropy Triton kernels (``d
 
 from __future__ import annotations
 
+import os
+
 from typing import Any
 
 import torch
@@ -21,7 +23,10 @@ from d9d_b200.core.autograd import GLOBAL_GRAD_CONTEXT, GradDirection
 from .._native import grad_dtype_of, native_ops, on_gpu
 
 IGNORE_INDEX = -100
-_CHUNK_BYTES = 1 << 30  # size of the dlogits chunk buffer used by the backward pass
+# Backward materialises g*(softmax - onehot) for a chunk of tokens at a time (bf16).  180 GB of HBM make a large chunk
+# affordable, and every extra chunk costs one more read-modify-write pass over the fp32 dC [V, K] accumulator plus the
+# tail waves of three GEMMs, so the default covers 16k tokens x 150k vocabulary in one piece.
+_CHUNK_BYTES = int(os.environ.get("D9D_CCE_CHUNK_BYTES", 6 << 30))
 
 
 def linear_cross_entropy_reference(e, c, targets, bias=None, ignore_index=IGNORE_INDEX, softcap=None):
