@@ -230,8 +230,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      // grouped modes read the tile's expert / row range from global memory: fetch it one whole tile ahead so that the
+      // load latency never sits between two tiles on the critical path
+      TileCoord t_next = get_tile<MODE, BLOCK_N>(p, blockIdx.x);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
+        const TileCoord t = t_next;
+        if (tile + static_cast<int>(gridDim.x) < total_tiles) t_next = get_tile<MODE, BLOCK_N>(p, tile + gridDim.x);
         if (!t.valid) continue;
         const int m_idx = t.m_blk * BLOCK_M, n_idx = t.n_blk * BLOCK_N;
         if constexpr (COMM == COMM_WAIT_A) {  // the shard holding this m-tile may still be in flight
@@ -302,8 +306,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    TileCoord t_next = get_tile<MODE, BLOCK_N>(p, blockIdx.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
+      const TileCoord t = t_next;
+      if (tile + static_cast<int>(gridDim.x) < total_tiles) t_next = get_tile<MODE, BLOCK_N>(p, tile + gridDim.x);
       if (!t.valid) continue;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -338,8 +344,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t epi_chunk = 0;  // running count of staged chunks (selects the staging buffer)
+    TileCoord t_next = get_tile<MODE, BLOCK_N>(p, blockIdx.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = get_tile<MODE, BLOCK_N>(p, tile);
+      const TileCoord t = t_next;
+      if (tile + static_cast<int>(gridDim.x) < total_tiles) t_next = get_tile<MODE, BLOCK_N>(p, tile + gridDim.x);
       if (!t.valid) continue;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
