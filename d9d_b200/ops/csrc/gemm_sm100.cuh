@@ -93,7 +93,10 @@ struct Cfg {
   static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * 2 * 4096;  // per epilogue warp: 2 x (32 rows x 128 B)
+  // Operand bytes in flight decide the throughput of the mid-size GEMMs (per-SM bandwidth = bytes in flight / load latency),
+  // so the 192-wide tile trades the second epilogue staging buffer for a fifth operand stage (200 KiB in flight).
+  static constexpr int EPI_BUFS = (BLOCK_N == 192) ? 1 : 2;
+  static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_BUFS * 4096;  // per epilogue warp: EPI_BUFS x (32 rows x 128 B)
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256 - EPI_STAGING_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -413,9 +416,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int c = 0; c < BLOCK_N / CHUNK_COLS; ++c) {
             const int cbase = col0 + c * CHUNK_COLS;
             if (cbase >= p.N) break;  // warp-uniform
-            uint8_t* stage_buf = smem_epi + (quad * 2 + (epi_chunk & 1)) * 4096;
+            uint8_t* stage_buf = smem_epi + (quad * C::EPI_BUFS + (epi_chunk % C::EPI_BUFS)) * 4096;
             ++epi_chunk;
-            if (lane == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained
+            if (lane == 0) tma_store_wait_read<C::EPI_BUFS - 1>();  // the store that last read this buffer has drained
             __syncwarp();
             uint32_t packed[32];
             if constexpr (OUT_BF16) {
