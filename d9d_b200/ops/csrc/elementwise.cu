@@ -504,7 +504,19 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 4 : 2) rms_bwd_block_reg_ker
 // cp.async.bulk copies of whole rows into a PIPE_STAGES-deep ring (mbarrier complete_tx), all threads compute from
 // shared memory, and dW accumulates in shared memory (thread-owned columns).  Bytes in flight per SM: blocks x stages x
 // two rows (e.g. 2 x 3 x 28 KiB at N = 7168) independent of the register budget.
-constexpr int PIPE_STAGES = 3;
+constexpr int PIPE_STAGES = 2;
+constexpr int PIPE_THREADS = 512;
+
+__device__ __forceinline__ float block_sum_pipe(float v, float* sm) {  // PIPE_THREADS / 32 = 16 warps
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = sm[threadIdx.x & 15];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
 
 __device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
@@ -513,7 +525,7 @@ __device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) rms_bwd_pipe_kernel(const T* __restrict__ dout, const T* __restrict__ x, const T* __restrict__ w,
+__global__ void __launch_bounds__(PIPE_THREADS) rms_bwd_pipe_kernel(const T* __restrict__ dout, const T* __restrict__ x, const T* __restrict__ w,
                                                            const float* __restrict__ inv_rms, T* __restrict__ dx,
                                                            float* __restrict__ dw_partial, long long M, int N, bool zero_centered) {
   extern __shared__ __align__(128) uint8_t pipe_smem[];
@@ -521,7 +533,7 @@ __global__ void __launch_bounds__(256) rms_bwd_pipe_kernel(const T* __restrict__
   T* ring = reinterpret_cast<T*>(pipe_smem);                                      // [stages][2][N]
   float* dw_acc = reinterpret_cast<float*>(pipe_smem + PIPE_STAGES * 2 * row_bytes);  // [N]
   uint64_t* full = reinterpret_cast<uint64_t*>(dw_acc + N);                         // [stages]
-  __shared__ float sm[8];
+  __shared__ float sm[PIPE_THREADS / 32];
   const int nvec = N >> 3;
   const long long my_rows = (M > blockIdx.x) ? (M - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -529,7 +541,7 @@ __global__ void __launch_bounds__(256) rms_bwd_pipe_kernel(const T* __restrict__
     for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
-  for (int c = threadIdx.x; c < N; c += 256) dw_acc[c] = 0.f;
+  for (int c = threadIdx.x; c < N; c += PIPE_THREADS) dw_acc[c] = 0.f;
   __syncthreads();
   auto issue = [&](long long it) {  // called by thread 0 only
     const int st = static_cast<int>(it % PIPE_STAGES);
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(256) rms_bwd_pipe_kernel(const T* __restrict__
     const T* xs = ring + (st * 2 + 0) * static_cast<long long>(N);
     const T* gs = ring + (st * 2 + 1) * static_cast<long long>(N);
     float dot = 0.f;
-    for (int vi = threadIdx.x; vi < nvec; vi += 256) {
+    for (int vi = threadIdx.x; vi < nvec; vi += PIPE_THREADS) {
       float xf[8], df[8], wf[8];
       Vec8<T>::load(xs + vi * 8, xf);
       Vec8<T>::load(gs + vi * 8, df);
@@ -565,9 +577,9 @@ __global__ void __launch_bounds__(256) rms_bwd_pipe_kernel(const T* __restrict__
 #pragma unroll
       for (int i = 0; i < 8; ++i) dot += df[i] * wf[i] * xh[i];
     }
-    dot = block_sum_256(dot, sm);
+    dot = block_sum_pipe(dot, sm);
     const float mean_dot = dot / static_cast<float>(N);
-    for (int vi = threadIdx.x; vi < nvec; vi += 256) {
+    for (int vi = threadIdx.x; vi < nvec; vi += PIPE_THREADS) {
       float xf[8], df[8], wf[8], o[8];
       Vec8<T>::load(xs + vi * 8, xf);
       Vec8<T>::load(gs + vi * 8, df);
@@ -582,7 +594,7 @@ __global__ void __launch_bounds__(256) rms_bwd_pipe_kernel(const T* __restrict__
       issue(it + PIPE_STAGES);
     }
   }
-  for (int c = threadIdx.x; c < N; c += 256) dw_partial[static_cast<long long>(blockIdx.x) * N + c] = dw_acc[c];
+  for (int c = threadIdx.x; c < N; c += PIPE_THREADS) dw_partial[static_cast<long long>(blockIdx.x) * N + c] = dw_acc[c];
 }
 
 template <typename T>
@@ -592,11 +604,11 @@ bool rms_bwd_pipe_launch(const void* dout, const void* x, const void* w, const f
   if (smem > 200 * 1024) return false;
   auto kern = rms_bwd_pipe_kernel<T>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  long long blocks = resident_blocks(kern, 256, smem);
+  long long blocks = resident_blocks(kern, PIPE_THREADS, smem);
   if (blocks > rms_norm_bwd_num_partials()) blocks = rms_norm_bwd_num_partials();
   if (blocks > M) blocks = M;
   if (blocks < 1) blocks = 1;
-  kern<<<static_cast<int>(blocks), 256, smem, s>>>(static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms,
+  kern<<<static_cast<int>(blocks), PIPE_THREADS, smem, s>>>(static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms,
                                                     static_cast<T*>(dx), dw_partial, M, N, zc);
   rms_dw_reduce_kernel<T><<<(N + 31) / 32, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
   return true;
