@@ -499,121 +499,6 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 4 : 2) rms_bwd_block_reg_ker
   }
 }
 
-// ---- wide rows, 2-byte dtypes: rows stream through a shared-memory ring filled by bulk async copies -------------------
-// Registers cannot hold enough of a wide row pair (x, dy) to keep the HBM pipe full, so one thread issues
-// cp.async.bulk copies of whole rows into a PIPE_STAGES-deep ring (mbarrier complete_tx), all threads compute from
-// shared memory, and dW accumulates in shared memory (thread-owned columns).  Bytes in flight per SM: blocks x stages x
-// two rows (e.g. 2 x 3 x 28 KiB at N = 7168) independent of the register budget.
-constexpr int PIPE_STAGES = 2;
-constexpr int PIPE_THREADS = 512;
-
-__device__ __forceinline__ float block_sum_pipe(float v, float* sm) {  // PIPE_THREADS / 32 = 16 warps
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = sm[threadIdx.x & 15];
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  return t;
-}
-
-__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <typename T>
-__global__ void __launch_bounds__(PIPE_THREADS) rms_bwd_pipe_kernel(const T* __restrict__ dout, const T* __restrict__ x, const T* __restrict__ w,
-                                                           const float* __restrict__ inv_rms, T* __restrict__ dx,
-                                                           float* __restrict__ dw_partial, long long M, int N, bool zero_centered) {
-  extern __shared__ __align__(128) uint8_t pipe_smem[];
-  const uint32_t row_bytes = static_cast<uint32_t>(N) * sizeof(T);
-  T* ring = reinterpret_cast<T*>(pipe_smem);                                      // [stages][2][N]
-  float* dw_acc = reinterpret_cast<float*>(pipe_smem + PIPE_STAGES * 2 * row_bytes);  // [N]
-  uint64_t* full = reinterpret_cast<uint64_t*>(dw_acc + N);                         // [stages]
-  __shared__ float sm[PIPE_THREADS / 32];
-  const int nvec = N >> 3;
-  const long long my_rows = (M > blockIdx.x) ? (M - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(&full[s], 1);
-    fence_barrier_init();
-  }
-  for (int c = threadIdx.x; c < N; c += PIPE_THREADS) dw_acc[c] = 0.f;
-  __syncthreads();
-  auto issue = [&](long long it) {  // called by thread 0 only
-    const int st = static_cast<int>(it % PIPE_STAGES);
-    const long long row = blockIdx.x + it * gridDim.x;
-    mbar_arrive_expect_tx(&full[st], 2 * row_bytes);
-    bulk_load_row(ring + (st * 2 + 0) * static_cast<long long>(N), x + row * N, row_bytes, &full[st]);
-    bulk_load_row(ring + (st * 2 + 1) * static_cast<long long>(N), dout + row * N, row_bytes, &full[st]);
-  };
-  if (threadIdx.x == 0)
-    for (long long it = 0; it < PIPE_STAGES && it < my_rows; ++it) issue(it);
-
-  for (long long it = 0; it < my_rows; ++it) {
-    const int st = static_cast<int>(it % PIPE_STAGES);
-    const long long row = blockIdx.x + it * gridDim.x;
-    const float ir = inv_rms[row];
-    mbar_wait(&full[st], static_cast<uint32_t>((it / PIPE_STAGES) & 1));
-    const T* xs = ring + (st * 2 + 0) * static_cast<long long>(N);
-    const T* gs = ring + (st * 2 + 1) * static_cast<long long>(N);
-    float dot = 0.f;
-    for (int vi = threadIdx.x; vi < nvec; vi += PIPE_THREADS) {
-      float xf[8], df[8], wf[8];
-      Vec8<T>::load(xs + vi * 8, xf);
-      Vec8<T>::load(gs + vi * 8, df);
-      load_weight<T>(w, vi, zero_centered, wf);
-      float4* acc = reinterpret_cast<float4*>(dw_acc + vi * 8);
-      float4 a0 = acc[0], a1 = acc[1];
-      float xh[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xh[i] = xf[i] * ir;
-      a0.x += df[0] * xh[0]; a0.y += df[1] * xh[1]; a0.z += df[2] * xh[2]; a0.w += df[3] * xh[3];
-      a1.x += df[4] * xh[4]; a1.y += df[5] * xh[5]; a1.z += df[6] * xh[6]; a1.w += df[7] * xh[7];
-      acc[0] = a0; acc[1] = a1;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dot += df[i] * wf[i] * xh[i];
-    }
-    dot = block_sum_pipe(dot, sm);
-    const float mean_dot = dot / static_cast<float>(N);
-    for (int vi = threadIdx.x; vi < nvec; vi += PIPE_THREADS) {
-      float xf[8], df[8], wf[8], o[8];
-      Vec8<T>::load(xs + vi * 8, xf);
-      Vec8<T>::load(gs + vi * 8, df);
-      load_weight<T>(w, vi, zero_centered, wf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = ir * (df[i] * wf[i] - xf[i] * ir * mean_dot);
-      Vec8<T>::store(dx + row * N + vi * 8, o);
-    }
-    __syncthreads();  // everybody is done with this ring slot
-    if (threadIdx.x == 0 && it + PIPE_STAGES < my_rows) {
-      fence_proxy_async_smem();  // order the generic-proxy reads above before the async-proxy refill
-      issue(it + PIPE_STAGES);
-    }
-  }
-  for (int c = threadIdx.x; c < N; c += PIPE_THREADS) dw_partial[static_cast<long long>(blockIdx.x) * N + c] = dw_acc[c];
-}
-
-template <typename T>
-bool rms_bwd_pipe_launch(const void* dout, const void* x, const void* w, const float* inv_rms, void* dx, void* dw, float* dw_partial,
-                         long long M, int N, bool zc, cudaStream_t s) {
-  const size_t smem = static_cast<size_t>(PIPE_STAGES) * 2 * N * sizeof(T) + static_cast<size_t>(N) * sizeof(float) + 64;
-  if (smem > 200 * 1024) return false;
-  auto kern = rms_bwd_pipe_kernel<T>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  long long blocks = resident_blocks(kern, PIPE_THREADS, smem);
-  if (blocks > rms_norm_bwd_num_partials()) blocks = rms_norm_bwd_num_partials();
-  if (blocks > M) blocks = M;
-  if (blocks < 1) blocks = 1;
-  kern<<<static_cast<int>(blocks), PIPE_THREADS, smem, s>>>(static_cast<const T*>(dout), static_cast<const T*>(x), static_cast<const T*>(w), inv_rms,
-                                                    static_cast<T*>(dx), dw_partial, M, N, zc);
-  rms_dw_reduce_kernel<T><<<(N + 31) / 32, 256, 0, s>>>(dw_partial, static_cast<int>(blocks), N, static_cast<T*>(dw));
-  return true;
-}
-
 template <typename T, int VPL>
 void rms_fwd_block_launch(const void* x, const void* w, void* out, float* inv_rms, long long M, int N, float eps,
                           bool zc, cudaStream_t s) {
@@ -694,12 +579,6 @@ void rms_norm_fwd(const void* x, const void* w, void* out, float* inv_rms, long 
 void rms_norm_bwd(const void* dout, const void* x, const void* w, const float* inv_rms, void* dx, void* dw,
                   float* dw_partial, long long M, int N, bool zero_centered, int dtype, cudaStream_t stream) {
   if (N % 8 != 0) throw std::runtime_error("d9d rms_norm: N must be a multiple of 8");
-  if (N > 2048 && dtype != 1) {  // wide 2-byte rows: shared-memory ring fed by bulk async copies
-    const bool done = (dtype == 0)
-        ? rms_bwd_pipe_launch<__nv_bfloat16>(dout, x, w, inv_rms, dx, dw, dw_partial, M, N, zero_centered, stream)
-        : rms_bwd_pipe_launch<__half>(dout, x, w, inv_rms, dx, dw, dw_partial, M, N, zero_centered, stream);
-    if (done) return;
-  }
   if (dtype == 0) D9D_RMS_BWD_DISPATCH(__nv_bfloat16, dout, x, w, inv_rms, dx, dw, dw_partial, M, N, zero_centered, stream);
   else if (dtype == 1) D9D_RMS_BWD_DISPATCH(float, dout, x, w, inv_rms, dx, dw, dw_partial, M, N, zero_centered, stream);
   else D9D_RMS_BWD_DISPATCH(__half, dout, x, w, inv_rms, dx, dw, dw_partial, M, N, zero_centered, stream);
