@@ -1,0 +1,94 @@
+"""Local-vs-parallel self-consistency of whole models over several meshes (CPU/gloo, 4 ranks).
+
+For every mesh the model is parallelised with its family plan, driven through the loop's gradient machinery for one
+step, and the *global* gradient of every parameter (DTensors gathered) must equal the single-process gradient over the
+whole global batch.  Mirrors the reference's ``modules/model/sequence/*/test_distributed.py`` (8 GPUs there).
+"""
+
+import pytest
+import torch
+
+from tests.dist_utils import run_distributed
+
+pytestmark = pytest.mark.dist
+
+MESHES = {
+    "dpr4": dict(data_parallel_replicate=4),
+    "dps4": dict(data_parallel_shard=4),
+    "dpr2_dps2": dict(data_parallel_replicate=2, data_parallel_shard=2),
+    "dpr4_ep2": dict(data_parallel_replicate=4, expert_parallel=2),
+    "dpr2_dps2_ep4": dict(data_parallel_replicate=2, data_parallel_shard=2, expert_parallel=4),
+}
+
+
+def _build(moe: bool):
+    from tests.helpers_train import dense_params, moe_params
+
+    from d9d_b200.module.block.hidden_states_aggregator import HiddenStatesAggregationMode
+    from d9d_b200.pipelining.api import PipelineStageInfo
+
+    torch.manual_seed(5)
+    if moe:
+        from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM as Cls
+
+        params = moe_params()
+    else:
+        from d9d_b200.module.model.qwen3_dense import Qwen3DenseForCausalLM as Cls
+
+        params = dense_params()
+    model = Cls(params, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    model.reset_parameters()
+    return model
+
+
+def _batch(i):
+    g = torch.Generator().manual_seed(900 + i)
+    ids = torch.randint(0, 128, (2, 16), generator=g)
+    labels = torch.randint(0, 128, (2, 16), generator=g)
+    return ids, labels, torch.arange(16)[None].expand(2, -1)
+
+
+def _worker(rank, world_size, mesh_name, moe):
+    import torch.distributed as dist
+    from torch.distributed.tensor import DTensor
+
+    from d9d_b200.core.dist_context import BATCH_DOMAIN, DeviceMeshParameters
+    from d9d_b200.internals.grad_sync import GradientSynchronizer
+    from d9d_b200.pipelining.api import PipelineStageInfo
+
+    ctx = DeviceMeshParameters(**MESHES[mesh_name]).build()
+    model = _build(moe)
+    if moe:
+        from d9d_b200.module.parallelism.model.qwen3_moe import parallelize_qwen3_moe_for_causal_lm as plan
+    else:
+        from d9d_b200.module.parallelism.model.qwen3_dense import parallelize_qwen3_dense_for_causal_lm as plan
+    plan(ctx, model, PipelineStageInfo(0, 1))
+
+    params = list(model.parameters())
+    sync = GradientSynchronizer([params], bucket_size_mb=1, require_accumulations=1)
+    sync.bind()
+    dp_rank = ctx.mesh_for(BATCH_DOMAIN)["dp"].get_local_rank()
+    ids, labels, pos = _batch(dp_rank)
+    model(input_ids=ids, position_ids=pos, labels=labels)["logps"].sum().backward()
+    sync.wait()
+
+    ref = _build(moe)
+    for b in range(world_size):  # every rank is its own data-parallel replica on these meshes
+        ids, labels, pos = _batch(b)
+        ref(input_ids=ids, position_ids=pos, labels=labels)["logps"].sum().backward()
+
+    for (name, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, name
+        got = p.grad.full_tensor() if isinstance(p.grad, DTensor) else p.grad
+        torch.testing.assert_close(got, q.grad, rtol=2e-4, atol=2e-5, msg=lambda m: f"[{mesh_name}] {name}: {m}")  # noqa: B023
+    dist.barrier()
+
+
+@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr2_dps2"])
+def test_dense_model_matches_single_process(mesh_name):
+    run_distributed(_worker, 4, mesh_name, False)
+
+
+@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr4_ep2", "dpr2_dps2_ep4"])
+def test_moe_model_matches_single_process(mesh_name):
+    run_distributed(_worker, 4, mesh_name, True)
