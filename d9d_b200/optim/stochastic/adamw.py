@@ -71,10 +71,29 @@ class StochasticAdamW(Optimizer):
         return sd
 
     def load_state_dict(self, state_dict: StateDict) -> None:
+        """Restore moments, step counters, hyper-parameters and the rounding stream.
+
+        ``torch.optim.Optimizer.load_state_dict`` casts every floating-point state tensor to the *parameter* dtype, which
+        would silently truncate fp32 moments of bf16 parameters on resume, so the state is re-attached here as saved
+        (matched to the parameters by position, like the base class does).
+        """
         state_dict = dict(state_dict)
         if _GENERATOR_STATE_KEY in state_dict:
             self._generator.set_state(state_dict.pop(_GENERATOR_STATE_KEY))
-        super().load_state_dict(state_dict)
+        saved_groups, saved_state = state_dict["param_groups"], state_dict["state"]
+        if len(saved_groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        by_id: dict[int, torch.Tensor] = {}
+        for saved, group in zip(saved_groups, self.param_groups, strict=True):
+            if len(saved["params"]) != len(group["params"]):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            by_id.update(zip(saved["params"], group["params"], strict=True))
+            group.update({k: v for k, v in saved.items() if k != "params"})
+        self.state.clear()
+        for pid, entries in saved_state.items():
+            param = by_id[pid]
+            device = _local(param).device
+            self.state[param] = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in entries.items()}
         self._plans.clear()
 
     @torch.no_grad()
