@@ -1,4 +1,15 @@
 from .decoder_layer import MixtralLayer
+from .huggingface import (
+    MixtralExpertsFormat,
+    mapper_from_huggingface_mixtral,
+    mapper_from_huggingface_mixtral_for_causal_lm,
+    mapper_from_huggingface_mixtral_for_classification,
+    mapper_from_huggingface_mixtral_for_embedding,
+    mapper_to_huggingface_mixtral,
+    mapper_to_huggingface_mixtral_for_causal_lm,
+    mapper_to_huggingface_mixtral_for_classification,
+    mapper_to_huggingface_mixtral_for_embedding,
+)
 from .model import MixtralForCausalLM, MixtralForClassification, MixtralForEmbedding, MixtralModel
 from .params import (
     MixtralForCausalLMParameters,
@@ -9,6 +20,7 @@ from .params import (
 )
 
 __all__ = [
+    "MixtralExpertsFormat",
     "MixtralForCausalLM",
     "MixtralForCausalLMParameters",
     "MixtralForClassification",
@@ -19,4 +31,12 @@ __all__ = [
     "MixtralLayerParameters",
     "MixtralModel",
     "MixtralParameters",
+    "mapper_from_huggingface_mixtral",
+    "mapper_from_huggingface_mixtral_for_causal_lm",
+    "mapper_from_huggingface_mixtral_for_classification",
+    "mapper_from_huggingface_mixtral_for_embedding",
+    "mapper_to_huggingface_mixtral",
+    "mapper_to_huggingface_mixtral_for_causal_lm",
+    "mapper_to_huggingface_mixtral_for_classification",
+    "mapper_to_huggingface_mixtral_for_embedding",
 ]

@@ -1,4 +1,14 @@
 from .decoder_layer import Qwen3DenseLayer
+from .huggingface import (
+    mapper_from_huggingface_qwen3_dense,
+    mapper_from_huggingface_qwen3_dense_for_causal_lm,
+    mapper_from_huggingface_qwen3_dense_for_classification,
+    mapper_from_huggingface_qwen3_dense_for_embedding,
+    mapper_to_huggingface_qwen3_dense,
+    mapper_to_huggingface_qwen3_dense_for_causal_lm,
+    mapper_to_huggingface_qwen3_dense_for_classification,
+    mapper_to_huggingface_qwen3_dense_for_embedding,
+)
 from .model import Qwen3DenseForCausalLM, Qwen3DenseForClassification, Qwen3DenseForEmbedding, Qwen3DenseModel
 from .params import (
     Qwen3DenseForCausalLMParameters,
@@ -19,4 +29,12 @@ __all__ = [
     "Qwen3DenseLayerParameters",
     "Qwen3DenseModel",
     "Qwen3DenseParameters",
+    "mapper_from_huggingface_qwen3_dense",
+    "mapper_from_huggingface_qwen3_dense_for_causal_lm",
+    "mapper_from_huggingface_qwen3_dense_for_classification",
+    "mapper_from_huggingface_qwen3_dense_for_embedding",
+    "mapper_to_huggingface_qwen3_dense",
+    "mapper_to_huggingface_qwen3_dense_for_causal_lm",
+    "mapper_to_huggingface_qwen3_dense_for_classification",
+    "mapper_to_huggingface_qwen3_dense_for_embedding",
 ]

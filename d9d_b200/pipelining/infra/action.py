@@ -40,9 +40,15 @@ class Action:
     def has_backward_work(self) -> bool:
         return self.kind in _BACKWARD
 
+    @property
+    def stage_idx(self) -> int:
+        return self.stage
+
+    @property
+    def microbatch_idx(self) -> int:
+        return self.microbatch
+
     def __str__(self) -> str:
-        if self.is_compute:
-            return f"{self.stage}{self.kind.value}{self.microbatch}"
         return f"{self.stage}{self.kind.value}{self.microbatch}"
 
 

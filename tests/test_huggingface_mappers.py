@@ -147,3 +147,102 @@ def test_qwen3_moe_matches_transformers():
         want = torch.nn.functional.cross_entropy(logits.view(-1, 96), labels.view(-1), reduction="none").view(2, 12)
         got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
     torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+
+def _load(ours, state):
+    missing, unexpected = ours.load_state_dict(state, strict=False)
+    assert not unexpected and all("rope" in k or "cos" in k or "sin" in k or "tokens_per_expert" in k for k in missing), (missing, unexpected)
+
+
+def _per_token_nll(hf_model, ids, pos, labels, vocab=96):
+    logits = hf_model(input_ids=ids, position_ids=pos).logits.float()
+    return torch.nn.functional.cross_entropy(logits.view(-1, vocab), labels.view(-1), reduction="none").view(labels.shape)
+
+
+def test_llama3_matches_transformers():
+    transformers = pytest.importorskip("transformers")
+    from d9d_b200.module.model.llama3 import (Llama3ForCausalLM, Llama3ForCausalLMParameters, Llama3LayerParameters, Llama3Parameters,
+                                              mapper_from_huggingface_llama3_for_causal_lm)
+
+    cfg = transformers.LlamaConfig(vocab_size=96, hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=2, head_dim=8, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=64,
+                                   tie_word_embeddings=False, attention_bias=False, mlp_bias=False)
+    torch.manual_seed(0)
+    hf_model = transformers.LlamaForCausalLM(cfg).eval()
+    p = Llama3ForCausalLMParameters(model=Llama3Parameters(
+        layer=Llama3LayerParameters(hidden_size=32, intermediate_size=48, num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-6,
+                                    head_dim=8), num_hidden_layers=2, rope_base=10000, max_position_ids=64, **VOCAB))
+    ours = Llama3ForCausalLM(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    ours.reset_parameters()
+    _load(ours, _run(mapper_from_huggingface_llama3_for_causal_lm(p), dict(hf_model.state_dict())))
+    ids, labels = torch.randint(0, 96, (2, 12)), torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        want = _per_token_nll(hf_model, ids, pos, labels)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+
+def test_mixtral_matches_transformers():
+    transformers = pytest.importorskip("transformers")
+    from d9d_b200.module.model.mixtral import mapper_from_huggingface_mixtral_for_causal_lm
+
+    cfg = transformers.MixtralConfig(vocab_size=96, hidden_size=32, intermediate_size=16, num_hidden_layers=2, num_attention_heads=4,
+                                     num_key_value_heads=2, head_dim=8, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=64,
+                                     tie_word_embeddings=False, num_local_experts=4, num_experts_per_tok=2, router_aux_loss_coef=0.0,
+                                     output_router_logits=False, sliding_window=None, router_jitter_noise=0.0)
+    torch.manual_seed(0)
+    hf_model = transformers.MixtralForCausalLM(cfg).eval()
+    hf_state = dict(hf_model.state_dict())
+    fmt = "fused" if any(k.endswith("experts.gate_up_proj") for k in hf_state) else "module_list"
+    p, ours = _moe_model("mixtral")
+    _load(ours, _run(mapper_from_huggingface_mixtral_for_causal_lm(p, fmt), hf_state))
+    ids, labels = torch.randint(0, 96, (2, 12)), torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        want = _per_token_nll(hf_model, ids, pos, labels)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+
+def test_qwen3_classification_and_embedding_match_transformers():
+    """HF classifies on the last token of every row; we select the same tokens with ``pooling_mask``."""
+    transformers = pytest.importorskip("transformers")
+    from d9d_b200.module.model.qwen3_dense import (Qwen3DenseForClassification, Qwen3DenseForClassificationParameters,
+                                                   Qwen3DenseForEmbedding, Qwen3DenseForEmbeddingParameters, Qwen3DenseLayerParameters,
+                                                   Qwen3DenseParameters, mapper_from_huggingface_qwen3_dense_for_classification,
+                                                   mapper_from_huggingface_qwen3_dense_for_embedding)
+
+    cfg = transformers.Qwen3Config(vocab_size=96, hidden_size=32, intermediate_size=48, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=2, head_dim=8, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=64,
+                                   tie_word_embeddings=False, attention_bias=False, num_labels=3, pad_token_id=None)
+    torch.manual_seed(0)
+    hf_cls = transformers.Qwen3ForSequenceClassification(cfg).eval()
+    base = Qwen3DenseParameters(layer=Qwen3DenseLayerParameters(hidden_size=32, intermediate_size=48, num_attention_heads=4,
+                                                                num_key_value_heads=2, rms_norm_eps=1e-6, head_dim=8),
+                                num_hidden_layers=2, rope_base=10000, max_position_ids=64, **VOCAB)
+    ids = torch.randint(0, 96, (1, 12))  # batch of one: without a pad token HF only accepts single rows
+    pos = torch.arange(12)[None]
+    last = torch.zeros(1, 12, dtype=torch.long)
+    last[:, -1] = 1
+
+    p = Qwen3DenseForClassificationParameters(model=base, num_labels=3, classifier_dropout=0.0)
+    ours = Qwen3DenseForClassification(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False).eval()
+    ours.reset_parameters()
+    _load(ours, _run(mapper_from_huggingface_qwen3_dense_for_classification(p), dict(hf_cls.state_dict())))
+    with torch.no_grad():
+        want = hf_cls(input_ids=ids, position_ids=pos).logits.float()
+        got = ours(input_ids=ids, position_ids=pos, pooling_mask=last)["scores"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+    p = Qwen3DenseForEmbeddingParameters(model=base)
+    ours = Qwen3DenseForEmbedding(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False).eval()
+    ours.reset_parameters()
+    _load(ours, _run(mapper_from_huggingface_qwen3_dense_for_embedding(p), dict(hf_cls.model.state_dict())))
+    with torch.no_grad():
+        hidden = hf_cls.model(input_ids=ids, position_ids=pos).last_hidden_state.float()
+        got = ours(input_ids=ids, position_ids=pos, pooling_mask=last)["embeddings"]
+    want = hidden[:, -1]
+    if got.norm(dim=-1).sub(1).abs().max() < 1e-4:  # the head L2-normalises by default
+        want = torch.nn.functional.normalize(want, dim=-1)
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
