@@ -70,8 +70,9 @@ class MetricAccumulator(Stateful):
         return {"local": self._local, "synchronized": self._synchronized, "is_synchronized": self._is_synchronized}
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        self._local = state_dict["local"].to(self._local.device)
-        self._synchronized = state_dict["synchronized"].to(self._synchronized.device)
+        # own copies: the accumulators are updated in place and must not alias the caller's tensors
+        self._local = state_dict["local"].detach().clone().to(self._local.device)
+        self._synchronized = state_dict["synchronized"].detach().clone().to(self._synchronized.device)
         self._is_synchronized = bool(state_dict["is_synchronized"])
 
 

@@ -190,14 +190,20 @@ def _pp_worker(rank, world, cfg_json, n_mb, freeze):
         losses[mb] = loss.detach()
         return loss
 
+    results = {}
+
+    def result_fn(outputs, mb):
+        results[mb] = outputs["hidden"].detach().clone()
+
     hits = {}
-    info, modules = build_schedule(ctx, n_mb, cfg, lambda st: _StageModel(st, freeze_some=freeze), loss_fn)
+    is_inference = cfg.schedule == "inference"
+    info, modules = build_schedule(ctx, n_mb, cfg, lambda st: _StageModel(st, freeze_some=freeze),
+                                   result_fn if is_inference else loss_fn)
     for mi, mod in enumerate(modules):
         for n, p in mod.named_parameters():
             if p.requires_grad:
                 hits[(mi, n)] = 0
                 p.register_post_accumulate_grad_hook(lambda _p, k=(mi, n): hits.__setitem__(k, hits[k] + 1))
-    is_inference = cfg.schedule == "inference"
     for _ in range(2):  # two steps: caches must be drained between them
         for mod in modules:
             mod.zero_grad()
@@ -215,6 +221,12 @@ def _pp_worker(rank, world, cfg_json, n_mb, freeze):
     for s, st in enumerate(ref_stages):
         h = st(x=h, scale=scale)["hidden"] if s == 0 else st(hidden=h, scale=scale)["hidden"]
     if is_inference:
+        if info.has_last_stage:  # every microbatch reached the result callback with the sequential model's output
+            assert sorted(results) == list(range(n_mb))
+            torch.testing.assert_close(torch.cat([results[i] for i in range(n_mb)]), h.detach(), rtol=1e-5, atol=1e-6)
+        else:
+            assert not results
+        assert all(p.grad is None for mod in modules for p in mod.parameters())
         return
     ((h - target) ** 2).sum().backward()
     for mod in modules:
