@@ -5,75 +5,25 @@ from pathlib import Path
 from tqdm import tqdm
 
 from d9d_b200.core.dist_context import DeviceMeshParameters
-from d9d_b200.internals.determinism import set_seeds
 from d9d_b200.internals.pipeline_state import PipelineStateHandler
-from d9d_b200.loop.component import (
-    BatchMaths,
-    DataLoaderFactory,
-    GradientClipper,
-    GradientManager,
-    JobLogger,
-    JobProfiler,
-    LossComputer,
-    ManualGarbageCollector,
-    ModelStageExporter,
-    ModelStageFactory,
-    OptimizerFactory,
-    StateCheckpointer,
-    Stepper,
-    TimeoutManager,
-    TrainTaskOperator,
-)
+from d9d_b200.loop import component as parts
+from d9d_b200.loop import control
 from d9d_b200.loop.config import TrainerConfig
-from d9d_b200.loop.control import (
-    CreateMetricsContext,
-    DatasetProvider,
-    FinalizeContext,
-    LRSchedulerProvider,
-    ModelProvider,
-    OptimizerProvider,
-    RegisterModelEventsContext,
-    RegisterTaskEventsContext,
-    TrainTaskProvider,
-    TrainTaskProviderContext,
-)
-from d9d_b200.loop.event import EventBus
-from d9d_b200.loop.event.catalogue.common import (
-    EventConfigurationStartedContext,
-    EventDataLoaderReadyContext,
-    EventModelStagesReadyContext,
-    EventStepContext,
-)
-from d9d_b200.loop.event.catalogue.train import (
-    EVENT_TRAIN_CONFIG_STARTED,
-    EVENT_TRAIN_DATA_LOADER_READY,
-    EVENT_TRAIN_FINISHED,
-    EVENT_TRAIN_FORWARD_BACKWARD_POST,
-    EVENT_TRAIN_FORWARD_BACKWARD_PRE,
-    EVENT_TRAIN_LR_SCHEDULER_READY,
-    EVENT_TRAIN_MODEL_STAGES_READY,
-    EVENT_TRAIN_OPTIMIZER_READY,
-    EVENT_TRAIN_OPTIMIZER_STEP_POST,
-    EVENT_TRAIN_OPTIMIZER_STEP_PRE,
-    EVENT_TRAIN_READY,
-    EVENT_TRAIN_STEP_POST,
-    EVENT_TRAIN_STEP_PRE,
-    EventLRSchedulerReadyContext,
-    EventOptimizerReadyContext,
-    EventTrainFinishedContext,
-    EventTrainReadyContext,
-)
+from d9d_b200.loop.event.catalogue import common as shared_events
+from d9d_b200.loop.event.catalogue import train as events
 from d9d_b200.loop.state import TrainJobState
 from d9d_b200.metric.impl.container import ComposeMetric
+
+from ._assembly import build_housekeeping, lay_foundation
 
 
 class TrainingConfigurator:
     """Assembles a :class:`Trainer` from the mesh, the trainer config and the user's providers
     (reference ``d9d/loop/run/train.py:68-248``)."""
 
-    def __init__(self, mesh: DeviceMeshParameters, parameters: TrainerConfig, task_provider: TrainTaskProvider,
-                 model_provider: ModelProvider, data_provider: DatasetProvider, optimizer_provider: OptimizerProvider,
-                 lr_scheduler_provider: LRSchedulerProvider):
+    def __init__(self, mesh: DeviceMeshParameters, parameters: TrainerConfig, task_provider: control.TrainTaskProvider,
+                 model_provider: control.ModelProvider, data_provider: control.DatasetProvider, optimizer_provider: control.OptimizerProvider,
+                 lr_scheduler_provider: control.LRSchedulerProvider):
         self._mesh = mesh
         self._parameters = parameters
         self._task_provider = task_provider
@@ -84,53 +34,51 @@ class TrainingConfigurator:
 
     def _build_state(self) -> TrainJobState:
         cfg = self._parameters
-        ctx = self._mesh.build()
-        set_seeds(ctx, seed=cfg.determinism.base_seed)
-        timeout = TimeoutManager(dist_context=ctx, config=cfg.timeout)
-        timeout.set_init()
+        base = lay_foundation(self._mesh, cfg, lambda ctx: self._task_provider(control.TrainTaskProviderContext(dist_context=ctx)),
+                              self._model_provider, cfg.batching, cfg.pipelining, events.EVENT_TRAIN_CONFIG_STARTED)
+        ctx, bus, maths, task = base.ctx, base.bus, base.maths, base.task
 
-        task = self._task_provider(TrainTaskProviderContext(dist_context=ctx))
-        bus = EventBus()
-        self._model_provider.register_events(RegisterModelEventsContext(dist_context=ctx, event_bus=bus))
-        task.register_events(RegisterTaskEventsContext(dist_context=ctx, event_bus=bus))
-        bus.trigger(EVENT_TRAIN_CONFIG_STARTED, EventConfigurationStartedContext(dist_context=ctx))
-
-        maths = BatchMaths(dist_context=ctx, config_batching=cfg.batching, config_pipelining=cfg.pipelining)
-        loader = DataLoaderFactory(dist_context=ctx, provider=self._data_provider, config_data_loading=cfg.data_loading,
-                                   batch_maths=maths).build_dataloader_for_train_job()
-        bus.trigger(EVENT_TRAIN_DATA_LOADER_READY, EventDataLoaderReadyContext(data_loader=loader))
-
+        loader = parts.DataLoaderFactory(dist_context=ctx, provider=self._data_provider, config_data_loading=cfg.data_loading,
+                                         batch_maths=maths).build_dataloader_for_train_job()
+        bus.trigger(events.EVENT_TRAIN_DATA_LOADER_READY, shared_events.EventDataLoaderReadyContext(data_loader=loader))
         # one step consumes a whole accumulation group (the reference counts loader batches here, which overstates
         # the number of optimizer steps by the accumulation factor)
-        stepper = Stepper(initial_step=0, total_steps=len(loader) // maths.num_microbatches_gradient_accumulation)
+        stepper = parts.Stepper(initial_step=0, total_steps=len(loader) // maths.num_microbatches_gradient_accumulation)
+
         pipeline_state = PipelineStateHandler(sharding_spec={}, num_shards=maths.num_microbatches_pipelining)
-        loss_computer = LossComputer(state=pipeline_state, task=task, stepper=stepper)
-        schedule, modules = ModelStageFactory(model_provider=self._model_provider, dist_context=ctx, batch_maths=maths,
-                                              config_model=cfg.model_stage_factory, config_pipelining=cfg.pipelining,
-                                              pipeline_callback=loss_computer).build_pipeline_and_modules()
-        bus.trigger(EVENT_TRAIN_MODEL_STAGES_READY, EventModelStagesReadyContext(modules=modules.modules))
+        schedule, modules = parts.ModelStageFactory(
+            model_provider=self._model_provider, dist_context=ctx, batch_maths=maths, config_model=cfg.model_stage_factory,
+            config_pipelining=cfg.pipelining, pipeline_callback=parts.LossComputer(state=pipeline_state, task=task, stepper=stepper),
+        ).build_pipeline_and_modules()
+        bus.trigger(events.EVENT_TRAIN_MODEL_STAGES_READY, shared_events.EventModelStagesReadyContext(modules=modules.modules))
+        metrics = ComposeMetric(task.create_metrics(control.CreateMetricsContext()).metrics)
 
-        metrics = ComposeMetric(task.create_metrics(CreateMetricsContext()).metrics)
-        operator = TrainTaskOperator(dist_context=ctx, task=task, pipeline=schedule, pipeline_state=pipeline_state, metrics=metrics)
-        clipper = GradientClipper(dist_context=ctx, tracked_modules=modules, config=cfg.gradient_clipping, stepper=stepper)
-        optimizer, scheduler = OptimizerFactory(dist_context=ctx, tracked_modules=modules, optimizer_provider=self._optimizer_provider,
-                                                lr_scheduler_provider=self._lr_scheduler_provider, stepper=stepper).build_optimizer_and_scheduler()
-        bus.trigger(EVENT_TRAIN_OPTIMIZER_READY, EventOptimizerReadyContext(optimizer=optimizer))
-        bus.trigger(EVENT_TRAIN_LR_SCHEDULER_READY, EventLRSchedulerReadyContext(lr_scheduler=scheduler))
+        optimizer, scheduler = parts.OptimizerFactory(
+            dist_context=ctx, tracked_modules=modules, optimizer_provider=self._optimizer_provider,
+            lr_scheduler_provider=self._lr_scheduler_provider, stepper=stepper,
+        ).build_optimizer_and_scheduler()
+        bus.trigger(events.EVENT_TRAIN_OPTIMIZER_READY, events.EventOptimizerReadyContext(optimizer=optimizer))
+        bus.trigger(events.EVENT_TRAIN_LR_SCHEDULER_READY, events.EventLRSchedulerReadyContext(lr_scheduler=scheduler))
 
-        gc = ManualGarbageCollector(dist_ctx=ctx, config=cfg.gc, step=stepper)
-        checkpointer = StateCheckpointer(dist_context=ctx, stepper=stepper, config=cfg.checkpointing, gc=gc, run_name=cfg.run.name)
-        profiler = JobProfiler(dist_context=ctx, stepper=stepper, config=cfg.profiling)
-        exporter = ModelStageExporter(model_provider=self._model_provider, dist_context=ctx, modules=modules)
-        grad_manager = GradientManager(dist_context=ctx, tracked_modules=modules, batch_maths=maths, config=cfg.gradient_manager)
+        # gradients: the manager hands its 1/sum(w) scale to optimizers that can fold it into their update kernel, and the
+        # clipper multiplies its coefficient into the same pending scalar
+        grad_manager = parts.GradientManager(dist_context=ctx, tracked_modules=modules, batch_maths=maths, config=cfg.gradient_manager)
         grad_manager.bind_optimizer(optimizer)
+        clipper = parts.GradientClipper(dist_context=ctx, tracked_modules=modules, config=cfg.gradient_clipping, stepper=stepper)
         clipper.bind_gradient_manager(grad_manager)
-        logger = JobLogger(dist_context=ctx, config=cfg.logging, metrics=metrics, stepper=stepper, run_config=cfg.run,
-                           additional_hparams={"task": task.dump_hparams(), "model": self._model_provider.dump_hparams()})
-        return TrainJobState(dist_context=ctx, data_loader=loader, stepper=stepper, tracked_modules=modules, garbage_collector=gc,
-                             batch_maths=maths, checkpointer=checkpointer, optimizer=optimizer, task=task, lr_scheduler=scheduler,
-                             gradient_clipper=clipper, profiler=profiler, exporter=exporter, metrics=metrics, logger=logger,
-                             gradient_manager=grad_manager, timeout_manager=timeout, task_operator=operator, event_bus=bus)
+
+        house = build_housekeeping(ctx, cfg, stepper, run_name=cfg.run.name)
+        hparams = {"task": task.dump_hparams(), "model": self._model_provider.dump_hparams()}
+        return TrainJobState(
+            dist_context=ctx, event_bus=bus, task=task, batch_maths=maths, data_loader=loader, stepper=stepper, tracked_modules=modules,
+            task_operator=parts.TrainTaskOperator(dist_context=ctx, task=task, pipeline=schedule, pipeline_state=pipeline_state,
+                                                  metrics=metrics),
+            metrics=metrics, optimizer=optimizer, lr_scheduler=scheduler, gradient_manager=grad_manager, gradient_clipper=clipper,
+            logger=parts.JobLogger(dist_context=ctx, config=cfg.logging, metrics=metrics, stepper=stepper, run_config=cfg.run,
+                                   additional_hparams=hparams),
+            exporter=parts.ModelStageExporter(model_provider=self._model_provider, dist_context=ctx, modules=modules),
+            garbage_collector=house.gc, checkpointer=house.checkpointer, profiler=house.profiler, timeout_manager=base.timeout,
+        )
 
     def configure(self) -> "Trainer":
         return Trainer(self._build_state())
@@ -160,7 +108,7 @@ class Trainer:
             s.dist_context.logger.info("Already trained fully, will do nothing")
             return
         s.dist_context.wait_world()
-        step_ctx = EventStepContext(stepper=s.stepper)
+        step_ctx = shared_events.EventStepContext(stepper=s.stepper)
         with (
             tqdm(desc="Training", total=s.stepper.total_steps, initial=s.stepper.current_step,
                  disable=not s.dist_context.is_local_main_process) as bar,
@@ -172,11 +120,11 @@ class Trainer:
             s.logger.install(),
         ):
             run.set_context({"stage": "train"})
-            s.event_bus.trigger(EVENT_TRAIN_READY, EventTrainReadyContext(run=run))
+            s.event_bus.trigger(events.EVENT_TRAIN_READY, events.EventTrainReadyContext(run=run))
             for batch_group in s.data_loader:
                 run.set_step(s.stepper.current_step)
-                s.event_bus.trigger(EVENT_TRAIN_STEP_PRE, step_ctx)
-                with s.event_bus.bounded(EVENT_TRAIN_FORWARD_BACKWARD_PRE, EVENT_TRAIN_FORWARD_BACKWARD_POST, step_ctx):
+                s.event_bus.trigger(events.EVENT_TRAIN_STEP_PRE, step_ctx)
+                with s.event_bus.bounded(events.EVENT_TRAIN_FORWARD_BACKWARD_PRE, events.EVENT_TRAIN_FORWARD_BACKWARD_POST, step_ctx):
                     for batch in batch_group:
                         result = s.task_operator.forward_backward(batch)
                         if result is not None:
@@ -184,7 +132,7 @@ class Trainer:
                 s.logger.trigger_sync()
                 s.gradient_manager.sync_and_scale()
                 s.gradient_clipper.clip_and_log(run)
-                with s.event_bus.bounded(EVENT_TRAIN_OPTIMIZER_STEP_PRE, EVENT_TRAIN_OPTIMIZER_STEP_POST, step_ctx):
+                with s.event_bus.bounded(events.EVENT_TRAIN_OPTIMIZER_STEP_PRE, events.EVENT_TRAIN_OPTIMIZER_STEP_POST, step_ctx):
                     s.optimizer.step()
                 s.lr_scheduler.step()
                 s.logger.log(run, loss_value=s.gradient_manager.compute_global_loss())
@@ -193,15 +141,15 @@ class Trainer:
                 if profiler:
                     profiler.step()
                 s.timeout_manager.set_periodic()
-                s.event_bus.trigger(EVENT_TRAIN_STEP_POST, step_ctx)
+                s.event_bus.trigger(events.EVENT_TRAIN_STEP_POST, step_ctx)
                 s.stepper.step()
                 s.checkpointer.checkpoint_if_needed(s)
                 bar.update()
                 if s.stepper.current_step >= s.stepper.total_steps:
                     break
             s.logger.flush(run)
-            s.task.finalize(FinalizeContext())
-            s.event_bus.trigger(EVENT_TRAIN_FINISHED, EventTrainFinishedContext())
+            s.task.finalize(control.FinalizeContext())
+            s.event_bus.trigger(events.EVENT_TRAIN_FINISHED, events.EventTrainFinishedContext())
 
     def export(self, export_to: Path, load_checkpoint: bool) -> None:
         if load_checkpoint:

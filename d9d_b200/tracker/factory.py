@@ -1,5 +1,7 @@
 from __future__ import annotations
 
+import importlib.util
+import sys
 from typing import Annotated
 
 from pydantic import Field
@@ -19,10 +21,10 @@ def tracker_from_config(config: AimConfig | NullTrackerConfig | JsonlTrackerConf
     if isinstance(config, JsonlTrackerConfig):
         return JsonlTracker.from_config(config)
     if isinstance(config, AimConfig):
-        try:
-            from .provider.aim.tracker import AimTracker
-        except ImportError as exc:
+        if "aim" not in sys.modules and importlib.util.find_spec("aim") is None:  # fail at configuration time, not at the first step
             raise ImportError(f"The tracker configuration {config.provider} could not be loaded - ensure these "
-                              "dependencies are installed: aim") from exc
+                              "dependencies are installed: aim")
+        from .provider.aim.tracker import AimTracker
+
         return AimTracker.from_config(config)
     raise TypeError(f"unknown tracker config {type(config).__name__}")

@@ -1,67 +1,88 @@
+"""Aim backend (reference ``d9d/tracker/provider/aim/tracker.py``).
+
+``aim`` is an optional dependency and is imported when a run is opened, so configs mentioning this tracker can be
+parsed - and the tracker constructed, checkpointed and restored - on machines without it.
+"""
+
 from __future__ import annotations
 
+import importlib
 from collections.abc import Generator
 from contextlib import contextmanager
-from typing import Any, Self
+from typing import Any, Self, TypedDict
 
 import torch
-from aim import Distribution, Run  # optional dependency: importing this module without aim raises ImportError
 
 from d9d_b200.tracker.base import BaseTracker, BaseTrackerRun, RunConfig
 
 from .config import AimConfig
 
 
+class AimState(TypedDict):
+    """Checkpointed tracker state: the hash of the Aim run to continue after a restart."""
+
+    restart_hash: str | None
+
+
+def _aim() -> Any:
+    try:
+        return importlib.import_module("aim")
+    except ImportError as exc:
+        raise ImportError("The Aim tracker needs the optional `aim` package") from exc
+
+
 class AimRun(BaseTrackerRun):
-    def __init__(self, run: Run):
-        self._run = run
+    """Forwards scalars / histograms to an ``aim.Run``, stamping them with the current step and tag context."""
+
+    def __init__(self, run: Any):
+        self._sink = run
         self._step = 0
-        self._context: dict[str, str] = {}
+        self._tags: dict[str, str] = {}
 
     def set_step(self, step: int) -> None:
         self._step = step
 
     def set_context(self, context: dict[str, str]) -> None:
-        self._context = context
+        self._tags = dict(context)
 
-    def _ctx(self, context: dict[str, str] | None) -> dict[str, str]:
-        return self._context if context is None else {**self._context, **context}
+    def _emit(self, name: str, value: Any, extra_tags: dict[str, str] | None) -> None:
+        tags = self._tags if not extra_tags else self._tags | extra_tags
+        self._sink.track(value, name=name, step=self._step, context=tags)
 
     def scalar(self, name: str, value: float, context: dict[str, str] | None = None) -> None:
-        self._run.track(name=name, value=value, context=self._ctx(context), step=self._step)
+        self._emit(name, value, context)
 
     def bins(self, name: str, values: torch.Tensor, context: dict[str, str] | None = None) -> None:
-        self._run.track(name=name, value=Distribution(hist=values.numpy(), bin_range=(0, values.shape[0])),
-                        context=self._ctx(context), step=self._step)
+        counts = values.detach().cpu().numpy()
+        self._emit(name, _aim().Distribution(hist=counts, bin_range=(0, counts.shape[0])), context)
 
 
 class AimTracker(BaseTracker[AimConfig]):
-    """Aim tracker that remembers the run hash in its state dict so a restarted job resumes the same run."""
+    """Opens Aim runs; the run hash travels in the job checkpoint so that a restarted job appends to the same run."""
 
     def __init__(self, config: AimConfig):
         self._config = config
-        self._restart_hash: str | None = None
-
-    def state_dict(self) -> dict[str, Any]:
-        return {"restart_hash": self._restart_hash}
-
-    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        self._restart_hash = state_dict["restart_hash"]
-
-    @contextmanager
-    def open(self, properties: RunConfig) -> Generator[BaseTrackerRun, None, None]:
-        run = Run(run_hash=self._restart_hash, repo=self._config.repo, log_system_params=self._config.log_system_params,
-                  capture_terminal_logs=self._config.capture_terminal_logs,
-                  system_tracking_interval=self._config.system_tracking_interval)
-        run.name = properties.name
-        run.description = properties.description
-        run["hparams"] = properties.hparams
-        self._restart_hash = run.hash
-        try:
-            yield AimRun(run)
-        finally:
-            run.close()
+        self._state = AimState(restart_hash=None)
 
     @classmethod
     def from_config(cls, config: AimConfig) -> Self:
         return cls(config)
+
+    def state_dict(self) -> dict[str, Any]:
+        return dict(self._state)
+
+    def load_state_dict(self, state_dict: dict[str, Any]) -> None:
+        self._state = AimState(restart_hash=state_dict["restart_hash"])
+
+    @contextmanager
+    def open(self, properties: RunConfig) -> Generator[BaseTrackerRun, None, None]:
+        cfg = self._config
+        run = _aim().Run(run_hash=self._state["restart_hash"], repo=cfg.repo, log_system_params=cfg.log_system_params,
+                         capture_terminal_logs=cfg.capture_terminal_logs, system_tracking_interval=cfg.system_tracking_interval)
+        try:
+            run.name, run.description = properties.name, properties.description
+            run["hparams"] = properties.hparams
+            self._state["restart_hash"] = run.hash
+            yield AimRun(run)
+        finally:
+            run.close()

@@ -216,3 +216,66 @@ def test_inference_loop_runs_the_task_over_every_batch(tmp_path):
                                 model_provider=LMProvider(dense_params()), data_provider=SyntheticDataProvider(num_samples=18)).configure()
     job.infer()
     assert task.batches == 5 and task.tokens == 18 * 16  # the ragged last batch is kept
+
+
+def test_aim_tracker_against_a_stub_backend(monkeypatch):
+    """The Aim adapter: run properties, step / context stamping, histogram conversion, run-hash resume
+    (reference ``test/d9d_test/tracker/test_aim.py``) - exercised against a stand-in ``aim`` module."""
+    import sys
+    import types
+
+    from d9d_b200.tracker import RunConfig
+    from d9d_b200.tracker.factory import tracker_from_config
+    from d9d_b200.tracker.provider.aim.config import AimConfig
+
+    config = AimConfig(repo="/tmp/aim-repo", log_system_params=False, capture_terminal_logs=False)
+    monkeypatch.delitem(sys.modules, "aim", raising=False)
+    import importlib.util
+
+    if importlib.util.find_spec("aim") is None:
+        with pytest.raises(ImportError):
+            tracker_from_config(config)
+
+    opened = []
+
+    class FakeRun(dict):
+        def __init__(self, run_hash=None, **kwargs):
+            super().__init__()
+            self.hash = run_hash or f"hash-{len(opened)}"
+            self.kwargs, self.tracked, self.closed = kwargs, [], False
+            opened.append(self)
+
+        def track(self, value, name, step, context):
+            self.tracked.append((name, value, step, dict(context)))
+
+        def close(self):
+            self.closed = True
+
+    class FakeDistribution:
+        def __init__(self, hist, bin_range):
+            self.hist, self.bin_range = hist, bin_range
+
+    monkeypatch.setitem(sys.modules, "aim", types.SimpleNamespace(Run=FakeRun, Distribution=FakeDistribution))
+    tracker = tracker_from_config(config)
+    assert tracker.state_dict() == {"restart_hash": None}
+    with tracker.open(RunConfig(name="exp", description="d", hparams={"lr": 1e-3})) as run:
+        run.set_context({"stage": "train"})
+        run.set_step(7)
+        run.scalar("loss", 0.5)
+        run.scalar("loss", 0.25, context={"subset": "val"})
+        run.bins("tokens_per_expert", torch.tensor([3, 0, 5]))
+    backend = opened[0]
+    assert backend.closed and backend.name == "exp" and backend["hparams"] == {"lr": 1e-3}
+    assert backend.kwargs["repo"] == "/tmp/aim-repo" and backend.kwargs["log_system_params"] is False
+    assert backend.tracked[0] == ("loss", 0.5, 7, {"stage": "train"})
+    assert backend.tracked[1] == ("loss", 0.25, 7, {"stage": "train", "subset": "val"})
+    name, dist, step, ctx = backend.tracked[2]
+    assert name == "tokens_per_expert" and list(dist.hist) == [3, 0, 5] and dist.bin_range == (0, 3) and step == 7
+
+    state = tracker.state_dict()
+    assert state == {"restart_hash": "hash-0"}
+    resumed = tracker_from_config(config)
+    resumed.load_state_dict(state)
+    with resumed.open(RunConfig(name="exp", description=None)):
+        pass
+    assert opened[1].hash == "hash-0"  # the restarted job appends to the same run
