@@ -2,6 +2,7 @@
 (reference ``d9d/dataset``) plus a synthetic token dataset for benchmarks."""
 
 from .buffer_sorted import BufferSortedDataset, DatasetImplementingSortKeyProtocol
+from .context_parallel import context_parallel_rank_and_size, shard_batch_for_context_parallel
 from .padding import PaddingSide1D, pad_stack_1d
 from .pooling import TokenPoolingType, token_pooling_mask_from_attention_mask
 from .sharded import ShardedDataset, ShardIndexingMode, shard_dataset_data_parallel
@@ -15,7 +16,9 @@ __all__ = [
     "ShardedDataset",
     "SyntheticTokenDataset",
     "TokenPoolingType",
+    "context_parallel_rank_and_size",
     "pad_stack_1d",
+    "shard_batch_for_context_parallel",
     "shard_dataset_data_parallel",
     "token_pooling_mask_from_attention_mask",
 ]

@@ -1,0 +1,42 @@
+from __future__ import annotations
+
+from typing import Any, TypeVar
+
+import torch
+from torch.utils import _pytree as pytree
+
+from d9d_b200.core.dist_context import BATCH_DOMAIN, DistributedContext
+from d9d_b200.kernel.context_parallel import ContextParallelLayout, shard_sequence
+
+T = TypeVar("T")
+
+
+def context_parallel_rank_and_size(dist_context: DistributedContext) -> tuple[int, int]:
+    """This rank's index in / the size of its context-parallel group (``(0, 1)`` without context parallelism)."""
+    if not dist_context.mesh_params.is_distributed:
+        return 0, 1
+    cp = dist_context.mesh_for(BATCH_DOMAIN)["cp"]
+    return cp.get_local_rank(), cp.size()
+
+
+def shard_batch_for_context_parallel(batch: T, dist_context: DistributedContext, seq_dim: int = 1,
+                                     layout: ContextParallelLayout = ContextParallelLayout.zigzag) -> T:
+    """Keep only this context-parallel rank's tokens of every tensor in ``batch`` (any pytree; tensors with fewer than
+    ``seq_dim + 1`` dims and non-tensors are returned unchanged).
+
+    Call it in ``Task.build_forward_inputs`` on the collated batch - ``input_ids``, ``position_ids`` (which keep their
+    *global* values, so rotary embeddings stay correct), ``labels`` and masks are cut consistently.  Ranks of one
+    context-parallel group read the same samples (the data-parallel sharding of datasets ignores the ``cp`` dim), each
+    keeps ``S / cp`` tokens of every sequence; losses weighted by the local token count then combine to the exact global
+    mean.  Identity when the context-parallel degree is 1.
+    """
+    rank, world = context_parallel_rank_and_size(dist_context)
+    if world == 1:
+        return batch
+
+    def cut(leaf: Any) -> Any:
+        if isinstance(leaf, torch.Tensor) and leaf.ndim > seq_dim:
+            return shard_sequence(leaf, seq_dim, world, rank, layout)
+        return leaf
+
+    return pytree.tree_map(cut, batch)

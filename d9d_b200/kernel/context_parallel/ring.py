@@ -1,0 +1,182 @@
+"""Ring attention with an exact backward pass.
+
+Every rank keeps its queries and, over ``world`` steps, sees every rank's K/V block once: while it computes attention of
+its queries against the block it holds it already exchanges blocks with its ring neighbours.  Per-block results
+``(out_b, lse_b)`` are merged on the fly (``lse = logaddexp(lse, lse_b)``, outputs re-weighted by ``exp(lse_b - lse)``),
+which is algebraically the softmax over the whole sequence.  The backward pass runs the same ring once more: with the
+saved global ``lse`` each block's probabilities are recomputed exactly, ``dQ`` accumulates locally and the ``dK / dV``
+accumulators travel with their K/V block until they are back at its owner.
+
+Masking is by *global token positions* (a ``[world, S_local]`` table of which tokens every rank holds), so any sharding
+layout works; block pairs that are entirely masked (frequent with the zig-zag layout) are skipped, entirely visible ones
+run unmasked.  The table lives on the host: which blocks to skip is decided without touching the device.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+
+_NEG_INF = float("-inf")
+
+
+def _exchange(tensors: list[torch.Tensor], group: dist.ProcessGroup) -> tuple[list[torch.Tensor], list[dist.Work]]:
+    """Start sending ``tensors`` to the next rank of the ring and receiving the previous rank's into fresh buffers."""
+    world, rank = group.size(), group.rank()
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    received = [torch.empty_like(t) for t in tensors]
+    ops = [dist.P2POp(dist.isend, t.contiguous(), group=group, group_peer=nxt) for t in tensors]
+    ops += [dist.P2POp(dist.irecv, r, group=group, group_peer=prv) for r in received]
+    return received, dist.batch_isend_irecv(ops)
+
+
+def _wait(works: list[dist.Work]) -> None:
+    for w in works:
+        w.wait()
+
+
+class _Masks:
+    """Visibility of (my queries, rank ``src``'s keys) derived from the host-side position table; device masks of the
+    partially visible pairs are built once and cached by the caller."""
+
+    def __init__(self, positions: torch.Tensor, rank: int, causal: bool, device: torch.device, cache: dict | None):
+        self._pos, self._rank, self._causal, self._device = positions, rank, causal, device
+        self._cache = cache if cache is not None else {}
+
+    def get(self, src: int) -> torch.Tensor | None | bool:
+        """``None``: everything visible, ``False``: nothing visible, tensor: boolean ``[Sq, Sk]`` mask."""
+        if not self._causal:
+            return None
+        pos_q, pos_k = self._pos[self._rank], self._pos[src]
+        if int(pos_k.min()) > int(pos_q.max()):
+            return False  # block lies entirely in the future
+        if int(pos_k.max()) <= int(pos_q.min()):
+            return None  # block lies entirely in the past
+        key = (self._rank, src, str(self._device))
+        mask = self._cache.get(key)
+        if mask is None:
+            mask = self._cache[key] = (pos_k[None, :] <= pos_q[:, None]).to(self._device)
+        return mask
+
+
+def _expand_heads(t: torch.Tensor, groups: int) -> torch.Tensor:
+    return t if groups == 1 else t.repeat_interleave(groups, dim=2)
+
+
+def _block_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, mask: torch.Tensor | None
+                   ) -> tuple[torch.Tensor, torch.Tensor]:
+    """``(out [B,Sq,H,Dv] fp32, lse [B,H,Sq] fp32)`` of attention against one K/V block."""
+    groups = q.shape[2] // k.shape[2]
+    scores = torch.einsum("bqhd,bkhd->bhqk", q.float(), _expand_heads(k, groups).float()) * scale
+    if mask is not None:
+        scores = scores.masked_fill(~mask, _NEG_INF)
+    lse = torch.logsumexp(scores, dim=-1)
+    probs = torch.exp(scores - lse.unsqueeze(-1).nan_to_num(neginf=0.0))  # rows without visible keys: exp(-inf) = 0
+    out = torch.einsum("bhqk,bkhd->bqhd", probs, _expand_heads(v, groups).float())
+    return out, lse
+
+
+def _merge(out: torch.Tensor | None, lse: torch.Tensor | None, out_b: torch.Tensor, lse_b: torch.Tensor
+           ) -> tuple[torch.Tensor, torch.Tensor]:
+    if out is None or lse is None:
+        return out_b, lse_b
+    new_lse = torch.logaddexp(lse, lse_b)
+    safe = new_lse.nan_to_num(neginf=0.0)  # both -inf -> weights exp(-inf - 0) = 0
+    w_old = torch.exp(lse - safe).transpose(1, 2).unsqueeze(-1)  # [B,Sq,H,1]
+    w_new = torch.exp(lse_b - safe).transpose(1, 2).unsqueeze(-1)
+    return out * w_old + out_b * w_new, new_lse
+
+
+def _block_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, grad_out: torch.Tensor, lse: torch.Tensor,
+                    delta: torch.Tensor, scale: float, mask: torch.Tensor | None
+                    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Gradients of one block given the *global* ``lse`` and ``delta = rowsum(dO * O)``: ``(dq, dk, dv)`` in fp32."""
+    groups = q.shape[2] // k.shape[2]
+    kf, vf = _expand_heads(k, groups).float(), _expand_heads(v, groups).float()
+    qf, gf = q.float(), grad_out.float()
+    scores = torch.einsum("bqhd,bkhd->bhqk", qf, kf) * scale
+    if mask is not None:
+        scores = scores.masked_fill(~mask, _NEG_INF)
+    probs = torch.exp(scores - lse.unsqueeze(-1).nan_to_num(neginf=0.0))
+    dv = torch.einsum("bhqk,bqhd->bkhd", probs, gf)
+    dprobs = torch.einsum("bqhd,bkhd->bhqk", gf, vf)
+    dscores = probs * (dprobs - delta.unsqueeze(-1)) * scale
+    dq = torch.einsum("bhqk,bkhd->bqhd", dscores, kf)
+    dk = torch.einsum("bhqk,bqhd->bkhd", dscores, qf)
+    if groups > 1:
+        b, sk, _, d = dk.shape
+        dk = dk.view(b, sk, k.shape[2], groups, d).sum(3)
+        dv = dv.view(b, sk, v.shape[2], groups, dv.shape[-1]).sum(3)
+    return dq, dk, dv
+
+
+class _RingAttention(Function):
+    @staticmethod
+    def forward(ctx: Any, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, masks: _Masks, group: dist.ProcessGroup,
+                scale: float) -> torch.Tensor:
+        world, rank = group.size(), group.rank()
+        out: torch.Tensor | None = None
+        lse: torch.Tensor | None = None
+        block = [k.detach(), v.detach()]
+        for step in range(world):
+            if step + 1 < world:
+                incoming, works = _exchange(block, group)  # overlaps with the attention below
+            mask = masks.get((rank - step) % world)
+            if mask is not False:
+                out_b, lse_b = _block_forward(q.detach(), block[0], block[1], scale, mask)
+                out, lse = _merge(out, lse, out_b, lse_b)
+            if step + 1 < world:
+                _wait(works)
+                block = incoming
+        if out is None or lse is None:  # cannot happen with a causal mask over real positions, but keep shapes right
+            out = q.new_zeros((*q.shape[:3], v.shape[-1]), dtype=torch.float32)
+            lse = q.new_full((q.shape[0], q.shape[2], q.shape[1]), _NEG_INF, dtype=torch.float32)
+        result = out.to(q.dtype)
+        ctx.save_for_backward(q, k, v, result, lse)
+        ctx.group, ctx.scale, ctx.masks = group, scale, masks
+        return result
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor):  # type: ignore[override]
+        q, k, v, out, lse = ctx.saved_tensors
+        group, world, rank = ctx.group, ctx.group.size(), ctx.group.rank()
+        delta = (grad_out.float() * out.float()).sum(-1).transpose(1, 2)  # [B,H,Sq]
+        dq = torch.zeros_like(q, dtype=torch.float32)
+        # the K/V block travels together with the gradient accumulated for it so far
+        block = [k, v, torch.zeros_like(k, dtype=torch.float32), torch.zeros_like(v, dtype=torch.float32)]
+        for step in range(world):
+            mask = ctx.masks.get((rank - step) % world)
+            if mask is not False:
+                dq_b, dk_b, dv_b = _block_backward(q, block[0], block[1], grad_out, lse, delta, ctx.scale, mask)
+                dq += dq_b
+                block[2] = block[2] + dk_b
+                block[3] = block[3] + dv_b
+            if world == 1:
+                break
+            # after the last step one more hop brings every block's gradient home
+            last = step + 1 == world
+            incoming, works = _exchange(block[2:] if last else block, group)
+            _wait(works)
+            block = [*block[:2], *incoming] if last else incoming
+        return dq.to(q.dtype), block[2].to(k.dtype), block[3].to(v.dtype), None, None, None
+
+
+def ring_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, group: dist.ProcessGroup, positions: torch.Tensor,
+                   softmax_scale: float | None = None, causal: bool = True, mask_cache: dict | None = None) -> torch.Tensor:
+    """Attention of the local queries over the keys / values of *all* ranks of ``group``.  Differentiable.
+
+    ``q [B, S_local, H, D]``, ``k / v [B, S_local, Hk, D(v)]`` (``H % Hk == 0``).  ``positions``: host int64
+    ``[world, S_local]`` - row ``r`` holds the global positions of rank ``r``'s tokens
+    (``torch.stack([local_sequence_indices(S, world, r, layout) for r in range(world)])``).  ``mask_cache``: optional dict
+    reused across calls so that device masks are built once.
+    """
+    if q.shape[2] % k.shape[2] != 0:
+        raise ValueError("the number of query heads must be a multiple of the number of key/value heads")
+    if positions.shape != (group.size(), q.shape[1]):
+        raise ValueError(f"positions must be [world, S_local] = {(group.size(), q.shape[1])}, got {tuple(positions.shape)}")
+    scale = softmax_scale if softmax_scale is not None else q.shape[-1] ** -0.5
+    masks = _Masks(positions.cpu(), group.rank(), bool(causal), q.device, mask_cache)
+    return _RingAttention.apply(q, k, v, masks, group, float(scale))

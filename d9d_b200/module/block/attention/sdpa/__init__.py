@@ -1,3 +1,3 @@
-from .flash import FlashSdpa
+from .flash import ContextParallelMode, FlashSdpa
 
-__all__ = ["FlashSdpa"]
+__all__ = ["ContextParallelMode", "FlashSdpa"]

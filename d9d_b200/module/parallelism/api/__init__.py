@@ -1,5 +1,6 @@
 """High-level helpers applying a parallelism strategy to a module (reference ``d9d/module/parallelism/api``)."""
 
+from .context_parallel import parallelize_context_parallel
 from .expert_parallel import parallelize_expert_parallel
 from .fully_sharded import parallelize_fsdp
 from .hybrid_sharded import parallelize_hsdp
@@ -8,6 +9,7 @@ from .tensor_parallel import parallelize_colwise, parallelize_rowwise
 
 __all__ = [
     "parallelize_colwise",
+    "parallelize_context_parallel",
     "parallelize_expert_parallel",
     "parallelize_fsdp",
     "parallelize_hsdp",

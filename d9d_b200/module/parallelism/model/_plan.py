@@ -1,4 +1,5 @@
-"""Shared plan: HSDP for dense sub-modules on the dense mesh, EP for MoE layers on the expert mesh.
+"""Shared plan: HSDP for dense sub-modules on the dense mesh, EP for MoE layers on the expert mesh, context-parallel
+attention over the ``cp`` ranks of the batch mesh.
 
 Parity: reference ``d9d/module/parallelism/model/qwen3_moe.py:12-146`` / ``qwen3_dense.py:12-145`` — every
 sub-module (embeddings, final norm, per layer: attention, both norms, dense MLP, heads) is its own unit.
@@ -8,10 +9,10 @@ from __future__ import annotations
 
 from torch import nn
 
-from d9d_b200.core.dist_context import DENSE_DOMAIN, EXPERT_DOMAIN, DistributedContext
+from d9d_b200.core.dist_context import BATCH_DOMAIN, DENSE_DOMAIN, EXPERT_DOMAIN, DistributedContext
 from d9d_b200.module.block.moe import MoELayer
 from d9d_b200.module.model.decoder import DecoderBackbone
-from d9d_b200.module.parallelism.api import parallelize_expert_parallel, parallelize_hsdp
+from d9d_b200.module.parallelism.api import parallelize_context_parallel, parallelize_expert_parallel, parallelize_hsdp
 from d9d_b200.pipelining.api import PipelineStageInfo
 
 _DENSE_DIMS = ("dp_replicate", "dp_cp_shard", "cp_replicate")
@@ -21,8 +22,6 @@ def _check_supported(dist_context: DistributedContext) -> None:
     dims = dist_context.mesh_params
     if dims.has_tensor_parallel:
         raise ValueError("Tensor Parallel currently is not supported for this model.")
-    if dims.has_context_parallel_replicate or dims.has_context_parallel_shard:
-        raise ValueError("Context Parallel currently is not supported for this model.")
 
 
 def dense_unit(dist_context: DistributedContext, module: nn.Module) -> None:
@@ -32,6 +31,8 @@ def dense_unit(dist_context: DistributedContext, module: nn.Module) -> None:
 def parallelize_backbone(dist_context: DistributedContext, model: DecoderBackbone, stage: PipelineStageInfo) -> None:
     _check_supported(dist_context)
     expert_mesh = dist_context.mesh_for(EXPERT_DOMAIN)["ep_replicate", "ep_shard"]
+    # cp_shard and cp_replicate both split the sequence (they differ in how the weights are held): attention spans both
+    cp_mesh = dist_context.mesh_for(BATCH_DOMAIN)["cp"]
     if stage.is_current_stage_first:
         dense_unit(dist_context, model.embed_tokens)
     if stage.is_current_stage_last:
@@ -41,6 +42,8 @@ def parallelize_backbone(dist_context: DistributedContext, model: DecoderBackbon
             parallelize_expert_parallel(layer.mlp, mesh_experts=expert_mesh)
         else:
             dense_unit(dist_context, layer.mlp)
+        if cp_mesh.size() > 1:
+            parallelize_context_parallel(layer.self_attn, cp_mesh)
         dense_unit(dist_context, layer.self_attn)
         dense_unit(dist_context, layer.input_layernorm)
         dense_unit(dist_context, layer.post_attention_layernorm)

@@ -11,7 +11,7 @@ from d9d_b200.core.dist_context import REGULAR_DOMAIN, DistributedContext
 from d9d_b200.core.sharding import ShardingSpec, shard_spec_on_dim, shard_tree
 from d9d_b200.pipelining.api import PipelineLossFn, PipelineResultFn, PipelineSchedule, PipelineShardingSpec
 
-from .action import Action, ActionKind, AnyAction, Program, flatten
+from .action import Action, ActionKind, Program, flatten
 from .stage import PipelineStage
 
 

@@ -9,8 +9,9 @@ from __future__ import annotations
 import torch
 from pydantic import BaseModel
 
+from d9d_b200.core.dist_context import DistributedContext
 from d9d_b200.core.types import ScalarTree
-from d9d_b200.dataset import SyntheticTokenDataset, shard_dataset_data_parallel
+from d9d_b200.dataset import SyntheticTokenDataset, shard_batch_for_context_parallel, shard_dataset_data_parallel
 from d9d_b200.loop.control import (
     BuildForwardInputsContext,
     BuildForwardInputsResult,
@@ -89,13 +90,18 @@ class Qwen3MoEModelProvider(ModelProvider):
 
 class CausalLMTask(TrainTask):
     """Token-mean next-token loss; the loss weight is the number of target tokens (so gradient accumulation and
-    data parallelism produce the exact global token mean)."""
+    data parallelism produce the exact global token mean).  Given the distributed context, batches are cut along the
+    sequence for context-parallel meshes (every ``cp`` rank keeps ``S / cp`` tokens of each sample)."""
+
+    def __init__(self, dist_context: DistributedContext | None = None) -> None:
+        self._ctx = dist_context
 
     def build_forward_inputs(self, ctx: BuildForwardInputsContext) -> BuildForwardInputsResult:
-        ctx.state["labels"] = ctx.batch["labels"]
+        batch = ctx.batch if self._ctx is None else shard_batch_for_context_parallel(ctx.batch, self._ctx)
+        ctx.state["labels"] = batch["labels"]
         return BuildForwardInputsResult(
-            inputs={"input_ids": ctx.batch["input_ids"]},
-            kwargs={"labels": ctx.batch["labels"], "position_ids": ctx.batch["position_ids"]},
+            inputs={"input_ids": batch["input_ids"]},
+            kwargs={"labels": batch["labels"], "position_ids": batch["position_ids"]},
         )
 
     def create_metrics(self, ctx: CreateMetricsContext) -> CreateMetricsResult:
@@ -107,7 +113,8 @@ class CausalLMTask(TrainTask):
     def compute_loss(self, ctx: ComputeLossContext) -> ComputeLossResult:
         num_tokens = (ctx.state["labels"] != LM_IGNORE_INDEX).sum()
         ctx.state["num_tokens"] = num_tokens
-        return ComputeLossResult(loss=ctx.pipeline_results["logps"].sum() / num_tokens, loss_weight=num_tokens / 1000)
+        # a context-parallel rank may hold no target token of a microbatch: its loss is 0 with weight 0
+        return ComputeLossResult(loss=ctx.pipeline_results["logps"].sum() / num_tokens.clamp_min(1), loss_weight=num_tokens / 1000)
 
 
 class CausalLMPerplexityTask(InferenceTask):

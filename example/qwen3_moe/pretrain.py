@@ -120,7 +120,7 @@ def main() -> None:
     trainer = TrainingConfigurator(
         mesh=mesh,
         parameters=config.trainer,
-        task_provider=lambda ctx: CausalLMTask(),
+        task_provider=lambda ctx: CausalLMTask(ctx.dist_context),  # context-parallel meshes shard the sequence in the task
         model_provider=Qwen3MoEModelProvider(config.model_provider),
         data_provider=data_provider,
         optimizer_provider=AutoOptimizerProvider(config.optimizer),

@@ -88,10 +88,16 @@ class LMProvider(ModelProvider):
 
 
 class SFTTask(TrainTask):
+    def __init__(self, dist_context=None):
+        self._ctx = dist_context
+
     def build_forward_inputs(self, ctx: BuildForwardInputsContext) -> BuildForwardInputsResult:
-        ctx.state["labels"] = ctx.batch["labels"]
-        return BuildForwardInputsResult(inputs={"input_ids": ctx.batch["input_ids"]},
-                                        kwargs={"labels": ctx.batch["labels"], "position_ids": ctx.batch["position_ids"]})
+        from d9d_b200.dataset import shard_batch_for_context_parallel
+
+        batch = ctx.batch if self._ctx is None else shard_batch_for_context_parallel(ctx.batch, self._ctx)
+        ctx.state["labels"] = batch["labels"]
+        return BuildForwardInputsResult(inputs={"input_ids": batch["input_ids"]},
+                                        kwargs={"labels": batch["labels"], "position_ids": batch["position_ids"]})
 
     def create_metrics(self, ctx: CreateMetricsContext) -> CreateMetricsResult:
         return CreateMetricsResult(metrics={"num_tokens": SumMetric()})
@@ -102,10 +108,10 @@ class SFTTask(TrainTask):
     def compute_loss(self, ctx: ComputeLossContext) -> ComputeLossResult:
         n = (ctx.state["labels"] != LM_IGNORE_INDEX).sum()
         ctx.state["num_tokens"] = n
-        return ComputeLossResult(loss=ctx.pipeline_results["logps"].sum() / n, loss_weight=n / 1000)
+        return ComputeLossResult(loss=ctx.pipeline_results["logps"].sum() / n.clamp_min(1), loss_weight=n / 1000)
 
 
-def trainer_config(tmp, total_batch=8, micro=4, schedule=None, ckpt_period="disable", log_dir=None):
+def trainer_config(tmp, total_batch=8, micro=4, schedule=None, ckpt_period="disable", log_dir=None, source=None):
     from d9d_b200.loop.config import TrainerConfig
 
     return TrainerConfig.model_validate({
@@ -114,7 +120,7 @@ def trainer_config(tmp, total_batch=8, micro=4, schedule=None, ckpt_period="disa
         "data_loading": {"num_workers": 0, "pin_memory": False, "persistent_workers": False},
         "logging": {"period_steps": 2, "tracker": {"provider": "jsonl", "directory": str(log_dir)} if log_dir else {"provider": "null"}},
         "pipelining": {"schedule": schedule or {"schedule": "gpipe"}},
-        "model_stage_factory": {"source_checkpoint": None, "checkpoint_only_trainable_parameters": False},
+        "model_stage_factory": {"source_checkpoint": str(source) if source else None, "checkpoint_only_trainable_parameters": False},
         "determinism": {"base_seed": 11},
         "gc": {"period_steps": 4},
         "checkpointing": {"save_dir": str(tmp / "ckpt"), "period_steps": ckpt_period, "num_to_keep": 2},

@@ -18,6 +18,11 @@ MESHES = {
     "dpr2_dps2": dict(data_parallel_replicate=2, data_parallel_shard=2),
     "dpr4_ep2": dict(data_parallel_replicate=4, expert_parallel=2),
     "dpr2_dps2_ep4": dict(data_parallel_replicate=2, data_parallel_shard=2, expert_parallel=4),
+    # context parallelism: ranks of one cp group read the same samples and keep S / cp tokens of every sequence
+    "cps4": dict(context_parallel_shard=4),
+    "cpr2_cps2": dict(context_parallel_replicate=2, context_parallel_shard=2),
+    "dpr2_cps2": dict(data_parallel_replicate=2, context_parallel_shard=2),
+    "dps2_cps2_ep2": dict(data_parallel_shard=2, context_parallel_shard=2, expert_parallel=2),
 }
 
 
@@ -67,13 +72,17 @@ def _worker(rank, world_size, mesh_name, moe):
     params = list(model.parameters())
     sync = GradientSynchronizer([params], bucket_size_mb=1, require_accumulations=1)
     sync.bind()
-    dp_rank = ctx.mesh_for(BATCH_DOMAIN)["dp"].get_local_rank()
-    ids, labels, pos = _batch(dp_rank)
+    from d9d_b200.dataset import shard_batch_for_context_parallel
+
+    batch_mesh = ctx.mesh_for(BATCH_DOMAIN)
+    dp_rank = batch_mesh["dp"].get_local_rank()
+    ids, labels, pos = shard_batch_for_context_parallel(_batch(dp_rank), ctx)  # identity without context parallelism
+    assert ids.shape[1] == 16 // batch_mesh["cp"].size()
     model(input_ids=ids, position_ids=pos, labels=labels)["logps"].sum().backward()
     sync.wait()
 
     ref = _build(moe)
-    for b in range(world_size):  # every rank is its own data-parallel replica on these meshes
+    for b in range(batch_mesh["dp"].size()):  # one batch per data-parallel replica
         ids, labels, pos = _batch(b)
         ref(input_ids=ids, position_ids=pos, labels=labels)["logps"].sum().backward()
 
@@ -84,11 +93,11 @@ def _worker(rank, world_size, mesh_name, moe):
     dist.barrier()
 
 
-@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr2_dps2"])
+@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr2_dps2", "cps4", "cpr2_cps2", "dpr2_cps2"])
 def test_dense_model_matches_single_process(mesh_name):
     run_distributed(_worker, 4, mesh_name, False)
 
 
-@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr4_ep2", "dpr2_dps2_ep4"])
+@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr4_ep2", "dpr2_dps2_ep4", "dps2_cps2_ep2"])
 def test_moe_model_matches_single_process(mesh_name):
     run_distributed(_worker, 4, mesh_name, True)

@@ -10,7 +10,7 @@ from tests.helpers_train import LMProvider, SFTTask, SyntheticDataProvider, dens
 
 
 def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable", total_batch=8, micro=4, log=True, samples=64,
-                  optimizer=None, fold_scaling=True, dtype=torch.float32):
+                  optimizer=None, fold_scaling=True, dtype=torch.float32, source=None):
     from d9d_b200.core.dist_context import DeviceMeshParameters
     from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
     from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
@@ -23,10 +23,11 @@ def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable
     return TrainingConfigurator(
         mesh=mesh or DeviceMeshParameters(),
         parameters=trainer_config(tmp, total_batch=total_batch, micro=micro, schedule=schedule, ckpt_period=ckpt_period,
-                                  log_dir=(tmp / "logs") if log else None).model_copy(update={}, deep=True)
+                                  log_dir=(tmp / "logs") if log else None, source=source).model_copy(update={}, deep=True)
         if fold_scaling else _without_folding(trainer_config(tmp, total_batch=total_batch, micro=micro, schedule=schedule,
-                                                             ckpt_period=ckpt_period, log_dir=(tmp / "logs") if log else None)),
-        task_provider=lambda ctx: SFTTask(),
+                                                             ckpt_period=ckpt_period, log_dir=(tmp / "logs") if log else None,
+                                                             source=source)),
+        task_provider=lambda ctx: SFTTask(ctx.dist_context),
         model_provider=LMProvider(moe_params() if moe else dense_params(), moe=moe, dtype=dtype),
         data_provider=SyntheticDataProvider(num_samples=samples),
         optimizer_provider=AutoOptimizerProvider(optimizer or AdamWOptimizerConfig(lr=3e-3, weight_decay=0.0)),
@@ -100,14 +101,14 @@ def test_resume_is_exact(tmp_path):
         torch.testing.assert_close(v, ref_state[k], rtol=0, atol=0)
 
 
-def _dist_worker(rank, world, tmp, mesh_kwargs, schedule, moe):
+def _dist_worker(rank, world, tmp, mesh_kwargs, schedule, moe, source=None):
     from pathlib import Path
 
     from d9d_b200.core.dist_context import DeviceMeshParameters
 
     tmp = Path(tmp)
     trainer = _make_trainer(tmp, mesh=DeviceMeshParameters(**mesh_kwargs), moe=moe, schedule=schedule, total_batch=8, micro=2,
-                            log=True, samples=32)
+                            log=True, samples=32, source=source)
     trainer.train()
     trainer.export(tmp / "export", load_checkpoint=False)
     if rank == 0:
@@ -138,6 +139,24 @@ def test_dp_matches_single_process(tmp_path):
     # samples are distributed differently (round-robin sharding) so per-step batches differ; the totals must be close
     # and the first step (same init, different but same-sized batch) must be within noise
     assert abs(ref[0] - got[0]) < 0.2
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("mesh_kwargs,world", [({"context_parallel_shard": 2}, 2),
+                                               ({"context_parallel_replicate": 2, "pipeline_parallel": 2}, 4)])
+def test_context_parallel_training_reproduces_the_single_process_run(tmp_path, mesh_kwargs, world):
+    """Ranks of a context-parallel group read the same samples and split every sequence: the loss trajectory must equal
+    the single-process one (same batches, same maths - only the reduction order differs)."""
+    _make_trainer(tmp_path / "init", log=False).export(tmp_path / "weights", load_checkpoint=False)  # shared initial weights
+    single = _make_trainer(tmp_path / "s", total_batch=8, micro=2, samples=32, source=tmp_path / "weights")
+    single.train()
+    ref, _ = _read_losses(tmp_path / "s")
+    schedule = {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": False} if "pipeline_parallel" in mesh_kwargs else {"schedule": "gpipe"}
+    run_distributed(_dist_worker, world, str(tmp_path / "cp"), mesh_kwargs, schedule, False, str(tmp_path / "weights"))
+    got, _ = _read_losses(tmp_path / "cp")
+    assert sorted(ref) == sorted(got)
+    for step in ref:
+        assert abs(ref[step] - got[step]) < 2e-3 * max(1.0, abs(ref[step])), (step, ref[step], got[step])
 
 
 def test_folding_the_gradient_scale_into_the_optimizer_changes_nothing(tmp_path):
