@@ -31,6 +31,10 @@ def shard_batch_for_context_parallel(batch: T, dist_context: DistributedContext,
     mean.  Identity when the context-parallel degree is 1.
     """
     rank, world = context_parallel_rank_and_size(dist_context)
+    return _cut(batch, seq_dim, world, rank, layout)
+
+
+def _cut(batch: T, seq_dim: int, world: int, rank: int, layout: ContextParallelLayout) -> T:
     if world == 1:
         return batch
 
@@ -40,3 +44,21 @@ def shard_batch_for_context_parallel(batch: T, dist_context: DistributedContext,
         return leaf
 
     return pytree.tree_map(cut, batch)
+
+
+def shard_batch_for_sequence_parallel(batch: T, dist_context: DistributedContext, seq_dim: int = 1) -> T:
+    """Keep this *tensor-parallel* rank's contiguous chunk of every sequence: the family plans run tensor parallelism
+    with sequence parallelism, i.e. activations between attention / MLP blocks carry ``S / tp`` tokens (the blocks gather
+    and scatter them in their GEMMs).  Identity when the tensor-parallel degree is 1."""
+    if not dist_context.mesh_params.is_distributed:
+        return batch
+    tp = dist_context.mesh_for(BATCH_DOMAIN)["tp"]
+    return _cut(batch, seq_dim, tp.size(), tp.get_local_rank(), ContextParallelLayout.contiguous)
+
+
+def shard_batch_along_sequence(batch: T, dist_context: DistributedContext, seq_dim: int = 1,
+                               layout: ContextParallelLayout = ContextParallelLayout.zigzag) -> T:
+    """Context-parallel cut (``layout``) followed by the tensor/sequence-parallel cut: what a task should apply to the
+    collated batch so that any mesh works.  Identity for meshes without ``cp`` / ``tp``."""
+    return shard_batch_for_sequence_parallel(shard_batch_for_context_parallel(batch, dist_context, seq_dim, layout),
+                                             dist_context, seq_dim)

@@ -54,12 +54,18 @@ class GroupedQueryAttention(nn.Module, ModuleLateInit):
         self.rope = RotaryEmbeddingApplicator(style=rope_style)
         self.kernel = FlashSdpa()
 
+    @property
+    def head_dim(self) -> int:
+        return self._head_dim
+
     def forward(self, hidden_states: torch.Tensor, attention_mask: torch.Tensor | None,
                 position_embeddings: tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
-        lead = hidden_states.shape[:-1]
+        # shapes are taken from the projections: under tensor + sequence parallelism they return the tokens of the whole
+        # tensor-parallel group for this rank's heads, while ``hidden_states`` holds only the local tokens
+        q = self.q_proj(hidden_states)
+        lead = q.shape[:-1]
         per_head = (*lead, -1, self._head_dim)
-
-        q = self.q_proj(hidden_states).view(per_head)
+        q = q.view(per_head)
         k = self.k_proj(hidden_states).view(per_head)
         v = self.v_proj(hidden_states).view(per_head)
         cos, sin = position_embeddings

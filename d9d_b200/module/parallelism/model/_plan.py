@@ -1,5 +1,5 @@
 """Shared plan: HSDP for dense sub-modules on the dense mesh, EP for MoE layers on the expert mesh, context-parallel
-attention over the ``cp`` ranks of the batch mesh.
+attention over the ``cp`` ranks of the batch mesh, tensor + sequence parallel attention / dense MLPs over ``tp``.
 
 Parity: reference ``d9d/module/parallelism/model/qwen3_moe.py:12-146`` / ``qwen3_dense.py:12-145`` — every
 sub-module (embeddings, final norm, per layer: attention, both norms, dense MLP, heads) is its own unit.
@@ -10,22 +10,52 @@ from __future__ import annotations
 from torch import nn
 
 from d9d_b200.core.dist_context import BATCH_DOMAIN, DENSE_DOMAIN, EXPERT_DOMAIN, DistributedContext
+from d9d_b200.module.block.attention import GroupedQueryAttention
+from d9d_b200.module.block.ffn import SwiGLU
 from d9d_b200.module.block.moe import MoELayer
 from d9d_b200.module.model.decoder import DecoderBackbone
-from d9d_b200.module.parallelism.api import parallelize_context_parallel, parallelize_expert_parallel, parallelize_hsdp
+from d9d_b200.module.parallelism.api import (
+    parallelize_attention_tensor_parallel,
+    parallelize_context_parallel,
+    parallelize_expert_parallel,
+    parallelize_hsdp,
+    parallelize_replicate,
+    parallelize_swiglu_tensor_parallel,
+)
 from d9d_b200.pipelining.api import PipelineStageInfo
 
 _DENSE_DIMS = ("dp_replicate", "dp_cp_shard", "cp_replicate")
+_TP_DIMS = ("dp_replicate", "cp_replicate", "tp")
 
 
 def _check_supported(dist_context: DistributedContext) -> None:
     dims = dist_context.mesh_params
-    if dims.has_tensor_parallel:
-        raise ValueError("Tensor Parallel currently is not supported for this model.")
+    if dims.has_tensor_parallel and (dims.has_data_parallel_shard or dims.has_context_parallel_shard):
+        raise ValueError("Tensor parallelism cannot be combined with FSDP sharding (data_parallel_shard / "
+                         "context_parallel_shard) yet: use the *_replicate degrees.")
 
 
 def dense_unit(dist_context: DistributedContext, module: nn.Module) -> None:
-    parallelize_hsdp(module, mesh=dist_context.mesh_for(DENSE_DOMAIN)[_DENSE_DIMS])
+    """HSDP over the data / context dims; with tensor parallelism the unit is additionally replicated over ``tp`` (its
+    activations are sequence-sharded there, so its gradients are partial sums that must be reduced over ``tp`` too)."""
+    dense = dist_context.mesh_for(DENSE_DOMAIN)
+    if dist_context.mesh_params.has_tensor_parallel:
+        dims = tuple(d for d in _TP_DIMS if dense[d].size() > 1)
+        parallelize_replicate(module, dense[dims], skip_distributed=True)
+    else:
+        parallelize_hsdp(module, mesh=dense[_DENSE_DIMS])
+
+
+def _tensor_parallel_layer(dist_context: DistributedContext, layer: nn.Module) -> None:
+    """Megatron-style tensor + sequence parallelism of one decoder layer: hidden states between blocks carry ``S / tp``
+    tokens; attention and the dense MLP gather them in their column-parallel input GEMMs and scatter them again in their
+    row-parallel output GEMMs (fused into the GEMMs on CUDA)."""
+    mesh = dist_context.mesh_for(DENSE_DOMAIN)[_TP_DIMS]
+    if not isinstance(layer.self_attn, GroupedQueryAttention):
+        raise ValueError(f"tensor parallelism is implemented for GroupedQueryAttention, got {type(layer.self_attn).__name__}")
+    parallelize_attention_tensor_parallel(layer.self_attn, mesh)
+    if isinstance(layer.mlp, SwiGLU):
+        parallelize_swiglu_tensor_parallel(layer.mlp, mesh)
 
 
 def parallelize_backbone(dist_context: DistributedContext, model: DecoderBackbone, stage: PipelineStageInfo) -> None:
@@ -33,18 +63,21 @@ def parallelize_backbone(dist_context: DistributedContext, model: DecoderBackbon
     expert_mesh = dist_context.mesh_for(EXPERT_DOMAIN)["ep_replicate", "ep_shard"]
     # cp_shard and cp_replicate both split the sequence (they differ in how the weights are held): attention spans both
     cp_mesh = dist_context.mesh_for(BATCH_DOMAIN)["cp"]
+    tensor_parallel = dist_context.mesh_params.has_tensor_parallel
     if stage.is_current_stage_first:
         dense_unit(dist_context, model.embed_tokens)
     if stage.is_current_stage_last:
         dense_unit(dist_context, model.norm)
     for layer in model.layers.values():
+        if tensor_parallel:
+            _tensor_parallel_layer(dist_context, layer)
         if isinstance(layer.mlp, MoELayer):
             parallelize_expert_parallel(layer.mlp, mesh_experts=expert_mesh)
-        else:
+        elif not tensor_parallel:
             dense_unit(dist_context, layer.mlp)
         if cp_mesh.size() > 1:
             parallelize_context_parallel(layer.self_attn, cp_mesh)
-        dense_unit(dist_context, layer.self_attn)
+        dense_unit(dist_context, layer.self_attn)  # with tensor parallelism: what the TP styles left (q/k norms)
         dense_unit(dist_context, layer.input_layernorm)
         dense_unit(dist_context, layer.post_attention_layernorm)
 

@@ -56,9 +56,11 @@ class ToLocalParallel(ParallelStyle):
     on each forward; here only the parameter dict entries are swapped).
     """
 
-    def __init__(self, param_placement: tuple[Placement, ...], grad_placement: tuple[Placement, ...]):
+    def __init__(self, param_placement: tuple[Placement, ...], grad_placement: tuple[Placement, ...],
+                 skip_distributed: bool = False):
         self._param_placement = tuple(param_placement)
         self._grad_placement = tuple(grad_placement)
+        self._skip_distributed = skip_distributed  # leave parameters another style (e.g. tensor parallel) already owns
 
     def _apply(self, module: nn.Module, device_mesh: DeviceMesh) -> nn.Module:
         slots: list[tuple[nn.Module, str]] = []
@@ -67,6 +69,8 @@ class ToLocalParallel(ParallelStyle):
                 if param is None:
                     continue
                 if isinstance(param.data, DTensor):
+                    if self._skip_distributed:
+                        continue
                     raise ValueError(f"parameter {name} of {type(sub).__name__} is already distributed")
                 dist_param = nn.Parameter(
                     distribute_tensor(param.data, device_mesh, self._param_placement, src_data_rank=None),

@@ -11,7 +11,7 @@ from pydantic import BaseModel
 
 from d9d_b200.core.dist_context import DistributedContext
 from d9d_b200.core.types import ScalarTree
-from d9d_b200.dataset import SyntheticTokenDataset, shard_batch_for_context_parallel, shard_dataset_data_parallel
+from d9d_b200.dataset import SyntheticTokenDataset, shard_batch_along_sequence, shard_dataset_data_parallel
 from d9d_b200.loop.control import (
     BuildForwardInputsContext,
     BuildForwardInputsResult,
@@ -97,7 +97,7 @@ class CausalLMTask(TrainTask):
         self._ctx = dist_context
 
     def build_forward_inputs(self, ctx: BuildForwardInputsContext) -> BuildForwardInputsResult:
-        batch = ctx.batch if self._ctx is None else shard_batch_for_context_parallel(ctx.batch, self._ctx)
+        batch = ctx.batch if self._ctx is None else shard_batch_along_sequence(ctx.batch, self._ctx)
         ctx.state["labels"] = batch["labels"]
         return BuildForwardInputsResult(
             inputs={"input_ids": batch["input_ids"]},

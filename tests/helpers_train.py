@@ -92,9 +92,9 @@ class SFTTask(TrainTask):
         self._ctx = dist_context
 
     def build_forward_inputs(self, ctx: BuildForwardInputsContext) -> BuildForwardInputsResult:
-        from d9d_b200.dataset import shard_batch_for_context_parallel
+        from d9d_b200.dataset import shard_batch_along_sequence
 
-        batch = ctx.batch if self._ctx is None else shard_batch_for_context_parallel(ctx.batch, self._ctx)
+        batch = ctx.batch if self._ctx is None else shard_batch_along_sequence(ctx.batch, self._ctx)
         ctx.state["labels"] = batch["labels"]
         return BuildForwardInputsResult(inputs={"input_ids": batch["input_ids"]},
                                         kwargs={"labels": batch["labels"], "position_ids": batch["position_ids"]})

@@ -23,7 +23,13 @@ MESHES = {
     "cpr2_cps2": dict(context_parallel_replicate=2, context_parallel_shard=2),
     "dpr2_cps2": dict(data_parallel_replicate=2, context_parallel_shard=2),
     "dps2_cps2_ep2": dict(data_parallel_shard=2, context_parallel_shard=2, expert_parallel=2),
+    # tensor parallelism (with sequence parallelism): heads and MLP columns split over tp, S / tp tokens between blocks
+    "tp2": dict(tensor_parallel=2),
+    "dpr2_tp2": dict(data_parallel_replicate=2, tensor_parallel=2),
+    "cpr2_tp2": dict(context_parallel_replicate=2, tensor_parallel=2),
+    "dpr2_tp2_ep2": dict(data_parallel_replicate=2, tensor_parallel=2, expert_parallel=2),
 }
+WORLD = {"tp2": 2}
 
 
 def _build(moe: bool):
@@ -72,12 +78,12 @@ def _worker(rank, world_size, mesh_name, moe):
     params = list(model.parameters())
     sync = GradientSynchronizer([params], bucket_size_mb=1, require_accumulations=1)
     sync.bind()
-    from d9d_b200.dataset import shard_batch_for_context_parallel
+    from d9d_b200.dataset import shard_batch_along_sequence
 
     batch_mesh = ctx.mesh_for(BATCH_DOMAIN)
     dp_rank = batch_mesh["dp"].get_local_rank()
-    ids, labels, pos = shard_batch_for_context_parallel(_batch(dp_rank), ctx)  # identity without context parallelism
-    assert ids.shape[1] == 16 // batch_mesh["cp"].size()
+    ids, labels, pos = shard_batch_along_sequence(_batch(dp_rank), ctx)  # identity without context / tensor parallelism
+    assert ids.shape[1] == 16 // (batch_mesh["cp"].size() * batch_mesh["tp"].size())
     model(input_ids=ids, position_ids=pos, labels=labels)["logps"].sum().backward()
     sync.wait()
 
@@ -93,11 +99,11 @@ def _worker(rank, world_size, mesh_name, moe):
     dist.barrier()
 
 
-@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr2_dps2", "cps4", "cpr2_cps2", "dpr2_cps2"])
+@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr2_dps2", "cps4", "cpr2_cps2", "dpr2_cps2", "tp2", "dpr2_tp2", "cpr2_tp2"])
 def test_dense_model_matches_single_process(mesh_name):
-    run_distributed(_worker, 4, mesh_name, False)
+    run_distributed(_worker, WORLD.get(mesh_name, 4), mesh_name, False)
 
 
-@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr4_ep2", "dpr2_dps2_ep4", "dps2_cps2_ep2"])
+@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr4_ep2", "dpr2_dps2_ep4", "dps2_cps2_ep2", "dpr2_tp2_ep2"])
 def test_moe_model_matches_single_process(mesh_name):
     run_distributed(_worker, 4, mesh_name, True)

@@ -143,10 +143,13 @@ def test_dp_matches_single_process(tmp_path):
 
 @pytest.mark.dist
 @pytest.mark.parametrize("mesh_kwargs,world", [({"context_parallel_shard": 2}, 2),
-                                               ({"context_parallel_replicate": 2, "pipeline_parallel": 2}, 4)])
-def test_context_parallel_training_reproduces_the_single_process_run(tmp_path, mesh_kwargs, world):
-    """Ranks of a context-parallel group read the same samples and split every sequence: the loss trajectory must equal
-    the single-process one (same batches, same maths - only the reduction order differs)."""
+                                               ({"context_parallel_replicate": 2, "pipeline_parallel": 2}, 4),
+                                               ({"tensor_parallel": 2}, 2),
+                                               ({"tensor_parallel": 2, "context_parallel_replicate": 2}, 4)])
+def test_sequence_sharded_training_reproduces_the_single_process_run(tmp_path, mesh_kwargs, world):
+    """Ranks of a context- / tensor-parallel group read the same samples and split every sequence (and, for tensor
+    parallelism, the heads and MLP columns): the loss trajectory must equal the single-process one (same batches, same
+    maths - only the reduction order differs)."""
     _make_trainer(tmp_path / "init", log=False).export(tmp_path / "weights", load_checkpoint=False)  # shared initial weights
     single = _make_trainer(tmp_path / "s", total_batch=8, micro=2, samples=32, source=tmp_path / "weights")
     single.train()
