@@ -2,9 +2,11 @@ from __future__ import annotations
 
 import re
 import shutil
+from concurrent.futures import Future
 from pathlib import Path
 
 import torch
+import torch.distributed as dist
 import torch.distributed.checkpoint as dcp
 from torch.distributed.checkpoint.stateful import Stateful
 
@@ -15,19 +17,25 @@ from .garbage_collector import ManualGarbageCollector
 from .stepper import Stepper
 
 _SAVE_RE = re.compile(r"^save-(\d+)$")
+_COMPLETE_MARKER = ".metadata"  # written by DCP after every rank's data files
 
 
 class StateCheckpointer:
     """Job checkpoints with ``torch.distributed.checkpoint``: ``{save_dir}[/{run_name}]/save-{step}`` holding
     ``{"state": JobState}``; keep-last-N rotation on the main process; barriers around IO.
 
-    Parity: reference ``d9d/loop/component/checkpointer.py:27-166`` (same on-disk layout).
+    Parity: reference ``d9d/loop/component/checkpointer.py:27-166`` (same on-disk layout).  Beyond the reference:
+    optional asynchronous saves (``async_save``: DCP stages the state on the host and writes it from a background thread -
+    the reference lists this as a TODO), and a directory only counts as a checkpoint once DCP's ``.metadata`` file - which
+    is written last - exists, so a job killed in the middle of a save resumes from the previous complete checkpoint.
     """
 
     def __init__(self, dist_context: DistributedContext, stepper: Stepper, config: CheckpointingConfig, gc: ManualGarbageCollector,
                  run_name: str | None):
         self._ctx, self._stepper, self._config, self._gc = dist_context, stepper, config, gc
         self._save_dir = config.save_dir / run_name if run_name else config.save_dir
+        self._in_flight: tuple[Future, Path] | None = None
+        self._host_group: dist.ProcessGroup | None = None
 
     def _free_memory(self) -> None:
         self._gc.collect_forced()
@@ -37,7 +45,8 @@ class StateCheckpointer:
     def _sorted_checkpoints(self) -> list[Path]:
         if not self._save_dir or not self._save_dir.is_dir():
             return []
-        found = [(int(m.group(1)), p) for p in self._save_dir.iterdir() if p.is_dir() and (m := _SAVE_RE.fullmatch(p.name))]
+        found = [(int(m.group(1)), p) for p in self._save_dir.iterdir()
+                 if p.is_dir() and (m := _SAVE_RE.fullmatch(p.name)) and (p / _COMPLETE_MARKER).exists()]
         return [p for _, p in sorted(found)]
 
     def _purge(self) -> None:
@@ -50,11 +59,36 @@ class StateCheckpointer:
     def _no_dist_kwargs(self) -> dict:
         return {} if self._ctx.mesh_params.is_distributed else {"no_dist": True}
 
+    def _background_group(self) -> dict:
+        """A background save issues its collectives from another thread while training keeps using the job's groups, so
+        it needs a process group of its own (host-side: gloo)."""
+        if not self._ctx.mesh_params.is_distributed:
+            return {"no_dist": True}
+        if self._host_group is None:
+            self._host_group = dist.new_group(backend="gloo")
+        return {"process_group": self._host_group}
+
+    def wait_pending(self) -> None:
+        """Block until the asynchronous save in flight (if any) is on disk, then rotate old checkpoints."""
+        if self._in_flight is None:
+            return
+        future, target = self._in_flight
+        self._in_flight = None
+        future.result()
+        self._ctx.wait_world()
+        self._purge()
+        self._ctx.logger.info(f"Checkpoint {target} successfully saved across the world")
+
     def checkpoint(self, state: Stateful) -> Path:
         target = self._save_dir / f"save-{self._stepper.current_step}"
+        self.wait_pending()
         self._free_memory()
         self._ctx.wait_world()
         self._ctx.logger.info(f"Saving checkpoint {target}")
+        if self._config.async_save:
+            response = dcp.async_save(state_dict={"state": state}, checkpoint_id=target, **self._background_group())
+            self._in_flight = (getattr(response, "upload_completion", response), target)
+            return target
         dcp.save(state_dict={"state": state}, checkpoint_id=target, **self._no_dist_kwargs())
         self._purge()
         self._free_memory()
@@ -67,7 +101,8 @@ class StateCheckpointer:
             self.checkpoint(state)
 
     def load_last_checkpoint(self, state: Stateful) -> bool:
-        """Load the newest ``save-N`` if any; returns whether something was loaded."""
+        """Load the newest complete ``save-N`` if any; returns whether something was loaded."""
+        self.wait_pending()
         existing = self._sorted_checkpoints()
         if not existing:
             self._ctx.logger.info("Starting job from scratch")

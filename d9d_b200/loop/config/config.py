@@ -35,6 +35,9 @@ class CheckpointingConfig(BaseModel):
     save_dir: Path
     period_steps: StepActionPeriod
     num_to_keep: int | None
+    # stage the state in host memory and write it from a background thread while training continues (the next save,
+    # a load and the end of the job wait for the write in flight)
+    async_save: bool = False
 
 
 class ModelStageFactoryConfig(BaseModel):

@@ -97,5 +97,6 @@ class Inference:
                     s.stepper.step()
                     s.checkpointer.checkpoint_if_needed(s)
                     bar.update()
+                s.checkpointer.wait_pending()
                 s.task.finalize(control.FinalizeContext())
                 s.event_bus.trigger(events.EVENT_INFERENCE_FINISHED, events.EventInferenceFinishedContext())

@@ -147,6 +147,7 @@ class Trainer:
                 bar.update()
                 if s.stepper.current_step >= s.stepper.total_steps:
                     break
+            s.checkpointer.wait_pending()
             s.logger.flush(run)
             s.task.finalize(control.FinalizeContext())
             s.event_bus.trigger(events.EVENT_TRAIN_FINISHED, events.EventTrainFinishedContext())

@@ -111,7 +111,8 @@ class SFTTask(TrainTask):
         return ComputeLossResult(loss=ctx.pipeline_results["logps"].sum() / n.clamp_min(1), loss_weight=n / 1000)
 
 
-def trainer_config(tmp, total_batch=8, micro=4, schedule=None, ckpt_period="disable", log_dir=None, source=None):
+def trainer_config(tmp, total_batch=8, micro=4, schedule=None, ckpt_period="disable", log_dir=None, source=None,
+                   async_save=False):
     from d9d_b200.loop.config import TrainerConfig
 
     return TrainerConfig.model_validate({
@@ -123,7 +124,7 @@ def trainer_config(tmp, total_batch=8, micro=4, schedule=None, ckpt_period="disa
         "model_stage_factory": {"source_checkpoint": str(source) if source else None, "checkpoint_only_trainable_parameters": False},
         "determinism": {"base_seed": 11},
         "gc": {"period_steps": 4},
-        "checkpointing": {"save_dir": str(tmp / "ckpt"), "period_steps": ckpt_period, "num_to_keep": 2},
+        "checkpointing": {"save_dir": str(tmp / "ckpt"), "period_steps": ckpt_period, "num_to_keep": 2, "async_save": async_save},
         "gradient_clipping": {"max_norm": 1.0, "log_total_steps": 2},
         "profiling": None,
         "gradient_manager": {"grad_dtype": "float32", "bucket_size_mb": 1},

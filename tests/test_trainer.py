@@ -10,7 +10,7 @@ from tests.helpers_train import LMProvider, SFTTask, SyntheticDataProvider, dens
 
 
 def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable", total_batch=8, micro=4, log=True, samples=64,
-                  optimizer=None, fold_scaling=True, dtype=torch.float32, source=None):
+                  optimizer=None, fold_scaling=True, dtype=torch.float32, source=None, async_save=False):
     from d9d_b200.core.dist_context import DeviceMeshParameters
     from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
     from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
@@ -23,7 +23,7 @@ def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable
     return TrainingConfigurator(
         mesh=mesh or DeviceMeshParameters(),
         parameters=trainer_config(tmp, total_batch=total_batch, micro=micro, schedule=schedule, ckpt_period=ckpt_period,
-                                  log_dir=(tmp / "logs") if log else None, source=source).model_copy(update={}, deep=True)
+                                  log_dir=(tmp / "logs") if log else None, source=source, async_save=async_save).model_copy(update={}, deep=True)
         if fold_scaling else _without_folding(trainer_config(tmp, total_batch=total_batch, micro=micro, schedule=schedule,
                                                              ckpt_period=ckpt_period, log_dir=(tmp / "logs") if log else None,
                                                              source=source)),
@@ -139,6 +139,46 @@ def test_dp_matches_single_process(tmp_path):
     # samples are distributed differently (round-robin sharding) so per-step batches differ; the totals must be close
     # and the first step (same init, different but same-sized batch) must be within noise
     assert abs(ref[0] - got[0]) < 0.2
+
+
+def _async_worker(rank, world, tmp):
+    from pathlib import Path
+
+    from d9d_b200.core.dist_context import DeviceMeshParameters
+
+    trainer = _make_trainer(Path(tmp), mesh=DeviceMeshParameters(data_parallel_replicate=2), ckpt_period=2, total_batch=8, micro=2,
+                            samples=32, async_save=True)
+    trainer.train()
+
+
+def test_asynchronous_checkpoints_and_interrupted_saves(tmp_path):
+    """``async_save``: writes overlap training and are complete (and rotated) when ``train()`` returns; a save directory
+    without DCP's ``.metadata`` (a job killed mid-save) is ignored on resume."""
+    import shutil
+
+    trainer = _make_trainer(tmp_path / "a", ckpt_period=3, async_save=True)
+    trainer.train()
+    saved = tmp_path / "a" / "ckpt" / "t"
+    assert sorted(p.name for p in saved.iterdir()) == ["save-6", "save-8"]  # 8 steps, period 3 + last step, keep 2
+    assert all((p / ".metadata").exists() for p in saved.iterdir())
+
+    # a later, half-written checkpoint must not be picked up; the job is complete at save-8 and does nothing
+    shutil.copytree(saved / "save-8", saved / "save-9")
+    (saved / "save-9" / ".metadata").unlink()
+    again = _make_trainer(tmp_path / "a", ckpt_period=3, async_save=True)
+    again.train()
+    assert again.state.stepper.current_step == 8
+
+    # resume after an interruption reproduces the uninterrupted weights also with background saves
+    reference = {k: v.clone() for k, v in trainer.state.tracked_modules.modules[0].state_dict().items()}
+    (saved / "save-8" / ".metadata").unlink()  # pretend the last save never finished -> resume from save-6
+    resumed = _make_trainer(tmp_path / "a", ckpt_period=3, async_save=True)
+    resumed.train()
+    for k, v in resumed.state.tracked_modules.modules[0].state_dict().items():
+        torch.testing.assert_close(v, reference[k], rtol=0, atol=0, msg=lambda m, k=k: f"{k}: {m}")
+
+    run_distributed(_async_worker, 2, str(tmp_path / "dist"))  # background saves with a process group
+    assert sorted(p.name for p in (tmp_path / "dist" / "ckpt" / "t").iterdir()) == ["save-2", "save-4"]
 
 
 @pytest.mark.dist
