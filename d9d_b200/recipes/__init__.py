@@ -9,6 +9,8 @@ from .causal_lm import (
     SyntheticDataProvider,
 )
 
+from .throughput import ThroughputMeter, transformer_flops_per_token
+
 __all__ = [
     "CausalLMPerplexityTask",
     "CausalLMTask",
@@ -16,4 +18,6 @@ __all__ = [
     "Qwen3MoEModelProviderConfig",
     "SyntheticDataConfig",
     "SyntheticDataProvider",
+    "ThroughputMeter",
+    "transformer_flops_per_token",
 ]

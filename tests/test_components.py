@@ -279,3 +279,40 @@ def test_aim_tracker_against_a_stub_backend(monkeypatch):
     with resumed.open(RunConfig(name="exp", description=None)):
         pass
     assert opened[1].hash == "hash-0"  # the restarted job appends to the same run
+
+
+def test_throughput_meter_reports_tokens_per_second_and_mfu():
+    import time
+
+    from d9d_b200.loop.component import Stepper
+    from d9d_b200.loop.event import EventBus
+    from d9d_b200.loop.event.catalogue.train import (EVENT_TRAIN_READY, EVENT_TRAIN_STEP_POST, EVENT_TRAIN_STEP_PRE, EventStepContext,
+                                                     EventTrainReadyContext)
+    from d9d_b200.recipes import ThroughputMeter, transformer_flops_per_token
+
+    class Run:
+        def __init__(self):
+            self.logged = []
+
+        def scalar(self, name, value, context=None):
+            self.logged.append((name, value))
+
+    flops = transformer_flops_per_token(num_parameters_active=1_000_000, num_layers=2, hidden_size=64, seq_len=128)
+    assert flops == 6e6 + 12 * 2 * 64 * 128 / 2
+    bus, run = EventBus(), Run()
+    meter = ThroughputMeter(tokens_per_step=1000, world_size=2, flops_per_token=flops, peak_flops_per_device=1e12, period_steps=3,
+                            skip_first_steps=1)
+    meter.install(bus)
+    bus.trigger(EVENT_TRAIN_READY, EventTrainReadyContext(run=run))
+    step = EventStepContext(stepper=Stepper(0, 10))
+    for _ in range(6):
+        bus.trigger(EVENT_TRAIN_STEP_PRE, step)
+        time.sleep(0.01)
+        bus.trigger(EVENT_TRAIN_STEP_POST, step)
+    meter.flush()
+    assert len(meter.history) == 2  # steps 2-4 after the skipped first one, then the rest on flush
+    for entry in meter.history:
+        assert 0.009 < entry["step_seconds"] < 0.05
+        assert abs(entry["tokens_per_second"] - 1000 / entry["step_seconds"]) < 1e-6
+        assert abs(entry["mfu"] - 1000 * flops / entry["step_seconds"] / 2e12) < 1e-9
+    assert {name for name, _ in run.logged} == {"throughput/tokens_per_second", "throughput/step_seconds", "throughput/mfu"}
