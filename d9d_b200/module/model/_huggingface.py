@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import dataclasses
 import enum
-from collections.abc import Sequence
+from collections.abc import Callable, Sequence
 
 from d9d_b200.model_state.mapper import ModelStateMapper
 from d9d_b200.model_state.mapper.compose import (
@@ -162,12 +162,33 @@ def dense_mlp_rules() -> tuple[Rule, ...]:
     return tuple(Same(f"mlp.{p}.weight") for p in ("gate_proj", "up_proj", "down_proj"))
 
 
-def backbone_rules(layer_rules: tuple[Rule, ...], num_layers: int, vocab_name: str) -> tuple[Rule, ...]:
+def backbone_rules(layer_rules: "tuple[Rule, ...] | Callable[[int], tuple[Rule, ...]]", num_layers: int,
+                   vocab_name: str) -> tuple[Rule, ...]:
+    """``layer_rules``: the rules of one decoder layer, or a function of the layer index for heterogeneous stacks."""
+    per_layer = layer_rules if callable(layer_rules) else (lambda _index: layer_rules)
     return (
         Renamed("embed_tokens.weight", f"embed_tokens.token_embedding.{vocab_name}.weight"),
-        *(Scoped(f"layers.{i}.", f"layers.{i}.", layer_rules) for i in range(num_layers)),
+        *(Scoped(f"layers.{i}.", f"layers.{i}.", per_layer(i)) for i in range(num_layers)),
         Same("norm.weight"),
     )
+
+
+def latent_attention_rules(low_rank_query: bool) -> tuple[Rule, ...]:
+    """DeepSeek multi-head latent attention: HF ``kv_a_proj_with_mqa / kv_a_layernorm / kv_b_proj`` (and the optional
+    ``q_a_proj / q_a_layernorm / q_b_proj`` bottleneck) <-> ``kv_down_proj / kv_down_norm / kv_up_proj`` (``q_proj.*``)."""
+    query = ((Renamed("self_attn.q_a_proj.weight", "self_attn.q_proj.down_proj.weight"),
+              Renamed("self_attn.q_a_layernorm.weight", "self_attn.q_proj.norm.weight"),
+              Renamed("self_attn.q_b_proj.weight", "self_attn.q_proj.up_proj.weight"))
+             if low_rank_query else (Same("self_attn.q_proj.weight"),))
+    return (*query,
+            Renamed("self_attn.kv_a_proj_with_mqa.weight", "self_attn.kv_down_proj.weight"),
+            Renamed("self_attn.kv_a_layernorm.weight", "self_attn.kv_down_norm.weight"),
+            Renamed("self_attn.kv_b_proj.weight", "self_attn.kv_up_proj.weight"),
+            Same("self_attn.o_proj.weight"))
+
+
+def shared_expert_rules(hf_name: str = "mlp.shared_experts") -> tuple[Rule, ...]:
+    return tuple(Renamed(f"{hf_name}.{p}.weight", f"mlp.shared_expert.expert.{p}.weight") for p in ("gate_proj", "up_proj", "down_proj"))
 
 
 def causal_lm_rules(backbone: tuple[Rule, ...], vocab_name: str) -> tuple[Rule, ...]:

@@ -12,6 +12,7 @@ shared classes; the forward/pipelining contracts are the reference's:
 
 from __future__ import annotations
 
+import inspect
 from collections.abc import Callable
 from typing import Any, Protocol
 
@@ -54,7 +55,7 @@ class DecoderBackbone(nn.Module, ModuleLateInit, ModuleSupportsPipelining):
         stage: PipelineStageInfo,
         hidden_states_snapshot_mode: HiddenStatesAggregationMode,
         enable_checkpointing: bool,
-        layer_factory: Callable[[Any], nn.Module],
+        layer_factory: Callable[..., nn.Module],
         rope_style: RotaryEmbeddingStyle = RotaryEmbeddingStyle.HALF,
         rope_scaling: RopeScaling | None = None,
     ):
@@ -72,7 +73,10 @@ class DecoderBackbone(nn.Module, ModuleLateInit, ModuleSupportsPipelining):
         )
         self._num_layers_before = first
         self._layer_keys = [str(i) for i in range(first, last)]
-        self.layers = nn.ModuleDict({key: layer_factory(params.layer) for key in self._layer_keys})
+        # heterogeneous stacks (e.g. dense first layers, MoE afterwards) take the global layer index as second argument
+        indexed = len(inspect.signature(layer_factory).parameters) >= 2
+        self.layers = nn.ModuleDict({key: (layer_factory(params.layer, int(key)) if indexed else layer_factory(params.layer))
+                                     for key in self._layer_keys})
         self.rope_provider = RotaryEmbeddingProvider(
             rope_base=params.rope_base, head_dim=params.layer.head_dim, max_position_ids=params.max_position_ids,
             style=rope_style, rope_scaling=rope_scaling,

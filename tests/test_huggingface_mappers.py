@@ -246,3 +246,49 @@ def test_qwen3_classification_and_embedding_match_transformers():
     if got.norm(dim=-1).sub(1).abs().max() < 1e-4:  # the head L2-normalises by default
         want = torch.nn.functional.normalize(want, dim=-1)
     torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("q_lora_rank", [None, 12])
+def test_deepseek_v2_matches_transformers_and_round_trips(q_lora_rank):
+    """Latent attention + dense first layer + MoE layers with shared experts, against ``DeepseekV2ForCausalLM``."""
+    transformers = pytest.importorskip("transformers")
+    from d9d_b200.module.model.deepseek_v2 import (DeepseekV2ForCausalLM, DeepseekV2ForCausalLMParameters, DeepseekV2LayerParameters,
+                                                   DeepseekV2Parameters, mapper_from_huggingface_deepseek_v2_for_causal_lm,
+                                                   mapper_to_huggingface_deepseek_v2_for_causal_lm)
+
+    cfg = transformers.DeepseekV2Config(
+        vocab_size=96, hidden_size=32, intermediate_size=48, moe_intermediate_size=16, num_hidden_layers=3, num_attention_heads=4,
+        num_key_value_heads=4, first_k_dense_replace=1, kv_lora_rank=16, q_lora_rank=q_lora_rank, n_routed_experts=4,
+        n_shared_experts=2, qk_nope_head_dim=8, qk_rope_head_dim=4, v_head_dim=8, num_experts_per_tok=2, topk_method="greedy",
+        norm_topk_prob=False, routed_scaling_factor=1.0, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=64,
+        tie_word_embeddings=False, attention_bias=False, mlp_bias=False)
+    torch.manual_seed(0)
+    hf_model = transformers.DeepseekV2ForCausalLM(cfg).eval()
+    p = DeepseekV2ForCausalLMParameters(model=DeepseekV2Parameters(
+        layer=DeepseekV2LayerParameters(hidden_size=32, rms_norm_eps=1e-6, num_attention_heads=4, qk_nope_head_dim=8, qk_rope_head_dim=4,
+                                        v_head_dim=8, kv_lora_rank=16, q_lora_rank=q_lora_rank, intermediate_size=48,
+                                        first_k_dense_replace=1, moe_intermediate_size=16, num_experts=4, experts_top_k=2,
+                                        num_shared_experts=2),
+        num_hidden_layers=3, rope_base=10000, max_position_ids=64, **VOCAB))
+    ours = DeepseekV2ForCausalLM(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    ours.reset_parameters()
+    from d9d_b200.module.block.ffn import SwiGLU
+    from d9d_b200.module.block.moe import MoELayer
+
+    assert isinstance(ours.model.layers["0"].mlp, SwiGLU) and isinstance(ours.model.layers["1"].mlp, MoELayer)
+
+    hf_state = dict(hf_model.state_dict())
+    fmt = "fused" if any(k.endswith("experts.gate_up_proj") for k in hf_state) else "module_list"
+    _load(ours, _run(mapper_from_huggingface_deepseek_v2_for_causal_lm(p, fmt), hf_state))
+    ids, labels = torch.randint(0, 96, (2, 12)), torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        want = _per_token_nll(hf_model, ids, pos, labels)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+    native = {k: v.detach().clone() for k, v in ours.state_dict().items() if "tokens_per_expert" not in k}
+    exported = _run(mapper_to_huggingface_deepseek_v2_for_causal_lm(p, fmt), native)
+    assert exported.keys() == hf_state.keys()
+    for k in hf_state:
+        torch.testing.assert_close(exported[k], hf_state[k], rtol=0, atol=0)

@@ -39,7 +39,18 @@ def _build(moe: bool):
     from d9d_b200.pipelining.api import PipelineStageInfo
 
     torch.manual_seed(5)
-    if moe:
+    if moe == "deepseek":
+        from d9d_b200.module.model.deepseek_v2 import (DeepseekV2ForCausalLM as Cls, DeepseekV2ForCausalLMParameters,
+                                                       DeepseekV2LayerParameters, DeepseekV2Parameters)
+
+        params = DeepseekV2ForCausalLMParameters(model=DeepseekV2Parameters(
+            layer=DeepseekV2LayerParameters(hidden_size=32, rms_norm_eps=1e-6, num_attention_heads=4, qk_nope_head_dim=8,
+                                            qk_rope_head_dim=4, v_head_dim=8, kv_lora_rank=16, q_lora_rank=12, intermediate_size=48,
+                                            first_k_dense_replace=1, moe_intermediate_size=16, num_experts=4, experts_top_k=2,
+                                            num_shared_experts=1),
+            num_hidden_layers=2, rope_base=10000, max_position_ids=64, split_vocab_size={"regular": 100, "special": 28},
+            split_vocab_order=["regular", "special"]))
+    elif moe:
         from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM as Cls
 
         params = moe_params()
@@ -69,7 +80,9 @@ def _worker(rank, world_size, mesh_name, moe):
 
     ctx = DeviceMeshParameters(**MESHES[mesh_name]).build()
     model = _build(moe)
-    if moe:
+    if moe == "deepseek":
+        from d9d_b200.module.parallelism.model.deepseek_v2 import parallelize_deepseek_v2_for_causal_lm as plan
+    elif moe:
         from d9d_b200.module.parallelism.model.qwen3_moe import parallelize_qwen3_moe_for_causal_lm as plan
     else:
         from d9d_b200.module.parallelism.model.qwen3_dense import parallelize_qwen3_dense_for_causal_lm as plan
@@ -107,3 +120,9 @@ def test_dense_model_matches_single_process(mesh_name):
 @pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr4_ep2", "dpr2_dps2_ep4", "dps2_cps2_ep2", "dpr2_tp2_ep2"])
 def test_moe_model_matches_single_process(mesh_name):
     run_distributed(_worker, 4, mesh_name, True)
+
+
+@pytest.mark.parametrize("mesh_name", ["dps2_cps2_ep2"])
+def test_deepseek_v2_model_matches_single_process(mesh_name):
+    """Latent attention under context parallelism, dense first layer + MoE layers with a shared expert under FSDP x EP."""
+    run_distributed(_worker, 4, mesh_name, "deepseek")
