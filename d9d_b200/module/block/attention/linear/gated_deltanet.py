@@ -134,7 +134,10 @@ class GatedDeltaNet(nn.Module, ModuleLateInit):
         self.out_norm = RMSNorm(head_v_dim, eps=norm_eps)
         self.o_proj = Linear(v_dim, hidden_size, bias=False)
 
-    def forward(self, hidden_states: torch.Tensor, attention_mask: torch.Tensor | None = None) -> torch.Tensor:
+    def forward(self, hidden_states: torch.Tensor, attention_mask: torch.Tensor | None = None,
+                position_embeddings: tuple[torch.Tensor, torch.Tensor] | None = None) -> torch.Tensor:
+        del position_embeddings  # order is encoded by the recurrence itself; accepted so that decoder layers can treat
+        # every token mixer alike
         b, s, _ = hidden_states.shape
         if attention_mask is not None:
             hidden_states = hidden_states * attention_mask.unsqueeze(-1).to(hidden_states.dtype)

@@ -12,7 +12,9 @@ import dataclasses
 import enum
 from collections.abc import Callable, Sequence
 
-from d9d_b200.model_state.mapper import ModelStateMapper
+import torch
+
+from d9d_b200.model_state.mapper import ModelStateMapper, StateGroup
 from d9d_b200.model_state.mapper.compose import (
     ModelStateMapperParallel,
     ModelStateMapperPrefixScope,
@@ -23,8 +25,10 @@ from d9d_b200.model_state.mapper.leaf import (
     ModelStateMapperConcatenateTensors,
     ModelStateMapperIdentity,
     ModelStateMapperRename,
+    ModelStateMapperSqueeze,
     ModelStateMapperStackTensors,
     ModelStateMapperTranspose,
+    ModelStateMapperUnsqueeze,
     ModelStateMapperUnstackTensors,
 )
 
@@ -79,7 +83,45 @@ class Scoped:
     rules: tuple["Rule", ...]
 
 
-Rule = Same | Renamed | ExpertsPerModule | ExpertsFused | Scoped
+@dataclasses.dataclass(frozen=True)
+class HeadInterleaved:
+    """HF fuses several per-head projections into one weight ``[heads * len(natives) * head_dim, in]`` laid out head by
+    head (``[part_0 | part_1 | ...]`` inside every head, e.g. Qwen3.5's query + output gate); native: one weight per part."""
+
+    hf: str
+    natives: tuple[str, ...]
+    head_dim: int
+
+
+@dataclasses.dataclass(frozen=True)
+class Unsqueezed:
+    """HF keeps an extra singleton dim (``conv1d.weight [C, 1, K]``), native does not (``[C, K]``)."""
+
+    hf: str
+    native: str
+    dim: int
+
+
+Rule = Same | Renamed | ExpertsPerModule | ExpertsFused | Scoped | HeadInterleaved | Unsqueezed
+
+
+class _HeadInterleaveMapper(ModelStateMapper):
+    def __init__(self, rule: HeadInterleaved, from_hf: bool):
+        self._rule, self._from_hf = rule, from_hf
+
+    def state_dependency_groups(self) -> frozenset[StateGroup]:
+        fused, parts = frozenset([self._rule.hf]), frozenset(self._rule.natives)
+        return frozenset([StateGroup(inputs=fused, outputs=parts) if self._from_hf else StateGroup(inputs=parts, outputs=fused)])
+
+    def apply(self, group: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        n, d = len(self._rule.natives), self._rule.head_dim
+        if self._from_hf:
+            fused = group[self._rule.hf]
+            per_head = fused.reshape(-1, n, d, fused.shape[-1])  # [heads, part, head_dim, in]
+            return {name: per_head[:, i].reshape(-1, fused.shape[-1]).contiguous() for i, name in enumerate(self._rule.natives)}
+        parts = [group[name] for name in self._rule.natives]
+        stacked = torch.stack([p.reshape(-1, d, p.shape[-1]) for p in parts], dim=1)  # [heads, part, head_dim, in]
+        return {self._rule.hf: stacked.reshape(-1, parts[0].shape[-1]).contiguous()}
 
 
 def _compile_one(rule: Rule, direction: Direction) -> list[ModelStateMapper]:
@@ -126,6 +168,12 @@ def _compile_one(rule: Rule, direction: Direction) -> list[ModelStateMapper]:
                 ModelStateMapperTranspose(rule.hf_down, dims=(-1, -2)),
             ]),
         ]
+    if isinstance(rule, HeadInterleaved):
+        return [_HeadInterleaveMapper(rule, from_hf)]
+    if isinstance(rule, Unsqueezed):
+        if from_hf:
+            return [ModelStateMapperSequential([ModelStateMapperSqueeze(rule.hf, rule.dim), ModelStateMapperRename(rule.hf, rule.native)])]
+        return [ModelStateMapperSequential([ModelStateMapperRename(rule.native, rule.hf), ModelStateMapperUnsqueeze(rule.hf, rule.dim)])]
     if isinstance(rule, Scoped):
         inner = compile_rules(rule.rules, direction)
         src, dst = (rule.hf_prefix, rule.native_prefix) if from_hf else (rule.native_prefix, rule.hf_prefix)

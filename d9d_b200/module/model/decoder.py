@@ -58,6 +58,7 @@ class DecoderBackbone(nn.Module, ModuleLateInit, ModuleSupportsPipelining):
         layer_factory: Callable[..., nn.Module],
         rope_style: RotaryEmbeddingStyle = RotaryEmbeddingStyle.HALF,
         rope_scaling: RopeScaling | None = None,
+        zero_centered_norm: bool = False,
     ):
         super().__init__()
         hidden = params.layer.hidden_size
@@ -78,11 +79,13 @@ class DecoderBackbone(nn.Module, ModuleLateInit, ModuleSupportsPipelining):
         self.layers = nn.ModuleDict({key: (layer_factory(params.layer, int(key)) if indexed else layer_factory(params.layer))
                                      for key in self._layer_keys})
         self.rope_provider = RotaryEmbeddingProvider(
-            rope_base=params.rope_base, head_dim=params.layer.head_dim, max_position_ids=params.max_position_ids,
+            # families with partial rotary embeddings expose the rotated width as ``layer.rope_dim``
+            rope_base=params.rope_base, head_dim=getattr(params.layer, "rope_dim", params.layer.head_dim),
+            max_position_ids=params.max_position_ids,
             style=rope_style, rope_scaling=rope_scaling,
         )
         if stage.is_current_stage_last:
-            self.norm = RMSNorm(hidden, eps=params.layer.rms_norm_eps)
+            self.norm = RMSNorm(hidden, eps=params.layer.rms_norm_eps, zero_centered=zero_centered_norm)
         self._stage = stage
         self._snapshot_mode = hidden_states_snapshot_mode
         self._hidden_size = hidden
@@ -273,12 +276,13 @@ class DecoderForEmbedding(_HeadedDecoder):
 class PreNormDecoderLayer(nn.Module, ModuleLateInit):
     """``x + attn(norm(x))`` then ``x + mlp(norm(x))`` — the layer shape shared by Qwen3 / Llama-3 / Mixtral."""
 
-    def __init__(self, self_attn: nn.Module, mlp: nn.Module, hidden_size: int, rms_norm_eps: float):
+    def __init__(self, self_attn: nn.Module, mlp: nn.Module, hidden_size: int, rms_norm_eps: float,
+                 zero_centered_norm: bool = False):
         super().__init__()
-        self.self_attn = self_attn
+        self.self_attn = self_attn  # any token mixer taking (hidden_states, position_embeddings, attention_mask)
         self.mlp = mlp
-        self.input_layernorm = RMSNorm(hidden_size, eps=rms_norm_eps)
-        self.post_attention_layernorm = RMSNorm(hidden_size, eps=rms_norm_eps)
+        self.input_layernorm = RMSNorm(hidden_size, eps=rms_norm_eps, zero_centered=zero_centered_norm)
+        self.post_attention_layernorm = RMSNorm(hidden_size, eps=rms_norm_eps, zero_centered=zero_centered_norm)
 
     def forward(self, hidden_states: torch.Tensor, position_embeddings: tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
         attn = self.self_attn(hidden_states=self.input_layernorm(hidden_states), position_embeddings=position_embeddings,

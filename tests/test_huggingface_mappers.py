@@ -292,3 +292,49 @@ def test_deepseek_v2_matches_transformers_and_round_trips(q_lora_rank):
     assert exported.keys() == hf_state.keys()
     for k in hf_state:
         torch.testing.assert_close(exported[k], hf_state[k], rtol=0, atol=0)
+
+
+def test_qwen3_5_hybrid_matches_transformers_and_round_trips():
+    """Gated DeltaNet layers interleaved with gated partial-rotary attention, zero-centred norms, vs ``Qwen3_5ForCausalLM``."""
+    pytest.importorskip("transformers")
+    from transformers.models.qwen3_5.configuration_qwen3_5 import Qwen3_5TextConfig
+    from transformers.models.qwen3_5.modeling_qwen3_5 import Qwen3_5ForCausalLM as HFModel
+
+    from d9d_b200.module.block.attention import GatedDeltaNet, GroupedQueryAttention
+    from d9d_b200.module.model.qwen3_5 import (Qwen3_5ForCausalLM, Qwen3_5ForCausalLMParameters, Qwen3_5LayerParameters, Qwen3_5Parameters,
+                                               mapper_from_huggingface_qwen3_5_for_causal_lm, mapper_to_huggingface_qwen3_5_for_causal_lm)
+
+    cfg = Qwen3_5TextConfig(vocab_size=96, hidden_size=32, intermediate_size=48, num_hidden_layers=4, num_attention_heads=4,
+                            num_key_value_heads=2, head_dim=16, rms_norm_eps=1e-6, max_position_embeddings=64, tie_word_embeddings=False,
+                            linear_conv_kernel_dim=4, linear_key_head_dim=8, linear_value_head_dim=8, linear_num_key_heads=2,
+                            linear_num_value_heads=4, full_attention_interval=2,
+                            rope_parameters={"rope_type": "default", "rope_theta": 10000.0, "partial_rotary_factor": 0.25})
+    assert cfg.layer_types == ["linear_attention", "full_attention"] * 2
+    torch.manual_seed(0)
+    hf_model = HFModel(cfg).eval()
+    with torch.no_grad():  # HF initialises the zero-centred norm weights at exactly 0: perturb them so that they matter
+        for name, param in hf_model.named_parameters():
+            if "norm" in name or "dt_bias" in name:
+                param.add_(torch.randn_like(param) * 0.1)
+    p = Qwen3_5ForCausalLMParameters(model=Qwen3_5Parameters(
+        layer=Qwen3_5LayerParameters(hidden_size=32, intermediate_size=48, rms_norm_eps=1e-6, num_attention_heads=4, num_key_value_heads=2,
+                                     head_dim=16, partial_rotary_factor=0.25, linear_num_key_heads=2, linear_num_value_heads=4,
+                                     linear_key_head_dim=8, linear_value_head_dim=8, linear_conv_kernel_dim=4, full_attention_interval=2),
+        num_hidden_layers=4, rope_base=10000, max_position_ids=64, **VOCAB))
+    ours = Qwen3_5ForCausalLM(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    ours.reset_parameters()
+    assert isinstance(ours.model.layers["0"].self_attn, GatedDeltaNet) and isinstance(ours.model.layers["1"].self_attn, GroupedQueryAttention)
+
+    hf_state = dict(hf_model.state_dict())
+    _load(ours, _run(mapper_from_huggingface_qwen3_5_for_causal_lm(p), hf_state))
+    ids, labels = torch.randint(0, 96, (2, 12)), torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        want = _per_token_nll(hf_model, ids, pos, labels)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+
+    exported = _run(mapper_to_huggingface_qwen3_5_for_causal_lm(p), {k: v.detach().clone() for k, v in ours.state_dict().items()})
+    assert exported.keys() == hf_state.keys()
+    for k in hf_state:
+        torch.testing.assert_close(exported[k], hf_state[k], rtol=0, atol=0)
