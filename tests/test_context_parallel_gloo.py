@@ -17,14 +17,26 @@ def _full_reference(q, k, v, causal):
     return q, k, v, out
 
 
-def _worker(rank, world, mode, layout_name, causal, heads, kv_heads):
+def _worker(rank, world, mode, heads, kv_heads):
+    """One process group, every (layout, causal) combination (spawning processes dominates the cost of these tests)."""
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo")
+    for layout_name in ("zigzag", "contiguous"):
+        for causal in (True, False):
+            try:
+                _check(rank, world, mode, layout_name, causal, heads, kv_heads)
+            except AssertionError as exc:
+                raise AssertionError(f"[{mode} layout={layout_name} causal={causal}] {exc}") from exc
+
+
+def _check(rank, world, mode, layout_name, causal, heads, kv_heads):
     import torch.distributed as dist
 
     from d9d_b200.kernel.context_parallel import (ContextParallelLayout, gather_sequence, local_sequence_indices, ring_attention,
                                                   shard_sequence, ulysses_attention)
     from d9d_b200.kernel.flash_attn import attention_reference
 
-    dist.init_process_group("gloo")
     group = dist.group.WORLD
     layout = ContextParallelLayout(layout_name)
     torch.manual_seed(0)  # identical full tensors on every rank
@@ -52,18 +64,14 @@ def _worker(rank, world, mode, layout_name, causal, heads, kv_heads):
         torch.testing.assert_close(mine.grad, shard_sequence(full.grad, 1, world, rank, layout), atol=1e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("layout", ["zigzag", "contiguous"])
-@pytest.mark.parametrize("causal", [True, False])
 @pytest.mark.parametrize("world,heads,kv_heads", [(2, 4, 2), (4, 4, 1), (3, 3, 3)])
-def test_ring_attention_matches_full_attention(world, heads, kv_heads, causal, layout):
-    run_distributed(_worker, world, "ring", layout, causal, heads, kv_heads)
+def test_ring_attention_matches_full_attention(world, heads, kv_heads):
+    run_distributed(_worker, world, "ring", heads, kv_heads)
 
 
-@pytest.mark.parametrize("layout", ["zigzag", "contiguous"])
-@pytest.mark.parametrize("causal", [True, False])
 @pytest.mark.parametrize("world,heads,kv_heads", [(2, 4, 2), (4, 8, 4)])
-def test_ulysses_attention_matches_full_attention(world, heads, kv_heads, causal, layout):
-    run_distributed(_worker, world, "ulysses", layout, causal, heads, kv_heads)
+def test_ulysses_attention_matches_full_attention(world, heads, kv_heads):
+    run_distributed(_worker, world, "ulysses", heads, kv_heads)
 
 
 def test_layout_indices_partition_the_sequence():

@@ -29,7 +29,6 @@ MESHES = {
     "cpr2_tp2": dict(context_parallel_replicate=2, tensor_parallel=2),
     "dpr2_tp2_ep2": dict(data_parallel_replicate=2, tensor_parallel=2, expert_parallel=2),
 }
-WORLD = {"tp2": 2}
 
 
 def _build(moe: bool):
@@ -70,7 +69,13 @@ def _batch(i):
     return ids, labels, torch.arange(16)[None].expand(2, -1)
 
 
-def _worker(rank, world_size, mesh_name, moe):
+def _worker(rank, world_size, mesh_names, moe):
+    """Several meshes over one set of processes (spawning processes dominates the cost of these tests)."""
+    for mesh_name in mesh_names:
+        _check_mesh(rank, world_size, mesh_name, moe)
+
+
+def _check_mesh(rank, world_size, mesh_name, moe):
     import torch.distributed as dist
     from torch.distributed.tensor import DTensor
 
@@ -112,17 +117,21 @@ def _worker(rank, world_size, mesh_name, moe):
     dist.barrier()
 
 
-@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr2_dps2", "cps4", "cpr2_cps2", "dpr2_cps2", "tp2", "dpr2_tp2", "cpr2_tp2"])
-def test_dense_model_matches_single_process(mesh_name):
-    run_distributed(_worker, WORLD.get(mesh_name, 4), mesh_name, False)
+@pytest.mark.parametrize("mesh_names", [("dpr4", "dps4", "dpr2_dps2"), ("cps4", "cpr2_cps2", "dpr2_cps2"), ("dpr2_tp2", "cpr2_tp2")],
+                         ids="+".join)
+def test_dense_model_matches_single_process(mesh_names):
+    run_distributed(_worker, 4, mesh_names, False)
 
 
-@pytest.mark.parametrize("mesh_name", ["dpr4", "dps4", "dpr4_ep2", "dpr2_dps2_ep4", "dps2_cps2_ep2", "dpr2_tp2_ep2"])
-def test_moe_model_matches_single_process(mesh_name):
-    run_distributed(_worker, 4, mesh_name, True)
+def test_dense_model_matches_single_process_on_two_tensor_parallel_ranks():
+    run_distributed(_worker, 2, ("tp2",), False)
 
 
-@pytest.mark.parametrize("mesh_name", ["dps2_cps2_ep2"])
-def test_deepseek_v2_model_matches_single_process(mesh_name):
+@pytest.mark.parametrize("mesh_names", [("dpr4", "dps4", "dpr4_ep2"), ("dpr2_dps2_ep4", "dps2_cps2_ep2", "dpr2_tp2_ep2")], ids="+".join)
+def test_moe_model_matches_single_process(mesh_names):
+    run_distributed(_worker, 4, mesh_names, True)
+
+
+def test_deepseek_v2_model_matches_single_process():
     """Latent attention under context parallelism, dense first layer + MoE layers with a shared expert under FSDP x EP."""
-    run_distributed(_worker, 4, mesh_name, "deepseek")
+    run_distributed(_worker, 4, ("dps2_cps2_ep2",), "deepseek")
