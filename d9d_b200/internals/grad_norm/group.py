@@ -6,7 +6,9 @@ from collections.abc import Iterable
 import torch
 from torch import nn
 from torch.distributed import DeviceMesh
-from torch.distributed.tensor import DTensor, Shard
+from torch.distributed.tensor import DTensor
+
+from d9d_b200.internals.grad_sync.placement import is_shard_placement
 
 
 @dataclasses.dataclass(kw_only=True, frozen=True)
@@ -28,7 +30,7 @@ def _shard_meshes(param: nn.Parameter) -> tuple[DeviceMesh, ...] | None:
     names = data.device_mesh.mesh_dim_names
     if names is None:
         raise ValueError("Only named meshes are supported.")
-    sharded = tuple(data.device_mesh[names[i]] for i, pl in enumerate(data.placements) if isinstance(pl, Shard))
+    sharded = tuple(data.device_mesh[names[i]] for i, pl in enumerate(data.placements) if is_shard_placement(pl))
     return sharded or None
 
 

@@ -40,7 +40,7 @@ def clip_grad_norm_distributed_(parameter_groups: ParametersForNorm, max_norm: f
                                 pp_mesh: DeviceMesh | None, pending_scale: torch.Tensor | None = None) -> torch.Tensor:
     """Global gradient norm over every parallel dimension, then in-place clipping (tensor coefficient, no host sync).
 
-    Sharded groups all-reduce their ``||g||^p`` over the mesh they are sharded on (async, launched first);
+    Sharded groups all-reduce their ``||g||^p`` over the mesh dim(s) they are sharded on (async, launched first);
     replicated groups contribute locally; finally one scalar all-reduce over the pipeline dimension.
     ``max_norm=None`` only measures.  ``pending_scale`` (device scalar) is a factor that has not been applied to the
     gradients yet: the norm is reported for the scaled gradients and the clip coefficient is multiplied into it instead
@@ -53,9 +53,11 @@ def clip_grad_norm_distributed_(parameter_groups: ParametersForNorm, max_norm: f
         for key, params in parameter_groups.items():
             value = _local_norm_pow(params, norm_type, device)
             if key.shard_meshes is not None:
-                if len(key.shard_meshes) != 1:
-                    raise ValueError("Currently we do not support calculating norm for tensors that are sharded on multiple dims")
-                works.append(dist.all_reduce(value, op=_reduce_op(norm_type), group=key.shard_meshes[0].get_group(), async_op=True))
+                # shards over several mesh dims (e.g. FSDP x tensor parallel) partition the tensor over the product of the
+                # dims: reduce over all but the last dim now, the last one asynchronously like single-dim groups
+                for mesh in key.shard_meshes[:-1]:
+                    dist.all_reduce(value, op=_reduce_op(norm_type), group=mesh.get_group())
+                works.append(dist.all_reduce(value, op=_reduce_op(norm_type), group=key.shard_meshes[-1].get_group(), async_op=True))
             partials.append(value)
         for w in works:
             w.wait()

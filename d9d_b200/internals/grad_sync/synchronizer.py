@@ -5,11 +5,12 @@ import dataclasses
 import torch
 from torch import nn
 from torch.distributed import DeviceMesh
-from torch.distributed.tensor import DTensor, Replicate, Shard
+from torch.distributed.tensor import DTensor
 
 from d9d_b200.kernel._native import EXTERNAL_GRAD_OWNER_ATTR
 
 from .bucket import AbstractGradientBucket, LocalGradientBucket, SyncGradientBucket, local_of
+from .placement import is_shard_placement
 
 _ARENA_ALIGN = 64  # elements; keeps every bucket / parameter slice 256-byte aligned for vectorised kernels
 
@@ -18,9 +19,9 @@ def find_reduce_mesh(data: DTensor) -> DeviceMesh | None:
     """Sub-mesh of the dims on which the tensor is ``Replicate`` (= where its gradient must be summed)."""
     dims = []
     for i, placement in enumerate(data.placements):
-        if isinstance(placement, Replicate):
+        if placement.is_replicate():
             dims.append(i)
-        elif not isinstance(placement, Shard):
+        elif not is_shard_placement(placement):
             raise ValueError(f"Unknown grad placement: {placement}")
     if not dims:
         return None

@@ -25,14 +25,23 @@ from d9d_b200.module.parallelism.api import (
 from d9d_b200.pipelining.api import PipelineStageInfo
 
 _DENSE_DIMS = ("dp_replicate", "dp_cp_shard", "cp_replicate")
-_TP_DIMS = ("dp_replicate", "cp_replicate", "tp")
+_TP_DIMS = ("dp_replicate", "cp_replicate", "tp")  # mesh of the tensor-parallel linears; FSDP adds dp_cp_shard on top
+_DENSE_TP_DIMS = ("dp_replicate", "dp_cp_shard", "cp_replicate", "tp")
 
 
 def _check_supported(dist_context: DistributedContext) -> None:
     dims = dist_context.mesh_params
-    if dims.has_tensor_parallel and (dims.has_data_parallel_shard or dims.has_context_parallel_shard):
-        raise ValueError("Tensor parallelism cannot be combined with FSDP sharding (data_parallel_shard / "
-                         "context_parallel_shard) yet: use the *_replicate degrees.")
+    sharded = dims.has_data_parallel_shard or dims.has_context_parallel_shard
+    replicated = dims.has_data_parallel_replicate or dims.has_context_parallel_replicate
+    if dims.has_tensor_parallel and sharded and replicated:
+        # FSDP2 accepts tensor-parallel parameters only on a 1-D ``tp`` mesh, so they cannot also carry replicate dims
+        raise ValueError("Tensor parallelism combines with FSDP sharding (data_parallel_shard / context_parallel_shard) or with "
+                         "replication (data_parallel_replicate / context_parallel_replicate), not with both at once.")
+
+
+def _tensor_parallel_mesh(dist_context: DistributedContext):  # noqa: ANN202
+    dense = dist_context.mesh_for(DENSE_DOMAIN)
+    return dense[tuple(d for d in _TP_DIMS if d == "tp" or dense[d].size() > 1)]
 
 
 def dense_unit(dist_context: DistributedContext, module: nn.Module) -> None:
@@ -40,8 +49,7 @@ def dense_unit(dist_context: DistributedContext, module: nn.Module) -> None:
     activations are sequence-sharded there, so its gradients are partial sums that must be reduced over ``tp`` too)."""
     dense = dist_context.mesh_for(DENSE_DOMAIN)
     if dist_context.mesh_params.has_tensor_parallel:
-        dims = tuple(d for d in _TP_DIMS if dense[d].size() > 1)
-        parallelize_replicate(module, dense[dims], skip_distributed=True)
+        parallelize_hsdp(module, mesh=dense[_DENSE_TP_DIMS], skip_distributed=True)
     else:
         parallelize_hsdp(module, mesh=dense[_DENSE_DIMS])
 
@@ -50,7 +58,7 @@ def _tensor_parallel_layer(dist_context: DistributedContext, layer: nn.Module) -
     """Megatron-style tensor + sequence parallelism of one decoder layer: hidden states between blocks carry ``S / tp``
     tokens; attention and the dense MLP gather them in their column-parallel input GEMMs and scatter them again in their
     row-parallel output GEMMs (fused into the GEMMs on CUDA)."""
-    mesh = dist_context.mesh_for(DENSE_DOMAIN)[_TP_DIMS]
+    mesh = _tensor_parallel_mesh(dist_context)
     if not isinstance(layer.self_attn, GroupedQueryAttention):
         raise ValueError(f"tensor parallelism is implemented for GroupedQueryAttention, got {type(layer.self_attn).__name__}")
     parallelize_attention_tensor_parallel(layer.self_attn, mesh)
@@ -73,8 +81,8 @@ def parallelize_backbone(dist_context: DistributedContext, model: DecoderBackbon
             _tensor_parallel_layer(dist_context, layer)
         if isinstance(layer.mlp, MoELayer):
             parallelize_expert_parallel(layer.mlp, mesh_experts=expert_mesh)
-        elif not tensor_parallel:
-            dense_unit(dist_context, layer.mlp)
+        else:
+            dense_unit(dist_context, layer.mlp)  # with tensor parallelism: FSDP-shards the column / row parallel weights
         if cp_mesh.size() > 1:
             parallelize_context_parallel(layer.self_attn, cp_mesh)
         dense_unit(dist_context, layer.self_attn)  # with tensor parallelism: what the TP styles left (q/k norms)

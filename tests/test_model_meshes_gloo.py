@@ -28,6 +28,7 @@ MESHES = {
     "dpr2_tp2": dict(data_parallel_replicate=2, tensor_parallel=2),
     "cpr2_tp2": dict(context_parallel_replicate=2, tensor_parallel=2),
     "dpr2_tp2_ep2": dict(data_parallel_replicate=2, tensor_parallel=2, expert_parallel=2),
+    "dps2_tp2": dict(data_parallel_shard=2, tensor_parallel=2),  # FSDP over tensor-parallel parameters (strided shards)
 }
 
 
@@ -117,7 +118,7 @@ def _check_mesh(rank, world_size, mesh_name, moe):
     dist.barrier()
 
 
-@pytest.mark.parametrize("mesh_names", [("dpr4", "dps4", "dpr2_dps2"), ("cps4", "cpr2_cps2", "dpr2_cps2"), ("dpr2_tp2", "cpr2_tp2")],
+@pytest.mark.parametrize("mesh_names", [("dpr4", "dps4", "dpr2_dps2"), ("cps4", "cpr2_cps2", "dpr2_cps2"), ("dpr2_tp2", "cpr2_tp2", "dps2_tp2")],
                          ids="+".join)
 def test_dense_model_matches_single_process(mesh_names):
     run_distributed(_worker, 4, mesh_names, False)

@@ -185,7 +185,8 @@ def test_asynchronous_checkpoints_and_interrupted_saves(tmp_path):
 @pytest.mark.parametrize("mesh_kwargs,world", [({"context_parallel_shard": 2}, 2),
                                                ({"context_parallel_replicate": 2, "pipeline_parallel": 2}, 4),
                                                ({"tensor_parallel": 2}, 2),
-                                               ({"tensor_parallel": 2, "context_parallel_replicate": 2}, 4)])
+                                               ({"tensor_parallel": 2, "context_parallel_replicate": 2}, 4),
+                                               ({"tensor_parallel": 2, "context_parallel_shard": 2}, 4)])
 def test_sequence_sharded_training_reproduces_the_single_process_run(tmp_path, mesh_kwargs, world):
     """Ranks of a context- / tensor-parallel group read the same samples and split every sequence (and, for tensor
     parallelism, the heads and MLP columns): the loss trajectory must equal the single-process one (same batches, same
