@@ -24,7 +24,7 @@ class LoRALinear(nn.Module):
         self.base = base_layer
         self.dropout = nn.Dropout(params.dropout)
         self._scale = params.alpha / params.r
-        self.reset_parameters()
+        self._reset_adapters()  # wrapping an initialised layer must not touch its weights
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.base(x) + self._scale * self.lora_B(self.lora_A(self.dropout(x)))
@@ -35,6 +35,14 @@ class LoRALinear(nn.Module):
         return self.base
 
     def reset_parameters(self) -> None:
+        """Late initialisation of the whole wrapped layer: the (frozen) base as well - a model built on the meta device and
+        materialised with ``to_empty`` has no valid base weights until they are initialised here or loaded."""
+        if self.lora_A.weight.is_meta:
+            return
+        self.base.reset_parameters()
+        self._reset_adapters()
+
+    def _reset_adapters(self) -> None:
         if self.lora_A.weight.is_meta:
             return
         self.lora_A.reset_parameters()
@@ -52,7 +60,7 @@ class LoRAGroupedLinear(nn.Module):
         self.base = base_layer
         self.dropout = nn.Dropout(params.dropout)
         self._scale = params.alpha / params.r
-        self.reset_parameters()
+        self._reset_adapters()  # wrapping an initialised layer must not touch its weights
 
     def forward(self, x: torch.Tensor, x_groups) -> torch.Tensor:
         return self.base(x, x_groups) + self._scale * self.lora_B(self.lora_A(self.dropout(x), x_groups), x_groups)
@@ -64,6 +72,14 @@ class LoRAGroupedLinear(nn.Module):
         return self.base
 
     def reset_parameters(self) -> None:
+        """Late initialisation of the whole wrapped layer: the (frozen) base as well - a model built on the meta device and
+        materialised with ``to_empty`` has no valid base weights until they are initialised here or loaded."""
+        if self.lora_A.weight.is_meta:
+            return
+        self.base.reset_parameters()
+        self._reset_adapters()
+
+    def _reset_adapters(self) -> None:
         if self.lora_A.weight.is_meta:
             return
         self.lora_A.reset_parameters()

@@ -316,3 +316,34 @@ def test_throughput_meter_reports_tokens_per_second_and_mfu():
         assert abs(entry["tokens_per_second"] - 1000 / entry["step_seconds"]) < 1e-6
         assert abs(entry["mfu"] - 1000 * flops / entry["step_seconds"] / 2e12) < 1e-9
     assert {name for name, _ in run.logged} == {"throughput/tokens_per_second", "throughput/step_seconds", "throughput/mfu"}
+
+
+def test_lora_layers_initialise_their_frozen_base_after_meta_construction():
+    """A stage is built on the meta device, adapters are injected there, and only then is memory allocated: the late
+    initialisation has to cover the frozen base weights too (they stay garbage otherwise when no checkpoint is loaded)."""
+    from d9d_b200.module.block.moe import GroupedLinear
+    from d9d_b200.peft import inject_peft_and_freeze
+    from d9d_b200.peft.all import peft_method_from_config
+    from d9d_b200.peft.lora.config import LoRAConfig
+
+    class Tiny(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.proj = nn.Linear(8, 8, bias=False)
+            self.experts = GroupedLinear(2, 8, 8)
+
+        def reset_parameters(self):
+            self.proj.reset_parameters()
+            self.experts.reset_parameters()
+
+    with torch.device("meta"):
+        model = Tiny()
+        inject_peft_and_freeze(peft_method_from_config(LoRAConfig.model_validate(
+            {"kind": "lora", "module_name_pattern": "proj|experts", "params": {"r": 2, "alpha": 4, "dropout": 0.0}})), model)
+    model.to_empty(device="cpu")
+    with torch.no_grad():
+        for p in model.parameters():
+            p.fill_(float("nan"))  # what uninitialised memory may look like
+        model.reset_parameters()
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+    assert float(model.proj.lora_B.weight.abs().sum()) == 0.0 and float(model.proj.base.weight.abs().sum()) > 0.0
