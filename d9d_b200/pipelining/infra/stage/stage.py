@@ -27,6 +27,18 @@ class _DeferredFull:
     inputs: list[torch.Tensor]
 
 
+class _AlreadyDone:
+    """Placeholder for a weight pass whose work was done together with the input pass."""
+
+
+def _manages_parameter_lifetime(module: nn.Module) -> bool:
+    """FSDP frees the unsharded parameters and reduce-scatters their gradients from hooks around *complete* backward
+    passes; replaying part of the graph later would read freed storage and bypass the reduction."""
+    from torch.distributed.fsdp import FSDPModule
+
+    return any(isinstance(m, FSDPModule) for m in module.modules())
+
+
 class PipelineStage:
     """One model chunk of the pipeline: runs forward / (split) backward per microbatch and owns its boundaries.
 
@@ -44,7 +56,8 @@ class PipelineStage:
         self._bwd_in: BoundaryChannel | None = None  # output gradients from the next stage
         self._forward: dict[int, _ForwardRecord] = {}
         self._input_grads: dict[int, dict[str, torch.Tensor | None]] = {}
-        self._deferred: dict[int, DeferredWeightBackward | _DeferredFull] = {}
+        self._deferred: dict[int, DeferredWeightBackward | _DeferredFull | _AlreadyDone] = {}
+        self._can_split_backward: bool | None = None
 
     @property
     def info(self) -> PipelineStageInfo:
@@ -151,7 +164,16 @@ class PipelineStage:
         in_keys = sorted(record.inputs)
         in_list = [record.inputs[k] for k in in_keys]
 
-        if full_backward:
+        if self._can_split_backward is None:
+            self._can_split_backward = not _manages_parameter_lifetime(self._module)
+        if not full_backward and not self._can_split_backward:
+            # FSDP-sharded stage: the input slot of a zero-bubble schedule runs the whole backward (correct, merely
+            # without the bubble-filling benefit on this stage); the weight slot becomes a no-op
+            grads = backward_full(outs, out_grads, in_list)
+            self._deferred[microbatch_index] = _AlreadyDone()
+            if not self._info.is_current_stage_first:
+                self._input_grads[microbatch_index] = dict(zip(in_keys, grads, strict=True))
+        elif full_backward:
             grads = backward_full(outs, out_grads, in_list)
             if not self._info.is_current_stage_first:
                 self._input_grads[microbatch_index] = dict(zip(in_keys, grads, strict=True))
@@ -173,6 +195,8 @@ class PipelineStage:
         if microbatch_index not in self._deferred:
             raise ValueError(f"S{self._info.current_stage}W{microbatch_index} - weight backward with no input backward before")
         deferred = self._deferred.pop(microbatch_index)
+        if isinstance(deferred, _AlreadyDone):
+            return
         if isinstance(deferred, _DeferredFull):
             backward_full(deferred.outputs, deferred.output_grads, deferred.inputs)
         else:

@@ -186,7 +186,9 @@ def test_asynchronous_checkpoints_and_interrupted_saves(tmp_path):
                                                ({"context_parallel_replicate": 2, "pipeline_parallel": 2}, 4),
                                                ({"tensor_parallel": 2}, 2),
                                                ({"tensor_parallel": 2, "context_parallel_replicate": 2}, 4),
-                                               ({"tensor_parallel": 2, "context_parallel_shard": 2}, 4)])
+                                               ({"tensor_parallel": 2, "context_parallel_shard": 2}, 4),
+                                               # FSDP-sharded stages under a zero-bubble schedule (whole backward in the I slot)
+                                               ({"pipeline_parallel": 2, "context_parallel_shard": 2, "zero_bubble": True}, 4)])
 def test_sequence_sharded_training_reproduces_the_single_process_run(tmp_path, mesh_kwargs, world):
     """Ranks of a context- / tensor-parallel group read the same samples and split every sequence (and, for tensor
     parallelism, the heads and MLP columns): the loss trajectory must equal the single-process one (same batches, same
@@ -195,7 +197,10 @@ def test_sequence_sharded_training_reproduces_the_single_process_run(tmp_path, m
     single = _make_trainer(tmp_path / "s", total_batch=8, micro=2, samples=32, source=tmp_path / "weights")
     single.train()
     ref, _ = _read_losses(tmp_path / "s")
-    schedule = {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": False} if "pipeline_parallel" in mesh_kwargs else {"schedule": "gpipe"}
+    mesh_kwargs = dict(mesh_kwargs)
+    zero_bubble = mesh_kwargs.pop("zero_bubble", False)
+    schedule = ({"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": zero_bubble} if "pipeline_parallel" in mesh_kwargs
+                else {"schedule": "gpipe"})
     run_distributed(_dist_worker, world, str(tmp_path / "cp"), mesh_kwargs, schedule, False, str(tmp_path / "weights"))
     got, _ = _read_losses(tmp_path / "cp")
     assert sorted(ref) == sorted(got)
@@ -219,3 +224,63 @@ def test_folding_the_gradient_scale_into_the_optimizer_changes_nothing(tmp_path)
     b = torch.cat([finals[1][k].float().flatten() for k in finals[0]])
     assert float((a != b).float().mean()) < 0.02
     torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2)
+
+
+def _resume_worker(rank, world, tmp, mesh_kwargs, schedule, moe, stop_at):
+    """Train with a checkpoint every 2 steps; ``stop_at``: simulate a crash right before that step."""
+    from pathlib import Path
+
+    from d9d_b200.core.dist_context import DeviceMeshParameters
+    from d9d_b200.loop.event.catalogue.train import EVENT_TRAIN_STEP_PRE
+
+    class _Crash(Exception):
+        pass
+
+    tmp = Path(tmp)
+    trainer = _make_trainer(tmp, mesh=DeviceMeshParameters(**mesh_kwargs), moe=moe, schedule=schedule, total_batch=8, micro=2, log=True,
+                            samples=64, ckpt_period=2, source=tmp.parent / "weights")
+    if stop_at is not None:
+        def crash(ctx):
+            if ctx.stepper.current_step == stop_at:
+                torch.distributed.barrier()  # let every rank finish the collectives of the previous step before anyone leaves
+                raise _Crash
+
+        trainer.state.event_bus.subscribe(EVENT_TRAIN_STEP_PRE, crash)
+        try:
+            trainer.train()
+        except _Crash:
+            return
+        raise AssertionError("the simulated crash did not happen")
+    trainer.train()
+    trainer.export(tmp / "export", load_checkpoint=False)
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("mesh_kwargs,schedule,moe", [
+    ({"pipeline_parallel": 2, "data_parallel_shard": 2}, {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": True}, False),
+    ({"data_parallel_replicate": 2, "data_parallel_shard": 2, "expert_parallel": 2}, {"schedule": "gpipe"}, True),
+])
+def test_distributed_resume_is_exact(tmp_path, mesh_kwargs, schedule, moe):
+    """Kill a 4-rank job (pipeline x FSDP, or HSDP x expert parallel) after step 5, restart it in fresh processes: sharded
+    DCP checkpoints, per-rank data-loader positions and per-stage optimizer states must bring it back onto the exact
+    trajectory of an uninterrupted job."""
+    from d9d_b200.model_state.io import read_model_state
+    from d9d_b200.model_state.mapper.adapters import identity_mapper_from_module
+
+    init = _make_trainer(tmp_path / "init", moe=moe, log=False)
+    init.export(tmp_path / "weights", load_checkpoint=False)
+    run_distributed(_resume_worker, 4, str(tmp_path / "full"), mesh_kwargs, schedule, moe, None)
+    run_distributed(_resume_worker, 4, str(tmp_path / "cut"), mesh_kwargs, schedule, moe, 5)
+    assert sorted(p.name for p in (tmp_path / "cut" / "ckpt" / "t").iterdir()) == ["save-2", "save-4"]
+    run_distributed(_resume_worker, 4, str(tmp_path / "cut"), mesh_kwargs, schedule, moe, None)
+
+    full_losses, _ = _read_losses(tmp_path / "full")
+    cut_losses, _ = _read_losses(tmp_path / "cut")
+    for step in range(4, 8):  # steps replayed after the restart
+        assert cut_losses[step] == full_losses[step], (step, cut_losses[step], full_losses[step])
+    mapper = identity_mapper_from_module(init.state.tracked_modules.modules[0])
+    want = dict(read_model_state(tmp_path / "full" / "export", mapper, "cpu", show_progress=False))
+    got = dict(read_model_state(tmp_path / "cut" / "export", mapper, "cpu", show_progress=False))
+    assert want.keys() == got.keys()
+    for name in want:
+        torch.testing.assert_close(got[name], want[name], rtol=0, atol=0, msg=lambda m, name=name: f"{name}: {m}")
