@@ -2,7 +2,7 @@
 
 from __future__ import annotations
 
-from collections.abc import Sequence
+from collections.abc import Callable, Sequence
 
 import torch
 
@@ -72,6 +72,21 @@ class ModelStateMapperShard(ModelStateMapper):
     def __init__(self, sub_mapper: ModelStateMapper, total_shards: int, current_shard: int):
         ordered = sorted(sub_mapper.state_dependency_groups(), key=lambda g: sorted(g.inputs))
         self._groups = frozenset(g for i, g in enumerate(ordered) if i % total_shards == current_shard)
+        self._sub = sub_mapper
+
+    def state_dependency_groups(self) -> frozenset[StateGroup]:
+        return self._groups
+
+    def apply(self, group: dict[str, torch.Tensor]) -> dict[str, torch.Tensor]:
+        return self._sub.apply(group)
+
+
+class ModelStateMapperSelectGroups(ModelStateMapper):
+    """Keep the dependency groups accepted by ``predicate`` - e.g. the part of a whole-model mapper that concerns the
+    parameters of one pipeline stage."""
+
+    def __init__(self, sub_mapper: ModelStateMapper, predicate: Callable[[StateGroup], bool]):
+        self._groups = frozenset(g for g in sub_mapper.state_dependency_groups() if predicate(g))
         self._sub = sub_mapper
 
     def state_dependency_groups(self) -> frozenset[StateGroup]:
@@ -183,6 +198,7 @@ class ModelStateMapperSequential(ModelStateMapper):
 __all__ = [
     "ModelStateMapperParallel",
     "ModelStateMapperPrefixScope",
+    "ModelStateMapperSelectGroups",
     "ModelStateMapperSequential",
     "ModelStateMapperShard",
     "filter_empty_mappers",

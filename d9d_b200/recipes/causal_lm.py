@@ -6,6 +6,8 @@ provider, SFT task), packaged so that the example script, the benchmark and the 
 
 from __future__ import annotations
 
+from typing import Literal
+
 import torch
 from pydantic import BaseModel
 
@@ -34,10 +36,16 @@ from d9d_b200.loop.control import (
     UpdateMetricsContext,
 )
 from d9d_b200.metric.impl.aggregation import SumMetric
-from d9d_b200.model_state.mapper.adapters import identity_mapper_from_module
+from d9d_b200.model_state.mapper.adapters import identity_mapper_from_module, restrict_mapper_to_module
 from d9d_b200.module.block.head import LM_IGNORE_INDEX
 from d9d_b200.module.block.hidden_states_aggregator import HiddenStatesAggregationMode
-from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM, Qwen3MoEForCausalLMParameters
+from d9d_b200.module.model.qwen3_moe import (
+    Qwen3MoEExpertsFormat,
+    Qwen3MoEForCausalLM,
+    Qwen3MoEForCausalLMParameters,
+    mapper_from_huggingface_qwen3_moe_for_causal_lm,
+    mapper_to_huggingface_qwen3_moe_for_causal_lm,
+)
 from d9d_b200.module.parallelism.model.qwen3_moe import parallelize_qwen3_moe_for_causal_lm
 
 
@@ -67,6 +75,11 @@ class Qwen3MoEModelProviderConfig(BaseModel):
     model: Qwen3MoEForCausalLMParameters
     checkpointing: bool = False
     dtype: str = "bfloat16"
+    # layout of ``model_stage_factory.source_checkpoint`` and of ``Trainer.export``: this framework's own parameter names
+    # or HuggingFace ``Qwen3MoeForCausalLM`` (``experts_format``: fused 3-D expert tensors of transformers 5, or one
+    # ``nn.Linear`` per expert of transformers 4)
+    checkpoint_format: Literal["native", "huggingface"] = "native"
+    experts_format: Qwen3MoEExpertsFormat = Qwen3MoEExpertsFormat.FUSED
 
 
 class Qwen3MoEModelProvider(ModelProvider):
@@ -76,12 +89,20 @@ class Qwen3MoEModelProvider(ModelProvider):
     def initialize_model_stage(self, context: InitializeModelStageContext) -> InitializeModelStageResult:
         model = Qwen3MoEForCausalLM(self._config.model, context.stage, HiddenStatesAggregationMode.no,
                                     self._config.checkpointing).to(getattr(torch, self._config.dtype))
+        if self._config.checkpoint_format == "huggingface":
+            # the whole-model mapper, cut down to the parameters this pipeline stage holds
+            whole = mapper_from_huggingface_qwen3_moe_for_causal_lm(self._config.model, self._config.experts_format)
+            return InitializeModelStageResult(model=model, state_mapper=restrict_mapper_to_module(whole, model, module_keys_are="outputs"))
         return InitializeModelStageResult(model=model, state_mapper=identity_mapper_from_module(model))
 
     def parallelize_model_stage(self, context: ParallelizeModelStageContext) -> None:
         parallelize_qwen3_moe_for_causal_lm(context.dist_context, context.model, context.stage)
 
     def prepare_export_model_stage(self, context: PrepareExportModelStageContext) -> PrepareExportModelStageResult:
+        if self._config.checkpoint_format == "huggingface":
+            whole = mapper_to_huggingface_qwen3_moe_for_causal_lm(self._config.model, self._config.experts_format)
+            return PrepareExportModelStageResult(state_mapper=restrict_mapper_to_module(whole, context.model,
+                                                                                        module_keys_are="inputs"))
         return PrepareExportModelStageResult(state_mapper=identity_mapper_from_module(context.model))
 
     def dump_hparams(self) -> ScalarTree:

@@ -62,15 +62,15 @@ class SyntheticDataProvider(DatasetProvider):
 
 
 class LMProvider(ModelProvider):
-    def __init__(self, params, moe: bool = False, dtype: torch.dtype = torch.float32):
-        self._params, self._moe, self._dtype = params, moe, dtype
+    def __init__(self, params, moe: bool = False, dtype: torch.dtype = torch.float32, activation_checkpointing: bool = False):
+        self._params, self._moe, self._dtype, self._recompute = params, moe, dtype, activation_checkpointing
 
     def initialize_model_stage(self, context: InitializeModelStageContext) -> InitializeModelStageResult:
         if self._moe:
             from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM as Cls
         else:
             from d9d_b200.module.model.qwen3_dense import Qwen3DenseForCausalLM as Cls
-        model = Cls(self._params, context.stage, HiddenStatesAggregationMode.no, False).to(self._dtype)
+        model = Cls(self._params, context.stage, HiddenStatesAggregationMode.no, self._recompute).to(self._dtype)
         return InitializeModelStageResult(model=model, state_mapper=identity_mapper_from_module(model))
 
     def parallelize_model_stage(self, context: ParallelizeModelStageContext) -> None:

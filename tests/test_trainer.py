@@ -10,7 +10,7 @@ from tests.helpers_train import LMProvider, SFTTask, SyntheticDataProvider, dens
 
 
 def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable", total_batch=8, micro=4, log=True, samples=64,
-                  optimizer=None, fold_scaling=True, dtype=torch.float32, source=None, async_save=False):
+                  optimizer=None, fold_scaling=True, dtype=torch.float32, source=None, async_save=False, recompute=False, layers=2):
     from d9d_b200.core.dist_context import DeviceMeshParameters
     from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
     from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
@@ -28,7 +28,8 @@ def _make_trainer(tmp, mesh=None, moe=False, schedule=None, ckpt_period="disable
                                                              ckpt_period=ckpt_period, log_dir=(tmp / "logs") if log else None,
                                                              source=source)),
         task_provider=lambda ctx: SFTTask(ctx.dist_context),
-        model_provider=LMProvider(moe_params() if moe else dense_params(), moe=moe, dtype=dtype),
+        model_provider=LMProvider(moe_params(layers) if moe else dense_params(layers), moe=moe, dtype=dtype,
+                                  activation_checkpointing=recompute),
         data_provider=SyntheticDataProvider(num_samples=samples),
         optimizer_provider=AutoOptimizerProvider(optimizer or AdamWOptimizerConfig(lr=3e-3, weight_decay=0.0)),
         lr_scheduler_provider=AutoLRSchedulerProvider(sched),
@@ -101,14 +102,14 @@ def test_resume_is_exact(tmp_path):
         torch.testing.assert_close(v, ref_state[k], rtol=0, atol=0)
 
 
-def _dist_worker(rank, world, tmp, mesh_kwargs, schedule, moe, source=None):
+def _dist_worker(rank, world, tmp, mesh_kwargs, schedule, moe, source=None, recompute=False, layers=2):
     from pathlib import Path
 
     from d9d_b200.core.dist_context import DeviceMeshParameters
 
     tmp = Path(tmp)
     trainer = _make_trainer(tmp, mesh=DeviceMeshParameters(**mesh_kwargs), moe=moe, schedule=schedule, total_batch=8, micro=2,
-                            log=True, samples=32, source=source)
+                            log=True, samples=32, source=source, recompute=recompute, layers=layers)
     trainer.train()
     trainer.export(tmp / "export", load_checkpoint=False)
     if rank == 0:
@@ -284,3 +285,27 @@ def test_distributed_resume_is_exact(tmp_path, mesh_kwargs, schedule, moe):
     assert want.keys() == got.keys()
     for name in want:
         torch.testing.assert_close(got[name], want[name], rtol=0, atol=0, msg=lambda m, name=name: f"{name}: {m}")
+
+
+@pytest.mark.dist
+@pytest.mark.parametrize("mesh_kwargs,schedule,moe", [
+    # expert-parallel all-to-alls inside the split backward of a zero-bubble schedule, activation recomputation
+    ({"pipeline_parallel": 2, "context_parallel_replicate": 2, "expert_parallel": 2},
+     {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": True}, True),
+    # interleaved (two stages per rank) schedule over FSDP-sharded stages, activation recomputation
+    ({"pipeline_parallel": 2, "context_parallel_shard": 2}, {"schedule": "looped_bfs", "num_stages_per_rank": 2}, False),
+    ({"pipeline_parallel": 2, "context_parallel_replicate": 2, "expert_parallel": 2}, {"schedule": "dual_pipe_v"}, True),
+])
+def test_pipeline_combinations_reproduce_the_single_process_run(tmp_path, mesh_kwargs, schedule, moe):
+    """Pipeline schedules combined with expert parallelism / FSDP / activation recomputation on meshes whose ranks all read the
+    same samples (context parallel), so the loss trajectory can be compared with the single-process job step by step."""
+    layers = 4  # two stages per rank on two pipeline ranks need four layers
+    _make_trainer(tmp_path / "init", moe=moe, log=False, layers=layers).export(tmp_path / "weights", load_checkpoint=False)
+    single = _make_trainer(tmp_path / "s", moe=moe, total_batch=8, micro=2, samples=32, source=tmp_path / "weights", layers=layers)
+    single.train()
+    ref, _ = _read_losses(tmp_path / "s")
+    run_distributed(_dist_worker, 4, str(tmp_path / "d"), mesh_kwargs, schedule, moe, str(tmp_path / "weights"), True, layers)
+    got, _ = _read_losses(tmp_path / "d")
+    assert sorted(ref) == sorted(got)
+    for step in ref:
+        assert abs(ref[step] - got[step]) < 2e-3 * max(1.0, abs(ref[step])), (step, ref[step], got[step])
