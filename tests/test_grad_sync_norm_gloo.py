@@ -46,15 +46,24 @@ def _backward_rank_valued(params, value: float):
     loss.backward()
 
 
-def _sync_worker(rank, world_size, param_dtype, grad_dtype):
+def _sync_worker(rank, world_size, dtype_pairs):
     import torch.distributed as dist
     from torch.distributed.device_mesh import init_device_mesh
+
+    dist.init_process_group("gloo")
+    mesh = init_device_mesh("cpu", (2, 2), mesh_dim_names=("dp_replicate", "dp_shard"))
+    for param_dtype, grad_dtype in dtype_pairs:
+        try:
+            _check_sync(rank, mesh, param_dtype, grad_dtype)
+        except AssertionError as exc:
+            raise AssertionError(f"[param {param_dtype}, grad {grad_dtype}] {exc}") from exc
+
+
+def _check_sync(rank, mesh, param_dtype, grad_dtype):
     from torch.distributed.tensor import DTensor
 
     from d9d_b200.internals.grad_sync import GradientSynchronizer
 
-    dist.init_process_group("gloo")
-    mesh = init_device_mesh("cpu", (2, 2), mesh_dim_names=("dp_replicate", "dp_shard"))
     params = _make_params(mesh, param_dtype, grad_dtype)
     plist = list(params.values())
     sync = GradientSynchronizer([plist], bucket_size_mb=1, require_accumulations=2)
@@ -95,10 +104,8 @@ def _sync_worker(rank, world_size, param_dtype, grad_dtype):
     assert torch.all(local_grad(params["replicated"]) == 1.0)
 
 
-@pytest.mark.parametrize("param_dtype,grad_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
-                                                    (torch.bfloat16, torch.bfloat16)])
-def test_gradient_synchronizer_sums_exactly(param_dtype, grad_dtype):
-    run_distributed(_sync_worker, 4, param_dtype, grad_dtype)
+def test_gradient_synchronizer_sums_exactly():
+    run_distributed(_sync_worker, 4, [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
 
 
 def test_bucket_splitting_respects_the_byte_budget():
@@ -121,15 +128,24 @@ def test_bucket_splitting_respects_the_byte_budget():
 
 
 # ------------------------------------------------------------------------------------------------ norms
-def _norm_worker(rank, world_size, norm_type):
+def _norm_worker(rank, world_size, norm_types):
     import torch.distributed as dist
     from torch.distributed.device_mesh import init_device_mesh
+
+    dist.init_process_group("gloo")
+    mesh = init_device_mesh("cpu", (2, 2), mesh_dim_names=("dp_replicate", "dp_shard"))
+    for norm_type in norm_types:
+        try:
+            _check_norm(mesh, norm_type)
+        except AssertionError as exc:
+            raise AssertionError(f"[norm {norm_type}] {exc}") from exc
+
+
+def _check_norm(mesh, norm_type):
     from torch.distributed.tensor import DTensor, Replicate, Shard
 
     from d9d_b200.internals.grad_norm import clip_grad_norm_distributed_, group_parameters_for_norm
 
-    dist.init_process_group("gloo")
-    mesh = init_device_mesh("cpu", (2, 2), mesh_dim_names=("dp_replicate", "dp_shard"))
     torch.manual_seed(0)
     full = {"a": torch.randn(8, 6), "b": torch.randn(4, 4), "c": torch.randn(10)}
 
@@ -173,6 +189,5 @@ def _norm_worker(rank, world_size, norm_type):
     assert math.isclose(float(pending) * float(expected * scale), 1e-3, rel_tol=1e-3)  # ... the scalar carries the clip
 
 
-@pytest.mark.parametrize("norm_type", [2.0, 1.0, math.inf])
-def test_distributed_norm_matches_gathered_clip(norm_type):
-    run_distributed(_norm_worker, 4, norm_type)
+def test_distributed_norm_matches_gathered_clip():
+    run_distributed(_norm_worker, 4, [2.0, 1.0, math.inf])

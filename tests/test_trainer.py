@@ -182,31 +182,49 @@ def test_asynchronous_checkpoints_and_interrupted_saves(tmp_path):
     assert sorted(p.name for p in (tmp_path / "dist" / "ckpt" / "t").iterdir()) == ["save-2", "save-4"]
 
 
+def _jobs_worker(rank, world, jobs):
+    """Several training jobs over one set of processes (spawning processes dominates the cost of these tests)."""
+    for job in jobs:
+        _dist_worker(rank, world, *job)
+
+
+def _assert_same_trajectory(reference_dir, job_dir, label):
+    ref, _ = _read_losses(reference_dir)
+    got, _ = _read_losses(job_dir)
+    assert sorted(ref) == sorted(got), label
+    for step in ref:
+        assert abs(ref[step] - got[step]) < 2e-3 * max(1.0, abs(ref[step])), (label, step, ref[step], got[step])
+
+
+_SEQUENCE_SHARDED = {
+    2: [{"context_parallel_shard": 2}, {"tensor_parallel": 2}],
+    4: [{"context_parallel_replicate": 2, "pipeline_parallel": 2},
+        {"tensor_parallel": 2, "context_parallel_replicate": 2},
+        {"tensor_parallel": 2, "context_parallel_shard": 2},
+        # FSDP-sharded stages under a zero-bubble schedule (whole backward in the I slot)
+        {"pipeline_parallel": 2, "context_parallel_shard": 2, "zero_bubble": True}],
+}
+
+
 @pytest.mark.dist
-@pytest.mark.parametrize("mesh_kwargs,world", [({"context_parallel_shard": 2}, 2),
-                                               ({"context_parallel_replicate": 2, "pipeline_parallel": 2}, 4),
-                                               ({"tensor_parallel": 2}, 2),
-                                               ({"tensor_parallel": 2, "context_parallel_replicate": 2}, 4),
-                                               ({"tensor_parallel": 2, "context_parallel_shard": 2}, 4),
-                                               # FSDP-sharded stages under a zero-bubble schedule (whole backward in the I slot)
-                                               ({"pipeline_parallel": 2, "context_parallel_shard": 2, "zero_bubble": True}, 4)])
-def test_sequence_sharded_training_reproduces_the_single_process_run(tmp_path, mesh_kwargs, world):
+@pytest.mark.parametrize("world", [2, 4])
+def test_sequence_sharded_training_reproduces_the_single_process_run(tmp_path, world):
     """Ranks of a context- / tensor-parallel group read the same samples and split every sequence (and, for tensor
     parallelism, the heads and MLP columns): the loss trajectory must equal the single-process one (same batches, same
     maths - only the reduction order differs)."""
     _make_trainer(tmp_path / "init", log=False).export(tmp_path / "weights", load_checkpoint=False)  # shared initial weights
     single = _make_trainer(tmp_path / "s", total_batch=8, micro=2, samples=32, source=tmp_path / "weights")
     single.train()
-    ref, _ = _read_losses(tmp_path / "s")
-    mesh_kwargs = dict(mesh_kwargs)
-    zero_bubble = mesh_kwargs.pop("zero_bubble", False)
-    schedule = ({"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": zero_bubble} if "pipeline_parallel" in mesh_kwargs
-                else {"schedule": "gpipe"})
-    run_distributed(_dist_worker, world, str(tmp_path / "cp"), mesh_kwargs, schedule, False, str(tmp_path / "weights"))
-    got, _ = _read_losses(tmp_path / "cp")
-    assert sorted(ref) == sorted(got)
-    for step in ref:
-        assert abs(ref[step] - got[step]) < 2e-3 * max(1.0, abs(ref[step])), (step, ref[step], got[step])
+    jobs = []
+    for i, mesh_kwargs in enumerate(_SEQUENCE_SHARDED[world]):
+        mesh_kwargs = dict(mesh_kwargs)
+        zero_bubble = mesh_kwargs.pop("zero_bubble", False)
+        schedule = ({"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": zero_bubble} if "pipeline_parallel" in mesh_kwargs
+                    else {"schedule": "gpipe"})
+        jobs.append((str(tmp_path / f"job{i}"), mesh_kwargs, schedule, False, str(tmp_path / "weights")))
+    run_distributed(_jobs_worker, world, jobs)
+    for i, mesh_kwargs in enumerate(_SEQUENCE_SHARDED[world]):
+        _assert_same_trajectory(tmp_path / "s", tmp_path / f"job{i}", mesh_kwargs)
 
 
 def test_folding_the_gradient_scale_into_the_optimizer_changes_nothing(tmp_path):
@@ -287,25 +305,27 @@ def test_distributed_resume_is_exact(tmp_path, mesh_kwargs, schedule, moe):
         torch.testing.assert_close(got[name], want[name], rtol=0, atol=0, msg=lambda m, name=name: f"{name}: {m}")
 
 
-@pytest.mark.dist
-@pytest.mark.parametrize("mesh_kwargs,schedule,moe", [
+_PIPELINE_COMBINATIONS = [
     # expert-parallel all-to-alls inside the split backward of a zero-bubble schedule, activation recomputation
     ({"pipeline_parallel": 2, "context_parallel_replicate": 2, "expert_parallel": 2},
      {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": True}, True),
     # interleaved (two stages per rank) schedule over FSDP-sharded stages, activation recomputation
     ({"pipeline_parallel": 2, "context_parallel_shard": 2}, {"schedule": "looped_bfs", "num_stages_per_rank": 2}, False),
     ({"pipeline_parallel": 2, "context_parallel_replicate": 2, "expert_parallel": 2}, {"schedule": "dual_pipe_v"}, True),
-])
-def test_pipeline_combinations_reproduce_the_single_process_run(tmp_path, mesh_kwargs, schedule, moe):
+]
+
+
+@pytest.mark.dist
+def test_pipeline_combinations_reproduce_the_single_process_run(tmp_path):
     """Pipeline schedules combined with expert parallelism / FSDP / activation recomputation on meshes whose ranks all read the
     same samples (context parallel), so the loss trajectory can be compared with the single-process job step by step."""
     layers = 4  # two stages per rank on two pipeline ranks need four layers
-    _make_trainer(tmp_path / "init", moe=moe, log=False, layers=layers).export(tmp_path / "weights", load_checkpoint=False)
-    single = _make_trainer(tmp_path / "s", moe=moe, total_batch=8, micro=2, samples=32, source=tmp_path / "weights", layers=layers)
-    single.train()
-    ref, _ = _read_losses(tmp_path / "s")
-    run_distributed(_dist_worker, 4, str(tmp_path / "d"), mesh_kwargs, schedule, moe, str(tmp_path / "weights"), True, layers)
-    got, _ = _read_losses(tmp_path / "d")
-    assert sorted(ref) == sorted(got)
-    for step in ref:
-        assert abs(ref[step] - got[step]) < 2e-3 * max(1.0, abs(ref[step])), (step, ref[step], got[step])
+    jobs = []
+    for moe in (False, True):
+        _make_trainer(tmp_path / f"init{moe}", moe=moe, log=False, layers=layers).export(tmp_path / f"weights{moe}", load_checkpoint=False)
+        _make_trainer(tmp_path / f"s{moe}", moe=moe, total_batch=8, micro=2, samples=32, source=tmp_path / f"weights{moe}", layers=layers).train()
+    for i, (mesh_kwargs, schedule, moe) in enumerate(_PIPELINE_COMBINATIONS):
+        jobs.append((str(tmp_path / f"job{i}"), mesh_kwargs, schedule, moe, str(tmp_path / f"weights{moe}"), True, layers))
+    run_distributed(_jobs_worker, 4, jobs)
+    for i, (mesh_kwargs, schedule, moe) in enumerate(_PIPELINE_COMBINATIONS):
+        _assert_same_trajectory(tmp_path / f"s{moe}", tmp_path / f"job{i}", (mesh_kwargs, schedule))
