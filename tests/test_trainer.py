@@ -329,3 +329,80 @@ def test_pipeline_combinations_reproduce_the_single_process_run(tmp_path):
     run_distributed(_jobs_worker, 4, jobs)
     for i, (mesh_kwargs, schedule, moe) in enumerate(_PIPELINE_COMBINATIONS):
         _assert_same_trajectory(tmp_path / f"s{moe}", tmp_path / f"job{i}", (mesh_kwargs, schedule))
+
+
+def test_resume_with_length_bucketed_data_lora_and_profiling(tmp_path):
+    """Less common knobs in one job: a length-bucketing dataset whose shuffling state must be checkpointed, LoRA with
+    adapter-only checkpoints, the profiler, no clipping, special step periods - interrupted and resumed exactly."""
+    from tests.helpers_train import LMProvider, SFTTask, dense_params, trainer_config
+
+    from d9d_b200.dataset import BufferSortedDataset, SyntheticTokenDataset, shard_dataset_data_parallel
+    from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
+    from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
+    from d9d_b200.loop.auto.auto_optimizer import AdamWOptimizerConfig
+    from d9d_b200.loop.control import InitializeDatasetResult, InitializeModelStageResult
+    from d9d_b200.loop.event.catalogue.train import EVENT_TRAIN_STEP_PRE
+    from d9d_b200.loop.run import TrainingConfigurator
+    from d9d_b200.model_state.mapper.compose import ModelStateMapperSequential
+    from d9d_b200.peft import inject_peft_and_freeze
+    from d9d_b200.peft.all import peft_method_from_config
+    from d9d_b200.peft.lora.config import LoRAConfig
+
+    class LoRAProvider(LMProvider):
+        def initialize_model_stage(self, context):
+            built = super().initialize_model_stage(context)
+            method = peft_method_from_config(LoRAConfig.model_validate(
+                {"kind": "lora", "module_name_pattern": r".*self_attn\.(q_proj|v_proj)", "params": {"r": 4, "alpha": 8, "dropout": 0.0}}))
+            redirect = inject_peft_and_freeze(method, built.model)
+            return InitializeModelStageResult(model=built.model, state_mapper=ModelStateMapperSequential([built.state_mapper, redirect]))
+
+    def data_provider(context):
+        base = SyntheticTokenDataset(64, 16, 128, seed=3, learnable=True)
+        bucketed = BufferSortedDataset(base, buffer_size=16, pack_size=4, init_seed=5)
+        return InitializeDatasetResult(dataset=shard_dataset_data_parallel(bucketed, context.dist_context), collator=SyntheticTokenDataset.collate)
+
+    def make(tmp, profiling):
+        cfg = trainer_config(tmp, total_batch=8, micro=4, ckpt_period=3, log_dir=tmp / "logs")
+        cfg.model_stage_factory.checkpoint_only_trainable_parameters = True
+        cfg.gradient_clipping.max_norm = None
+        cfg.gc.period_steps = "disable"
+        cfg.logging.period_steps = 1
+        if profiling:
+            from d9d_b200.loop.config import ProfilingConfig
+
+            cfg.profiling = ProfilingConfig(enabled=True, traces_dir=tmp / "traces", period_steps=4, warmup_steps=1, active_steps=1)
+        sched = PiecewiseConfig.model_validate({"name": "piecewise", "scheduler": {"initial_multiplier": 1.0, "phases": [
+            {"mode": "rest", "target_multiplier": 0.5, "curve": {"type": "linear"}}]}})
+        return TrainingConfigurator(
+            mesh=__import__("d9d_b200.core.dist_context", fromlist=["DeviceMeshParameters"]).DeviceMeshParameters(), parameters=cfg,
+            task_provider=lambda ctx: SFTTask(ctx.dist_context), model_provider=LoRAProvider(dense_params()), data_provider=data_provider,
+            optimizer_provider=AutoOptimizerProvider(AdamWOptimizerConfig(lr=3e-3, weight_decay=0.0)),
+            lr_scheduler_provider=AutoLRSchedulerProvider(sched)).configure()
+
+    full = make(tmp_path / "full", profiling=True)
+    full.train()
+    traces = list((tmp_path / "full" / "traces").rglob("*trace.tar.gz"))
+    assert traces and all(t.parent.name.startswith("step_") for t in traces)
+    trainable = {n for n, p in full.state.tracked_modules.modules[0].named_parameters() if p.requires_grad}
+    assert trainable and all("lora_" in n for n in trainable)
+
+    class _Stop(Exception):
+        pass
+
+    def stop(ctx):
+        if ctx.stepper.current_step == 5:
+            raise _Stop
+
+    part = make(tmp_path / "cut", profiling=False)
+    part.state.event_bus.subscribe(EVENT_TRAIN_STEP_PRE, stop)
+    with pytest.raises(_Stop):
+        part.train()
+    resumed = make(tmp_path / "cut", profiling=False)  # resumes from save-3: frozen base weights come from the deterministic init
+    resumed.train()
+    ref, _ = _read_losses(tmp_path / "full")
+    got, _ = _read_losses(tmp_path / "cut")
+    for step in range(3, 8):
+        assert got[step] == ref[step], (step, got[step], ref[step])
+    want = full.state.tracked_modules.modules[0].state_dict()
+    for k, v in resumed.state.tracked_modules.modules[0].state_dict().items():
+        torch.testing.assert_close(v, want[k], rtol=0, atol=0, msg=lambda m, k=k: f"{k}: {m}")
