@@ -91,9 +91,13 @@ class StochasticAdamW(Optimizer):
             group.update({k: v for k, v in saved.items() if k != "params"})
         self.state.clear()
         for pid, entries in saved_state.items():
+            if isinstance(pid, str) and pid.isdigit():
+                # torch.distributed.checkpoint loads tensors in place (under the original integer ids) and hands the
+                # non-tensor leaves - the step counters - back under stringified ids: merge both views
+                pid = int(pid)
             param = by_id[pid]
             device = _local(param).device
-            self.state[param] = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in entries.items()}
+            self.state[param].update({k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in entries.items()})
         self._plans.clear()
 
     @torch.no_grad()

@@ -227,6 +227,39 @@ def test_sequence_sharded_training_reproduces_the_single_process_run(tmp_path, w
         _assert_same_trajectory(tmp_path / "s", tmp_path / f"job{i}", mesh_kwargs)
 
 
+def test_resume_is_exact_with_stochastic_adamw(tmp_path):
+    """The stochastic-rounding optimizer through a DCP checkpoint: moments, the *integer* step counters (which DCP hands back
+    under stringified parameter ids) and the rounding generator must all resume, otherwise the trajectory drifts."""
+    from d9d_b200.loop.auto.auto_optimizer import StochasticAdamWOptimizerConfig
+    from d9d_b200.loop.event.catalogue.train import EVENT_TRAIN_STEP_PRE
+
+    def make(tmp):
+        return _make_trainer(tmp, ckpt_period=2, dtype=torch.bfloat16,
+                             optimizer=StochasticAdamWOptimizerConfig(lr=3e-3, weight_decay=0.01, state_dtype="float32"))
+
+    full = make(tmp_path / "full")
+    full.train()
+
+    class _Stop(Exception):
+        pass
+
+    def stop(ctx):
+        if ctx.stepper.current_step == 5:
+            raise _Stop
+
+    part = make(tmp_path / "cut")
+    part.state.event_bus.subscribe(EVENT_TRAIN_STEP_PRE, stop)
+    with pytest.raises(_Stop):
+        part.train()
+    resumed = make(tmp_path / "cut")
+    resumed.train()
+    optimizer = resumed.state.optimizer.optimizers[0]
+    assert {int(s["step"]) for s in optimizer.state.values()} == {8}
+    want = full.state.tracked_modules.modules[0].state_dict()
+    for k, v in resumed.state.tracked_modules.modules[0].state_dict().items():
+        assert torch.equal(v, want[k]), k
+
+
 def test_folding_the_gradient_scale_into_the_optimizer_changes_nothing(tmp_path):
     """1/sum(w) and the clip coefficient handed to StochasticAdamW as a device scalar == rewriting the gradients."""
     from d9d_b200.loop.auto.auto_optimizer import StochasticAdamWOptimizerConfig
