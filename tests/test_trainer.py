@@ -307,35 +307,49 @@ def _resume_worker(rank, world, tmp, mesh_kwargs, schedule, moe, stop_at):
     trainer.export(tmp / "export", load_checkpoint=False)
 
 
+_RESUME_CASES = [
+    ("pp_fsdp", {"pipeline_parallel": 2, "data_parallel_shard": 2}, {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": True}, False),
+    ("hsdp_ep", {"data_parallel_replicate": 2, "data_parallel_shard": 2, "expert_parallel": 2}, {"schedule": "gpipe"}, True),
+]
+
+
+def _resume_phase(rank, world, root, phase, stop_at):
+    """One phase (uninterrupted run / run until the crash / restart) of every case over one set of processes."""
+    from pathlib import Path
+
+    for name, mesh_kwargs, schedule, moe in _RESUME_CASES:
+        _resume_worker(rank, world, str(Path(root) / name / phase), mesh_kwargs, schedule, moe, stop_at)
+
+
 @pytest.mark.dist
-@pytest.mark.parametrize("mesh_kwargs,schedule,moe", [
-    ({"pipeline_parallel": 2, "data_parallel_shard": 2}, {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": True}, False),
-    ({"data_parallel_replicate": 2, "data_parallel_shard": 2, "expert_parallel": 2}, {"schedule": "gpipe"}, True),
-])
-def test_distributed_resume_is_exact(tmp_path, mesh_kwargs, schedule, moe):
-    """Kill a 4-rank job (pipeline x FSDP, or HSDP x expert parallel) after step 5, restart it in fresh processes: sharded
-    DCP checkpoints, per-rank data-loader positions and per-stage optimizer states must bring it back onto the exact
-    trajectory of an uninterrupted job."""
+def test_distributed_resume_is_exact(tmp_path):
+    """Kill a 4-rank job (pipeline x FSDP with a zero-bubble schedule; HSDP x expert parallel MoE) after step 5, restart it in
+    fresh processes: sharded DCP checkpoints, per-rank data-loader positions and per-stage optimizer states must bring it
+    back onto the exact trajectory of an uninterrupted job."""
     from d9d_b200.model_state.io import read_model_state
     from d9d_b200.model_state.mapper.adapters import identity_mapper_from_module
 
-    init = _make_trainer(tmp_path / "init", moe=moe, log=False)
-    init.export(tmp_path / "weights", load_checkpoint=False)
-    run_distributed(_resume_worker, 4, str(tmp_path / "full"), mesh_kwargs, schedule, moe, None)
-    run_distributed(_resume_worker, 4, str(tmp_path / "cut"), mesh_kwargs, schedule, moe, 5)
-    assert sorted(p.name for p in (tmp_path / "cut" / "ckpt" / "t").iterdir()) == ["save-2", "save-4"]
-    run_distributed(_resume_worker, 4, str(tmp_path / "cut"), mesh_kwargs, schedule, moe, None)
+    inits = {}
+    for name, _, _, moe in _RESUME_CASES:
+        inits[name] = _make_trainer(tmp_path / name / "init", moe=moe, log=False)
+        inits[name].export(tmp_path / name / "weights", load_checkpoint=False)
+    run_distributed(_resume_phase, 4, str(tmp_path), "full", None)
+    run_distributed(_resume_phase, 4, str(tmp_path), "cut", 5)
+    for name, *_ in _RESUME_CASES:
+        assert sorted(p.name for p in (tmp_path / name / "cut" / "ckpt" / "t").iterdir()) == ["save-2", "save-4"]
+    run_distributed(_resume_phase, 4, str(tmp_path), "cut", None)  # fresh processes: the restart
 
-    full_losses, _ = _read_losses(tmp_path / "full")
-    cut_losses, _ = _read_losses(tmp_path / "cut")
-    for step in range(4, 8):  # steps replayed after the restart
-        assert cut_losses[step] == full_losses[step], (step, cut_losses[step], full_losses[step])
-    mapper = identity_mapper_from_module(init.state.tracked_modules.modules[0])
-    want = dict(read_model_state(tmp_path / "full" / "export", mapper, "cpu", show_progress=False))
-    got = dict(read_model_state(tmp_path / "cut" / "export", mapper, "cpu", show_progress=False))
-    assert want.keys() == got.keys()
-    for name in want:
-        torch.testing.assert_close(got[name], want[name], rtol=0, atol=0, msg=lambda m, name=name: f"{name}: {m}")
+    for name, *_ in _RESUME_CASES:
+        full_losses, _ = _read_losses(tmp_path / name / "full")
+        cut_losses, _ = _read_losses(tmp_path / name / "cut")
+        for step in range(4, 8):  # steps replayed after the restart
+            assert cut_losses[step] == full_losses[step], (name, step, cut_losses[step], full_losses[step])
+        mapper = identity_mapper_from_module(inits[name].state.tracked_modules.modules[0])
+        want = dict(read_model_state(tmp_path / name / "full" / "export", mapper, "cpu", show_progress=False))
+        got = dict(read_model_state(tmp_path / name / "cut" / "export", mapper, "cpu", show_progress=False))
+        assert want.keys() == got.keys()
+        for key in want:
+            torch.testing.assert_close(got[key], want[key], rtol=0, atol=0, msg=lambda m, key=key: f"{name} {key}: {m}")  # noqa: B023
 
 
 _PIPELINE_COMBINATIONS = [
