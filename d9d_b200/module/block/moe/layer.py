@@ -8,7 +8,7 @@ from d9d_b200.module.base import ModuleLateInit
 
 from .communications import ExpertCommunicationHandler, NoCommunicationHandler
 from .grouped_experts import GroupedSwiGLU
-from .router import TopKRouter
+from .router import RouterParameters, TopKRouter
 from .shared_expert import SharedExpertParameters, SharedSwiGLU
 
 
@@ -19,10 +19,11 @@ class MoELayer(nn.Module, ModuleLateInit):
     """
 
     def __init__(self, hidden_dim: int, intermediate_dim_grouped: int, num_grouped_experts: int, top_k: int,
-                 router_renormalize_probabilities: bool, shared_expert: SharedExpertParameters | None = None):
+                 router_renormalize_probabilities: bool, shared_expert: SharedExpertParameters | None = None,
+                 router: RouterParameters | None = None):
         super().__init__()
         self.router = TopKRouter(dim=hidden_dim, num_experts=num_grouped_experts, top_k=top_k,
-                                 renormalize_probabilities=router_renormalize_probabilities)
+                                 renormalize_probabilities=router_renormalize_probabilities, options=router)
         self.grouped_experts = GroupedSwiGLU(hidden_dim=hidden_dim, intermediate_dim=intermediate_dim_grouped,
                                              num_experts=num_grouped_experts)
         self.shared_expert = SharedSwiGLU(hidden_size=hidden_dim, params=shared_expert) if shared_expert is not None else None

@@ -26,5 +26,6 @@ class DeepseekV2Layer(PreNormDecoderLayer):
                       if params.num_shared_experts > 0 else None)
             mlp = MoELayer(hidden_dim=params.hidden_size, intermediate_dim_grouped=params.moe_intermediate_size,
                            num_grouped_experts=params.num_experts, top_k=params.experts_top_k,
-                           router_renormalize_probabilities=params.router_renormalize_probabilities, shared_expert=shared)
+                           router_renormalize_probabilities=params.router_renormalize_probabilities, shared_expert=shared,
+                           router=params.router)
         super().__init__(attention, mlp, params.hidden_size, params.rms_norm_eps)

@@ -30,7 +30,8 @@ def _feed_forward(layer: DeepseekV2LayerParameters, index: int, experts_format: 
     else:
         raise ValueError(f"Unsupported experts format {experts_format}")
     shared = hf.shared_expert_rules() if layer.num_shared_experts > 0 else ()
-    return (hf.Renamed("mlp.gate.weight", "mlp.router.gate.weight"), experts, *shared)
+    bias = (hf.Renamed("mlp.gate.e_score_correction_bias", "mlp.router.expert_bias"),) if layer.router.enable_expert_bias else ()
+    return (hf.Renamed("mlp.gate.weight", "mlp.router.gate.weight"), *bias, experts, *shared)
 
 
 def _backbone(params: DeepseekV2Parameters, experts_format: hf.ExpertsFormat) -> tuple[hf.Rule, ...]:

@@ -1,8 +1,10 @@
-"""Hyper-parameters of the DeepSeek-V2 family: multi-head latent attention, dense first layers, then MoE layers with
-always-on shared experts (classes generated from the field set below by ``module/model/_params.py``)."""
+"""Hyper-parameters of the DeepSeek-V2 / V3 family: multi-head latent attention, dense first layers, then MoE layers with
+always-on shared experts; ``router`` selects V3's sigmoid / group-limited / bias-corrected routing (classes generated from
+the field set below by ``module/model/_params.py``)."""
 
 from pydantic import BaseModel, NonNegativeInt, PositiveInt, model_validator
 
+from d9d_b200.module.block.moe.router import RouterParameters
 from d9d_b200.module.model._params import family_parameters
 
 
@@ -24,6 +26,8 @@ class LatentMoELayerFields(BaseModel):
     experts_top_k: PositiveInt
     num_shared_experts: NonNegativeInt
     router_renormalize_probabilities: bool = False
+    # DeepSeek-V3 routing: sigmoid scores, selection bias, group-limited top-k, weight scaling (defaults = DeepSeek-V2 greedy)
+    router: RouterParameters = RouterParameters()
 
     @model_validator(mode="after")
     def _check(self):  # noqa: ANN202

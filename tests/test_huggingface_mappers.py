@@ -338,3 +338,45 @@ def test_qwen3_5_hybrid_matches_transformers_and_round_trips():
     assert exported.keys() == hf_state.keys()
     for k in hf_state:
         torch.testing.assert_close(exported[k], hf_state[k], rtol=0, atol=0)
+
+
+def test_deepseek_v3_routing_matches_transformers():
+    """Sigmoid scores + selection bias + group-limited top-k + weight scaling, latent attention with a low-rank query, vs
+    ``DeepseekV3ForCausalLM``."""
+    transformers = pytest.importorskip("transformers")
+    from d9d_b200.module.model.deepseek_v3 import (DeepseekV3ForCausalLM, DeepseekV3ForCausalLMParameters, DeepseekV3LayerParameters,
+                                                   DeepseekV3Parameters, deepseek_v3_router, mapper_from_huggingface_deepseek_v3_for_causal_lm,
+                                                   mapper_to_huggingface_deepseek_v3_for_causal_lm)
+
+    cfg = transformers.DeepseekV3Config(
+        vocab_size=96, hidden_size=32, intermediate_size=48, moe_intermediate_size=16, num_hidden_layers=3, num_attention_heads=4,
+        num_key_value_heads=4, first_k_dense_replace=1, kv_lora_rank=16, q_lora_rank=12, n_routed_experts=8, n_shared_experts=1,
+        qk_nope_head_dim=8, qk_rope_head_dim=4, v_head_dim=8, num_experts_per_tok=3, n_group=4, topk_group=2, norm_topk_prob=True,
+        routed_scaling_factor=2.5, rms_norm_eps=1e-6, rope_theta=10000.0, max_position_embeddings=64, tie_word_embeddings=False,
+        attention_bias=False)
+    torch.manual_seed(0)
+    hf_model = transformers.DeepseekV3ForCausalLM(cfg).eval()
+    with torch.no_grad():
+        for name, buf in hf_model.named_buffers():
+            if name.endswith("e_score_correction_bias"):
+                buf.copy_(torch.randn_like(buf) * 0.05)  # make the selection bias matter
+    p = DeepseekV3ForCausalLMParameters(model=DeepseekV3Parameters(
+        layer=DeepseekV3LayerParameters(hidden_size=32, rms_norm_eps=1e-6, num_attention_heads=4, qk_nope_head_dim=8, qk_rope_head_dim=4,
+                                        v_head_dim=8, kv_lora_rank=16, q_lora_rank=12, intermediate_size=48, first_k_dense_replace=1,
+                                        moe_intermediate_size=16, num_experts=8, experts_top_k=3, num_shared_experts=1,
+                                        router_renormalize_probabilities=True,
+                                        router=deepseek_v3_router(n_group=4, topk_group=2, routed_scaling_factor=2.5)),
+        num_hidden_layers=3, rope_base=10000, max_position_ids=64, **VOCAB))
+    ours = DeepseekV3ForCausalLM(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    ours.reset_parameters()
+    hf_state = dict(hf_model.state_dict())
+    fmt = "fused" if any(k.endswith("experts.gate_up_proj") for k in hf_state) else "module_list"
+    _load(ours, _run(mapper_from_huggingface_deepseek_v3_for_causal_lm(p, fmt), hf_state))
+    ids, labels = torch.randint(0, 96, (2, 12)), torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        want = _per_token_nll(hf_model, ids, pos, labels)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+    exported = _run(mapper_to_huggingface_deepseek_v3_for_causal_lm(p, fmt), {k: v.detach().clone() for k, v in ours.state_dict().items()})
+    assert exported.keys() == hf_state.keys()
