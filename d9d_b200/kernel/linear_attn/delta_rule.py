@@ -19,8 +19,11 @@ import torch.nn.functional as F
 
 def _prep(q: torch.Tensor, k: torch.Tensor, use_qk_l2norm: bool, scale: float | None):
     if use_qk_l2norm:
-        q = F.normalize(q.float(), p=2, dim=-1, eps=1e-6)
-        k = F.normalize(k.float(), p=2, dim=-1, eps=1e-6)
+        # x * rsqrt(sum(x^2) + eps), the convention of the fla kernels / transformers (NOT x / max(|x|, eps): the two differ
+        # for the small q / k of freshly initialised models)
+        q, k = q.float(), k.float()
+        q = q * torch.rsqrt(q.square().sum(dim=-1, keepdim=True) + 1e-6)
+        k = k * torch.rsqrt(k.square().sum(dim=-1, keepdim=True) + 1e-6)
     scale = q.shape[-1] ** -0.5 if scale is None else scale
     return q.float() * scale, k.float()
 

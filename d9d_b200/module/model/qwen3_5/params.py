@@ -6,9 +6,10 @@ from pydantic import BaseModel, Field, PositiveInt, model_validator
 from d9d_b200.module.model._params import family_parameters
 
 
-class HybridLayerFields(BaseModel):
+class HybridMixerFields(BaseModel):
+    """Fields describing the token mixers of a hybrid layer stack (shared by the dense and the MoE variant)."""
+
     hidden_size: PositiveInt
-    intermediate_size: PositiveInt
     rms_norm_eps: float
     # full (softmax) attention layers
     num_attention_heads: PositiveInt
@@ -40,6 +41,10 @@ class HybridLayerFields(BaseModel):
 
     def uses_full_attention(self, layer_index: int) -> bool:
         return (layer_index + 1) % self.full_attention_interval == 0
+
+
+class HybridLayerFields(HybridMixerFields):
+    intermediate_size: PositiveInt
 
 
 _generated = family_parameters("Qwen3_5", HybridLayerFields, __name__)

@@ -380,3 +380,50 @@ def test_deepseek_v3_routing_matches_transformers():
     torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
     exported = _run(mapper_to_huggingface_deepseek_v3_for_causal_lm(p, fmt), {k: v.detach().clone() for k, v in ours.state_dict().items()})
     assert exported.keys() == hf_state.keys()
+
+
+def test_qwen3_5_moe_matches_transformers_and_round_trips():
+    """Hybrid token mixers + MoE feed-forward with a sigmoid-gated shared expert, vs ``Qwen3_5MoeForCausalLM``."""
+    pytest.importorskip("transformers")
+    from transformers.models.qwen3_5_moe.configuration_qwen3_5_moe import Qwen3_5MoeTextConfig
+    from transformers.models.qwen3_5_moe.modeling_qwen3_5_moe import Qwen3_5MoeForCausalLM as HFModel
+
+    from d9d_b200.module.model.qwen3_5_moe import (Qwen3_5MoEForCausalLM, Qwen3_5MoEForCausalLMParameters, Qwen3_5MoELayerParameters,
+                                                   Qwen3_5MoEParameters, mapper_from_huggingface_qwen3_5_moe_for_causal_lm,
+                                                   mapper_to_huggingface_qwen3_5_moe_for_causal_lm)
+
+    cfg = Qwen3_5MoeTextConfig(vocab_size=96, hidden_size=32, num_hidden_layers=4, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
+                               rms_norm_eps=1e-6, max_position_embeddings=64, tie_word_embeddings=False, linear_conv_kernel_dim=4,
+                               linear_key_head_dim=8, linear_value_head_dim=8, linear_num_key_heads=2, linear_num_value_heads=4,
+                               moe_intermediate_size=16, shared_expert_intermediate_size=24, num_experts_per_tok=2, num_experts=4,
+                               full_attention_interval=2,
+                               rope_parameters={"rope_type": "default", "rope_theta": 10000.0, "partial_rotary_factor": 0.25})
+    torch.manual_seed(0)
+    hf_model = HFModel(cfg).eval()
+    with torch.no_grad():
+        for name, param in hf_model.named_parameters():
+            if "norm" in name or "dt_bias" in name:
+                param.add_(torch.randn_like(param) * 0.1)
+            if name.endswith("mlp.gate.weight") or "experts" in name or "shared_expert_gate" in name:
+                param.normal_(0, 0.2)  # HF initialises the router to zeros
+    p = Qwen3_5MoEForCausalLMParameters(model=Qwen3_5MoEParameters(
+        layer=Qwen3_5MoELayerParameters(hidden_size=32, rms_norm_eps=1e-6, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
+                                        partial_rotary_factor=0.25, linear_num_key_heads=2, linear_num_value_heads=4,
+                                        linear_key_head_dim=8, linear_value_head_dim=8, linear_conv_kernel_dim=4, full_attention_interval=2,
+                                        moe_intermediate_size=16, shared_expert_intermediate_size=24, num_experts=4, experts_top_k=2),
+        num_hidden_layers=4, rope_base=10000, max_position_ids=64, **VOCAB))
+    ours = Qwen3_5MoEForCausalLM(p, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False)
+    ours.reset_parameters()
+    hf_state = dict(hf_model.state_dict())
+    fmt = "fused" if any(k.endswith("experts.gate_up_proj") for k in hf_state) else "module_list"
+    _load(ours, _run(mapper_from_huggingface_qwen3_5_moe_for_causal_lm(p, fmt), hf_state))
+    ids, labels = torch.randint(0, 96, (2, 12)), torch.randint(0, 96, (2, 12))
+    pos = torch.arange(12)[None].expand(2, -1)
+    with torch.no_grad():
+        want = _per_token_nll(hf_model, ids, pos, labels)
+        got = ours(input_ids=ids, position_ids=pos, labels=labels)["logps"]
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-4)
+    exported = _run(mapper_to_huggingface_qwen3_5_moe_for_causal_lm(p, fmt), {k: v.detach().clone() for k, v in ours.state_dict().items()})
+    assert exported.keys() == hf_state.keys()
+    for k in hf_state:
+        torch.testing.assert_close(exported[k], hf_state[k], rtol=0, atol=0)
