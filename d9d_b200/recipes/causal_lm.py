@@ -139,22 +139,37 @@ class CausalLMTask(TrainTask):
 
 
 class CausalLMPerplexityTask(InferenceTask):
-    """Accumulates summed negative log-likelihood and token counts; ``perplexity()`` after the run."""
+    """Accumulates summed negative log-likelihood and token counts; ``perplexity()`` after the run.
 
-    def __init__(self) -> None:
+    The running sums are part of the job checkpoint (keyed by rank: every rank holding a last pipeline stage accumulates
+    its own share), so an interrupted evaluation resumes without losing what was already scored."""
+
+    def __init__(self, dist_context: DistributedContext | None = None) -> None:
+        self._ctx = dist_context
         self.nll_sum = 0.0
         self.num_tokens = 0
 
     def build_forward_inputs(self, ctx: BuildForwardInputsContext) -> BuildForwardInputsResult:
-        ctx.state["labels"] = ctx.batch["labels"]
+        batch = ctx.batch if self._ctx is None else shard_batch_along_sequence(ctx.batch, self._ctx)
+        ctx.state["labels"] = batch["labels"]
         return BuildForwardInputsResult(
-            inputs={"input_ids": ctx.batch["input_ids"]},
-            kwargs={"labels": ctx.batch["labels"], "position_ids": ctx.batch["position_ids"]},
+            inputs={"input_ids": batch["input_ids"]},
+            kwargs={"labels": batch["labels"], "position_ids": batch["position_ids"]},
         )
 
     def process_outputs(self, ctx: ProcessOutputsContext) -> None:
         self.nll_sum += float(ctx.pipeline_results["logps"].sum())
         self.num_tokens += int((ctx.state["labels"] != LM_IGNORE_INDEX).sum())
+
+    def _key(self) -> str:
+        return f"rank_{self._ctx.global_rank if self._ctx is not None else 0}"
+
+    def state_dict(self) -> dict[str, torch.Tensor]:
+        return {self._key(): torch.tensor([self.nll_sum, float(self.num_tokens)], dtype=torch.float64)}
+
+    def load_state_dict(self, state_dict: dict[str, torch.Tensor]) -> None:
+        sums = state_dict[self._key()]
+        self.nll_sum, self.num_tokens = float(sums[0]), int(sums[1])
 
     def perplexity(self) -> float:
         return float(torch.tensor(self.nll_sum / max(self.num_tokens, 1)).exp())

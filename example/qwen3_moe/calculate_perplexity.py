@@ -34,16 +34,22 @@ def main() -> None:
     ap.add_argument("--single", action="store_true")
     args = ap.parse_args()
     config = ProjectConfig.model_validate_json(Path(args.config).read_text(encoding="utf-8"))
-    task = CausalLMPerplexityTask()
+    tasks: list[CausalLMPerplexityTask] = []
+
+    def task_provider(ctx):  # noqa: ANN001, ANN202  rank-aware: the running sums are checkpointed per rank
+        tasks.append(CausalLMPerplexityTask(ctx.dist_context))
+        return tasks[-1]
+
     data_provider = SyntheticDataProvider(config.data) if config.data.kind == "synthetic" else TextDataProvider(config.data)
     job = InferenceConfigurator(
         mesh=DeviceMeshParameters() if args.single else config.mesh,
         parameters=config.inference,
-        task_provider=lambda ctx: task,
+        task_provider=task_provider,
         model_provider=Qwen3MoEModelProvider(config.model_provider),
         data_provider=data_provider,
     ).configure()
     job.infer()
+    task = tasks[0]
 
     # every data-parallel replica saw a different shard: sum the statistics before reporting
     stats = torch.tensor([task.nll_sum, float(task.num_tokens)], dtype=torch.float64)

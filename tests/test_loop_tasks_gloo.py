@@ -171,3 +171,38 @@ def test_classification_job_over_pipeline_and_data_parallel(tmp_path):
     accuracy = [r["value"] for r in records if r.get("name") == "accuracy"]
     assert len(losses) == 8 and all(v == v for v in losses) and losses[-1] < losses[0]
     assert accuracy and 0.0 <= accuracy[-1] <= 1.0
+
+
+# ------------------------------------------------------------------------------------- resumable evaluation
+
+def _perplexity_job(tmp, task, ckpt_period):
+    from d9d_b200.core.dist_context import DeviceMeshParameters
+    from d9d_b200.loop.config import InferenceConfig
+    from d9d_b200.loop.run import InferenceConfigurator
+    from tests.helpers_train import LMProvider, SyntheticDataProvider, dense_params
+    config = InferenceConfig.model_validate({
+        "batching": {"global_batch_size": 8, "microbatch_size": 4},
+        "data_loading": {"num_workers": 0, "pin_memory": False, "persistent_workers": False},
+        "model_stage_factory": {"source_checkpoint": None, "checkpoint_only_trainable_parameters": False},
+        "determinism": {"base_seed": 0}, "gc": {"period_steps": "disable"},
+        "checkpointing": {"save_dir": str(tmp / "progress"), "period_steps": ckpt_period, "num_to_keep": None}, "profiling": None})
+    return InferenceConfigurator(mesh=DeviceMeshParameters(), parameters=config, task_provider=lambda ctx: task,
+                                 model_provider=LMProvider(dense_params()), data_provider=SyntheticDataProvider(num_samples=32)).configure()
+
+def test_interrupted_inference_resumes_with_its_running_sums(tmp_path):
+    """The perplexity task checkpoints its sums (per rank): an evaluation killed after two batches and restarted reports the
+    same totals as an uninterrupted one."""
+    from d9d_b200.loop.event.catalogue.inference import EVENT_INFERENCE_STEP_PRE
+    from d9d_b200.recipes import CausalLMPerplexityTask
+    full = CausalLMPerplexityTask()
+    _perplexity_job(tmp_path / "full", full, "disable").infer()
+    class Stop(Exception): pass
+    part = CausalLMPerplexityTask()
+    job = _perplexity_job(tmp_path / "cut", part, 1)
+    def stop(ctx):
+        if ctx.stepper.current_step == 2: raise Stop
+    job.state.event_bus.subscribe(EVENT_INFERENCE_STEP_PRE, stop)
+    with pytest.raises(Stop): job.infer()
+    resumed = CausalLMPerplexityTask()
+    _perplexity_job(tmp_path / "cut", resumed, 1).infer()
+    assert resumed.num_tokens == full.num_tokens and abs(resumed.nll_sum - full.nll_sum) < 1e-6 * abs(full.nll_sum)
