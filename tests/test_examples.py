@@ -62,3 +62,24 @@ def test_qwen3_moe_pretrain_example(tmp_path, monkeypatch):
     _load(EXAMPLES / "qwen3_moe" / "pretrain.py").main()
     assert (tmp_path / "export" / "model.safetensors.index.json").exists()
     assert any((tmp_path / "logs").glob("*.jsonl"))
+
+
+def test_qwen3_moe_perplexity_example(tmp_path, monkeypatch, capsys):
+    config = json.loads((EXAMPLES / "qwen3_moe" / "calculate_perplexity.json").read_text())
+    config["data"].update(num_samples=16, seq_len=16, vocab_size=64)
+    model = config["model_provider"]["model"]["model"]
+    model["layer"].update(hidden_size=32, intermediate_size=16, num_experts=4, experts_top_k=2, num_attention_heads=4, num_key_value_heads=2, head_dim=8)
+    model.update(num_hidden_layers=2, max_position_ids=64, split_vocab_size={"regular": 60, "special": 4})
+    config["model_provider"]["dtype"] = "float32"
+    config["inference"]["batching"] = {"global_batch_size": 8, "microbatch_size": 4}
+    config["inference"]["data_loading"].update(num_workers=0, pin_memory=False)
+    config["inference"]["model_stage_factory"]["source_checkpoint"] = None
+    config["inference"]["checkpointing"]["save_dir"] = str(tmp_path / "progress")
+    config["inference"]["profiling"] = None
+    path = tmp_path / "perplexity.json"
+    path.write_text(json.dumps(config))
+    monkeypatch.setattr(sys, "argv", ["calculate_perplexity.py", str(path), "--single"])
+    monkeypatch.syspath_prepend(str(EXAMPLES / "qwen3_moe"))  # the script imports its sibling ``pretrain`` like when run in place
+    _load(EXAMPLES / "qwen3_moe" / "calculate_perplexity.py").main()
+    out = capsys.readouterr().out
+    assert "tokens=256" in out and "perplexity=" in out
