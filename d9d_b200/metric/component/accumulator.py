@@ -67,11 +67,22 @@ class MetricAccumulator(Stateful):
         self._synchronized = self._synchronized.to(device)
 
     def state_dict(self) -> dict[str, Any]:
-        return {"local": self._local, "synchronized": self._synchronized, "is_synchronized": self._is_synchronized}
+        """Checkpoint view.  The keys are rank independent (the reference's key tree) and a distributed checkpoint stores ONE
+        copy of such tensors, so what is stored is the *global* accumulation: ``local`` holds the reduction of every rank's
+        local value.  Collective - every rank has to call it (``torch.distributed.checkpoint`` does, on save and on load)."""
+        total = self._local.clone()
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(total, op=_TORCH_OP[self._reduce_op])
+        return {"local": total, "synchronized": self._synchronized.clone(), "is_synchronized": self._is_synchronized}
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        # own copies: the accumulators are updated in place and must not alias the caller's tensors
-        self._local = state_dict["local"].detach().clone().to(self._local.device)
+        """Inverse of :meth:`state_dict`: the stored global value becomes the local value of rank 0 (every rank for max / min,
+        which are idempotent) and the other ranks restart from the identity, so the next ``sync`` reproduces the total."""
+        total = state_dict["local"].detach().clone().to(self._local.device)
+        distributed = dist.is_available() and dist.is_initialized()
+        if distributed and self._reduce_op == MetricReduceOp.sum and dist.get_rank() != 0:
+            total = self._initial.clone()
+        self._local = total
         self._synchronized = state_dict["synchronized"].detach().clone().to(self._synchronized.device)
         self._is_synchronized = bool(state_dict["is_synchronized"])
 

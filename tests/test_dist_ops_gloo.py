@@ -50,3 +50,35 @@ def _worker(rank, world_size):
 
 def test_dist_ops_and_metric_sync():
     run_distributed(_worker, 3)
+
+
+def _metric_checkpoint_worker(rank, world_size, tmp):
+    import torch.distributed as dist
+    import torch.distributed.checkpoint as dcp
+
+    from d9d_b200.metric.impl.aggregation import SumMetric, WeightedMeanMetric
+    from d9d_b200.metric.impl.container import ComposeMetric
+
+    dist.init_process_group("gloo")
+
+    def fresh():
+        return ComposeMetric({"tokens": SumMetric(), "loss": WeightedMeanMetric()})
+
+    metrics = fresh()
+    metrics["tokens"].update(torch.tensor(10.0 * (rank + 1)))  # rank-specific partial sums in the middle of a logging period
+    metrics["loss"].update(torch.tensor([float(rank)]), torch.tensor([1.0 + rank]))
+    dcp.save({"metrics": metrics}, checkpoint_id=tmp)
+
+    restored = fresh()
+    dcp.load({"metrics": restored}, checkpoint_id=tmp)
+    restored["tokens"].update(torch.tensor(1.0))  # accumulation continues after the restart
+    restored.sync(None)
+    values = restored.compute()
+    assert float(values["tokens"]) == 10.0 * sum(r + 1 for r in range(world_size)) + world_size
+    expected_loss = sum(r * (1.0 + r) for r in range(world_size)) / sum(1.0 + r for r in range(world_size))
+    assert abs(float(values["loss"]) - expected_loss) < 1e-6
+
+
+def test_metric_state_survives_a_distributed_checkpoint(tmp_path):
+    """Rank-specific partial metric sums are checkpointed under rank-independent keys: the global totals must come back."""
+    run_distributed(_metric_checkpoint_worker, 2, str(tmp_path / "ckpt"))
