@@ -102,14 +102,14 @@ def test_resume_is_exact(tmp_path):
         torch.testing.assert_close(v, ref_state[k], rtol=0, atol=0)
 
 
-def _dist_worker(rank, world, tmp, mesh_kwargs, schedule, moe, source=None, recompute=False, layers=2):
+def _dist_worker(rank, world, tmp, mesh_kwargs, schedule, moe, source=None, recompute=False, layers=2, samples=32):
     from pathlib import Path
 
     from d9d_b200.core.dist_context import DeviceMeshParameters
 
     tmp = Path(tmp)
     trainer = _make_trainer(tmp, mesh=DeviceMeshParameters(**mesh_kwargs), moe=moe, schedule=schedule, total_batch=8, micro=2,
-                            log=True, samples=32, source=source, recompute=recompute, layers=layers)
+                            log=True, samples=samples, source=source, recompute=recompute, layers=layers)
     trainer.train()
     trainer.export(tmp / "export", load_checkpoint=False)
     if rank == 0:
@@ -359,6 +359,9 @@ _PIPELINE_COMBINATIONS = [
     # interleaved (two stages per rank) schedule over FSDP-sharded stages, activation recomputation
     ({"pipeline_parallel": 2, "context_parallel_shard": 2}, {"schedule": "looped_bfs", "num_stages_per_rank": 2}, False),
     ({"pipeline_parallel": 2, "context_parallel_replicate": 2, "expert_parallel": 2}, {"schedule": "dual_pipe_v"}, True),
+    # split backward through real decoder layers: interleaved zero-bubble 1F1B and the V-shaped zero-bubble schedule
+    ({"pipeline_parallel": 2, "context_parallel_replicate": 2}, {"schedule": "1f1b", "num_stages_per_rank": 2, "zero_bubble": True}, False),
+    ({"pipeline_parallel": 2, "context_parallel_replicate": 2, "expert_parallel": 2}, {"schedule": "zero_bubble_v"}, True),
 ]
 
 
@@ -370,9 +373,9 @@ def test_pipeline_combinations_reproduce_the_single_process_run(tmp_path):
     jobs = []
     for moe in (False, True):
         _make_trainer(tmp_path / f"init{moe}", moe=moe, log=False, layers=layers).export(tmp_path / f"weights{moe}", load_checkpoint=False)
-        _make_trainer(tmp_path / f"s{moe}", moe=moe, total_batch=8, micro=2, samples=32, source=tmp_path / f"weights{moe}", layers=layers).train()
+        _make_trainer(tmp_path / f"s{moe}", moe=moe, total_batch=8, micro=2, samples=16, source=tmp_path / f"weights{moe}", layers=layers).train()
     for i, (mesh_kwargs, schedule, moe) in enumerate(_PIPELINE_COMBINATIONS):
-        jobs.append((str(tmp_path / f"job{i}"), mesh_kwargs, schedule, moe, str(tmp_path / f"weights{moe}"), True, layers))
+        jobs.append((str(tmp_path / f"job{i}"), mesh_kwargs, schedule, moe, str(tmp_path / f"weights{moe}"), True, layers, 16))
     run_distributed(_jobs_worker, 4, jobs)
     for i, (mesh_kwargs, schedule, moe) in enumerate(_PIPELINE_COMBINATIONS):
         _assert_same_trajectory(tmp_path / f"s{moe}", tmp_path / f"job{i}", (mesh_kwargs, schedule))
