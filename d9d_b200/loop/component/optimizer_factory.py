@@ -14,6 +14,31 @@ from .model_stage_factory import TrackedModules
 from .stepper import Stepper
 
 
+class _FrozenStageOptimizer(OptimizerProtocol):
+    """Stands in for the optimizer of a model stage without trainable parameters (e.g. the first pipeline stage when only a
+    head on the last stage is tuned): torch optimizers refuse empty parameter lists."""
+
+    param_groups: list = []
+
+    def step(self) -> None: ...
+
+    def zero_grad(self) -> None: ...
+
+    def state_dict(self) -> dict:
+        return {}
+
+    def load_state_dict(self, state_dict: dict) -> None: ...
+
+
+class _FrozenStageScheduler(LRSchedulerProtocol):
+    def step(self) -> None: ...
+
+    def state_dict(self) -> dict:
+        return {}
+
+    def load_state_dict(self, state_dict: dict) -> None: ...
+
+
 class OptimizerFactory:
     """One optimizer + LR scheduler per local model stage, wrapped into the pipeline-aware aggregates."""
 
@@ -25,6 +50,10 @@ class OptimizerFactory:
     def build_optimizer_and_scheduler(self) -> tuple[OptimizerProtocol, LRSchedulerProtocol]:
         optimizers, schedulers = [], []
         for module in self._modules.modules:
+            if not any(p.requires_grad for p in module.parameters()):
+                optimizers.append(_FrozenStageOptimizer())
+                schedulers.append(_FrozenStageScheduler())
+                continue
             opt = self._opt_provider(InitializeOptimizerStageContext(dist_context=self._ctx, model=module))
             optimizers.append(opt)
             schedulers.append(self._lr_provider(InitializeLRSchedulerContext(dist_context=self._ctx, total_steps=self._stepper.total_steps, optimizer=opt)))

@@ -77,7 +77,7 @@ def test_inference_loop_over_pipeline_and_data_parallel(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------- classification
-def _classification_worker(rank, world, tmp, mesh_kwargs):
+def _classification_worker(rank, world, tmp, mesh_kwargs, head_only=False):
     from pathlib import Path
 
     from tests.helpers_train import trainer_config
@@ -106,6 +106,13 @@ def _classification_worker(rank, world, tmp, mesh_kwargs):
     class Provider(ModelProvider):
         def initialize_model_stage(self, context):
             model = Qwen3DenseForClassification(params, context.stage, HiddenStatesAggregationMode.no, False)
+            if head_only:  # tune the classification head only: the first pipeline stage ends up without trainable parameters
+                from d9d_b200.peft import inject_peft_and_freeze
+                from d9d_b200.peft.all import peft_method_from_config
+                from d9d_b200.peft.full_tune.config import FullTuneConfig
+
+                inject_peft_and_freeze(peft_method_from_config(FullTuneConfig.model_validate(
+                    {"kind": "full_tune", "module_name_pattern": "cls_head.*"})), model)
             return InitializeModelStageResult(model=model, state_mapper=identity_mapper_from_module(model))
 
         def parallelize_model_stage(self, context):
@@ -162,6 +169,19 @@ def _classification_worker(rank, world, tmp, mesh_kwargs):
         optimizer_provider=AutoOptimizerProvider(AdamWOptimizerConfig(lr=5e-3, weight_decay=0.0)),
         lr_scheduler_provider=AutoLRSchedulerProvider(schedule)).configure()
     trainer.train()
+    if head_only:
+        trainable = [n for m in trainer.state.tracked_modules.modules for n, p in m.named_parameters() if p.requires_grad]
+        assert all(n.startswith("cls_head") for n in trainable)
+        assert bool(trainable) == trainer.state.tracked_modules.modules[0]._stage.is_current_stage_last  # noqa: SLF001
+
+
+def test_head_only_tuning_with_a_fully_frozen_pipeline_stage(tmp_path):
+    """Only the classification head (last stage) is trainable: the other stage has no trainable parameter at all, which the
+    optimizer factory, gradient synchronisation and clipping have to cope with."""
+    run_distributed(_classification_worker, 2, str(tmp_path), {"pipeline_parallel": 2}, True)
+    records = [json.loads(line) for line in next((tmp_path / "logs").glob("*.jsonl")).read_text().splitlines()]
+    losses = [r["value"] for r in records if r.get("name") == "loss"]
+    assert len(losses) == 8 and all(v == v for v in losses)
 
 
 def test_classification_job_over_pipeline_and_data_parallel(tmp_path):
