@@ -50,6 +50,17 @@ def _build(moe: bool):
                                             num_shared_experts=1),
             num_hidden_layers=2, rope_base=10000, max_position_ids=64, split_vocab_size={"regular": 100, "special": 28},
             split_vocab_order=["regular", "special"]))
+    elif moe == "qwen3_5_moe":
+        from d9d_b200.module.model.qwen3_5_moe import (Qwen3_5MoEForCausalLM as Cls, Qwen3_5MoEForCausalLMParameters,
+                                                       Qwen3_5MoELayerParameters, Qwen3_5MoEParameters)
+
+        params = Qwen3_5MoEForCausalLMParameters(model=Qwen3_5MoEParameters(
+            layer=Qwen3_5MoELayerParameters(hidden_size=32, rms_norm_eps=1e-6, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
+                                            linear_num_key_heads=2, linear_num_value_heads=4, linear_key_head_dim=8,
+                                            linear_value_head_dim=8, full_attention_interval=2, moe_intermediate_size=16,
+                                            shared_expert_intermediate_size=24, num_experts=4, experts_top_k=2),
+            num_hidden_layers=2, rope_base=10000, max_position_ids=64, split_vocab_size={"regular": 100, "special": 28},
+            split_vocab_order=["regular", "special"]))
     elif moe:
         from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM as Cls
 
@@ -86,7 +97,9 @@ def _check_mesh(rank, world_size, mesh_name, moe):
 
     ctx = DeviceMeshParameters(**MESHES[mesh_name]).build()
     model = _build(moe)
-    if moe == "deepseek":
+    if moe == "qwen3_5_moe":
+        from d9d_b200.module.parallelism.model.qwen3_5_moe import parallelize_qwen3_5_moe_for_causal_lm as plan
+    elif moe == "deepseek":
         from d9d_b200.module.parallelism.model.deepseek_v2 import parallelize_deepseek_v2_for_causal_lm as plan
     elif moe:
         from d9d_b200.module.parallelism.model.qwen3_moe import parallelize_qwen3_moe_for_causal_lm as plan
@@ -136,3 +149,8 @@ def test_moe_model_matches_single_process(mesh_names):
 def test_deepseek_v2_model_matches_single_process():
     """Latent attention under context parallelism, dense first layer + MoE layers with a shared expert under FSDP x EP."""
     run_distributed(_worker, 4, ("dps2_cps2_ep2",), "deepseek")
+
+
+def test_qwen3_5_moe_model_matches_single_process():
+    """Gated DeltaNet / gated attention hybrid with MoE + gated shared expert under HSDP x EP and FSDP."""
+    run_distributed(_worker, 4, ("dpr2_dps2_ep4", "dps4"), "qwen3_5_moe")
