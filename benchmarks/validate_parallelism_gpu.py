@@ -19,6 +19,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+DEVICE, DTYPE = "cuda", torch.bfloat16  # ``--cpu`` (logic dry run on gloo) switches to cpu / fp32
+
 MESHES = {
     "cps2": dict(context_parallel_shard=2), "tp2": dict(tensor_parallel=2),
     "cps4": dict(context_parallel_shard=4), "dpr2_tp2": dict(data_parallel_replicate=2, tensor_parallel=2),
@@ -42,8 +44,8 @@ def check_attention(mode: str, layout_name: str, causal: bool) -> None:
     group, world, rank = dist.group.WORLD, dist.get_world_size(), dist.get_rank()
     layout = ContextParallelLayout(layout_name)
     torch.manual_seed(0)
-    batch, seq, heads, kv_heads, dim = 2, 256 * world, 8, 4, 128
-    q, k, v, w = (torch.randn(batch, seq, h, dim, device="cuda", dtype=torch.bfloat16) for h in (heads, kv_heads, kv_heads, heads))
+    batch, seq, heads, kv_heads, dim = (2, 256 * world, 8, 4, 128) if DEVICE == "cuda" else (1, 16 * world, 4, 2, 8)
+    q, k, v, w = (torch.randn(batch, seq, h, dim, device=DEVICE, dtype=DTYPE) for h in (heads, kv_heads, kv_heads, heads))
     ref_in = [t.clone().requires_grad_() for t in (q, k, v)]
     ref_out, _ = flash_attn_func(*ref_in, causal=causal)
     (ref_out.float() * w.float()).sum().backward()
@@ -52,7 +54,7 @@ def check_attention(mode: str, layout_name: str, causal: bool) -> None:
     if mode == "ring":
         out = ring_attention(*local, group, positions, causal=causal, mask_cache={})
     else:
-        out = ulysses_attention(*local, group, lambda a, b, c: flash_attn_func(a, b, c, causal=causal)[0], positions=positions.reshape(-1).cuda())
+        out = ulysses_attention(*local, group, lambda a, b, c: flash_attn_func(a, b, c, causal=causal)[0], positions=positions.reshape(-1).to(DEVICE))
     _close(out.float(), shard_sequence(ref_out.detach(), 1, world, rank, layout).float(), "output")
     (out.float() * shard_sequence(w, 1, world, rank, layout).float()).sum().backward()
     for name, mine, full in zip("qkv", local, ref_in):
@@ -68,25 +70,28 @@ def check_model(mesh_name: str, moe: bool) -> None:
     from d9d_b200.module.block.hidden_states_aggregator import HiddenStatesAggregationMode
     from d9d_b200.pipelining.api import PipelineStageInfo
 
+    small = DEVICE != "cuda"
+    hidden, vocab, seq = (64, 128, 32) if small else (512, 4096, 1024)
+
     def build():
         torch.manual_seed(5)
         if moe:
             from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM as Cls, Qwen3MoEForCausalLMParameters as P, Qwen3MoELayerParameters as L, Qwen3MoEParameters as B
-            layer = L(hidden_size=512, intermediate_size=256, num_experts=8, experts_top_k=2, num_attention_heads=8, num_key_value_heads=4, rms_norm_eps=1e-6, head_dim=64)
+            layer = L(hidden_size=hidden, intermediate_size=hidden // 2, num_experts=8, experts_top_k=2, num_attention_heads=8, num_key_value_heads=4, rms_norm_eps=1e-6, head_dim=hidden // 8)
         else:
             from d9d_b200.module.model.qwen3_dense import Qwen3DenseForCausalLM as Cls, Qwen3DenseForCausalLMParameters as P, Qwen3DenseLayerParameters as L, Qwen3DenseParameters as B
-            layer = L(hidden_size=512, intermediate_size=1024, num_attention_heads=8, num_key_value_heads=4, rms_norm_eps=1e-6, head_dim=64)
-        params = P(model=B(layer=layer, num_hidden_layers=2, rope_base=10000, max_position_ids=2048, split_vocab_size={"text": 4096}, split_vocab_order=["text"]))
-        with torch.device("cuda"):
-            model = Cls(params, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False).bfloat16()
+            layer = L(hidden_size=hidden, intermediate_size=2 * hidden, num_attention_heads=8, num_key_value_heads=4, rms_norm_eps=1e-6, head_dim=hidden // 8)
+        params = P(model=B(layer=layer, num_hidden_layers=2, rope_base=10000, max_position_ids=2048, split_vocab_size={"text": vocab}, split_vocab_order=["text"]))
+        with torch.device(DEVICE):
+            model = Cls(params, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False).to(DTYPE)
         model.reset_parameters()
         return model
 
     def batch(i):
         g = torch.Generator().manual_seed(900 + i)
-        ids = torch.randint(0, 4096, (2, 1024), generator=g).cuda()
-        labels = torch.randint(0, 4096, (2, 1024), generator=g).cuda()
-        return ids, labels, torch.arange(1024, device="cuda")[None].expand(2, -1).contiguous()
+        ids = torch.randint(0, vocab, (2, seq), generator=g).to(DEVICE)
+        labels = torch.randint(0, vocab, (2, seq), generator=g).to(DEVICE)
+        return ids, labels, torch.arange(seq, device=DEVICE)[None].expand(2, -1).contiguous()
 
     ctx = DeviceMeshParameters(**MESHES[mesh_name]).build()
     model = build()
@@ -118,9 +123,15 @@ def check_model(mesh_name: str, moe: bool) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--meshes", nargs="*", default=None)
+    ap.add_argument("--cpu", action="store_true", help="dry run of the script's logic on gloo / cpu / fp32 with tiny shapes")
     args = ap.parse_args()
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    dist.init_process_group("nccl")
+    global DEVICE, DTYPE
+    if args.cpu:
+        DEVICE, DTYPE = "cpu", torch.float32
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     world, rank = dist.get_world_size(), dist.get_rank()
     failures = 0
 
