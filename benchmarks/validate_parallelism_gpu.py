@@ -44,7 +44,7 @@ def check_attention(mode: str, layout_name: str, causal: bool) -> None:
     group, world, rank = dist.group.WORLD, dist.get_world_size(), dist.get_rank()
     layout = ContextParallelLayout(layout_name)
     torch.manual_seed(0)
-    batch, seq, heads, kv_heads, dim = (2, 256 * world, 8, 4, 128) if DEVICE == "cuda" else (1, 16 * world, 4, 2, 8)
+    batch, seq, heads, kv_heads, dim = (2, 256 * world, 8, 4, 128) if DEVICE == "cuda" else (1, 16 * world, 8, 4, 8)
     q, k, v, w = (torch.randn(batch, seq, h, dim, device=DEVICE, dtype=DTYPE) for h in (heads, kv_heads, kv_heads, heads))
     ref_in = [t.clone().requires_grad_() for t in (q, k, v)]
     ref_out, _ = flash_attn_func(*ref_in, causal=causal)
