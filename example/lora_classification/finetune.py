@@ -11,8 +11,12 @@ The task is synthetic (no network needed): does token 1 occur more often than to
 
 from __future__ import annotations
 
-import argparse
+import sys
 from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))  # run in place without installing the package
+
+import argparse
 
 import torch
 from pydantic import BaseModel

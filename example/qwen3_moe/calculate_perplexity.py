@@ -6,9 +6,13 @@
 
 from __future__ import annotations
 
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))  # run in place without installing the package
+
 import argparse
 import math
-from pathlib import Path
 
 import torch
 import torch.distributed as dist

@@ -11,9 +11,13 @@ dataset column with a ``tokenizers`` tokenizer file and batches by length throug
 
 from __future__ import annotations
 
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))  # run in place without installing the package
+
 import argparse
 from collections.abc import Sequence
-from pathlib import Path
 from typing import Any, Literal
 
 import torch
