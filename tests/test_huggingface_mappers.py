@@ -1,6 +1,8 @@
 """HF <-> native mappers: round trip over every family / head / expert layout, and numerical parity with the
 transformers implementation where it is importable (CPU, fp32, tiny configs)."""
 
+import json
+
 import pytest
 import torch
 
@@ -427,3 +429,22 @@ def test_qwen3_5_moe_matches_transformers_and_round_trips():
     assert exported.keys() == hf_state.keys()
     for k in hf_state:
         torch.testing.assert_close(exported[k], hf_state[k], rtol=0, atol=0)
+
+
+def test_mapper_groups_whose_inputs_live_in_different_shard_files(tmp_path):
+    """Streaming load keeps a group's early inputs resident until the shard holding the rest has been read."""
+    from tests.test_huggingface_mappers import _moe_model
+    from d9d_b200.model_state.io import load_model_state, save_model_state
+    from d9d_b200.module.model.qwen3_moe import mapper_from_huggingface_qwen3_moe_for_causal_lm, mapper_to_huggingface_qwen3_moe_for_causal_lm
+    p, m = _moe_model("qwen3_moe")
+    # export in the per-expert layout with shards so small that the experts of one layer land in many files
+    save_model_state(tmp_path / "hf", mapper_to_huggingface_qwen3_moe_for_causal_lm(p, "module_list"), m, shard_size_gb=1.3e-5, show_progress=False)
+    index = json.loads((tmp_path / "hf" / "model.safetensors.index.json").read_text())
+    files = {index["weight_map"][f"model.layers.0.mlp.experts.{e}.up_proj.weight"] for e in range(4)}
+    assert len(files) > 1
+    _, clone = _moe_model("qwen3_moe")
+    with torch.no_grad():
+        for prm in clone.parameters(): prm.zero_()
+    load_model_state(tmp_path / "hf", mapper_from_huggingface_qwen3_moe_for_causal_lm(p, "module_list"), "cpu", clone, show_progress=False)
+    for k, v in m.state_dict().items():
+        assert torch.equal(clone.state_dict()[k], v), k
