@@ -56,10 +56,11 @@ def _train(tmp, source, fmt, mesh_kwargs):
     trainer.export(tmp / "export", load_checkpoint=False)
 
 
-def _worker(rank, world, tmp, source, fmt, mesh_kwargs):
+def _worker(rank, world, jobs, mesh_kwargs):
     from pathlib import Path
 
-    _train(Path(tmp), Path(source), fmt, mesh_kwargs)
+    for tmp, source, fmt in jobs:  # both expert layouts over one set of processes
+        _train(Path(tmp), Path(source), fmt, mesh_kwargs)
 
 
 def _losses(tmp):
@@ -67,10 +68,9 @@ def _losses(tmp):
     return {r["step"]: r["value"] for r in records if r.get("name") == "loss"}
 
 
-@pytest.mark.parametrize("fmt", ["fused", "module_list"])
-def test_huggingface_checkpoint_through_a_sharded_pipelined_job(tmp_path, fmt):
-    transformers = pytest.importorskip("transformers")
-    from safetensors.torch import load_file, save_file
+def _write_hf_checkpoint(root, fmt):
+    import transformers
+    from safetensors.torch import save_file
 
     cfg = transformers.Qwen3MoeConfig(vocab_size=96, hidden_size=32, intermediate_size=48, moe_intermediate_size=16, num_hidden_layers=2,
                                       num_attention_heads=4, num_key_value_heads=2, head_dim=8, rms_norm_eps=1e-6, rope_theta=10000.0,
@@ -85,21 +85,24 @@ def test_huggingface_checkpoint_through_a_sharded_pipelined_job(tmp_path, fmt):
                 gate, up = gate_up[e].chunk(2, dim=0)
                 state[f"{prefix}{e}.gate_proj.weight"], state[f"{prefix}{e}.up_proj.weight"] = gate.contiguous(), up.contiguous()
                 state[f"{prefix}{e}.down_proj.weight"] = down[e].contiguous()
-    source = tmp_path / "hf"
-    source.mkdir()
-    save_file(state, str(source / "model-00001-of-00001.safetensors"))
-    (source / "model.safetensors.index.json").write_text(json.dumps({
+    root.mkdir(parents=True)
+    save_file(state, str(root / "model-00001-of-00001.safetensors"))
+    (root / "model.safetensors.index.json").write_text(json.dumps({
         "metadata": {"total_size": sum(v.numel() * v.element_size() for v in state.values())},
         "weight_map": dict.fromkeys(state, "model-00001-of-00001.safetensors")}))
+    return state
 
-    _train(tmp_path / "single", source, fmt, {})
+
+def test_huggingface_checkpoint_through_a_sharded_pipelined_job(tmp_path):
+    pytest.importorskip("transformers")
+    from safetensors.torch import load_file
+
+    formats = ("fused", "module_list")
+    states = {fmt: _write_hf_checkpoint(tmp_path / fmt / "hf", fmt) for fmt in formats}
+    for fmt in formats:
+        _train(tmp_path / fmt / "single", tmp_path / fmt / "hf", fmt, {})
     mesh = {"pipeline_parallel": 2, "context_parallel_shard": 2, "expert_parallel": 2}  # all ranks read the same samples
-    run_distributed(_worker, 4, str(tmp_path / "dist"), str(source), fmt, mesh)
-
-    ref, got = _losses(tmp_path / "single"), _losses(tmp_path / "dist")
-    assert sorted(ref) == sorted(got) == [0, 1, 2]
-    for step in ref:  # same weights in, same trajectory
-        assert abs(ref[step] - got[step]) < 2e-3 * max(1.0, abs(ref[step])), (step, ref[step], got[step])
+    run_distributed(_worker, 4, [(str(tmp_path / fmt / "dist"), str(tmp_path / fmt / "hf"), fmt) for fmt in formats], mesh)
 
     def exported(path):
         index = json.loads((path / "model.safetensors.index.json").read_text())
@@ -108,7 +111,12 @@ def test_huggingface_checkpoint_through_a_sharded_pipelined_job(tmp_path, fmt):
             tensors.update(load_file(str(path / file)))
         return tensors
 
-    single, dist = exported(tmp_path / "single" / "export"), exported(tmp_path / "dist" / "export")
-    assert single.keys() == dist.keys() == state.keys()  # the export is again a complete HuggingFace checkpoint
-    for name in single:
-        torch.testing.assert_close(dist[name], single[name], rtol=2e-3, atol=2e-4, msg=lambda m, name=name: f"{name}: {m}")
+    for fmt in formats:
+        ref, got = _losses(tmp_path / fmt / "single"), _losses(tmp_path / fmt / "dist")
+        assert sorted(ref) == sorted(got) == [0, 1, 2], fmt
+        for step in ref:  # same weights in, same trajectory
+            assert abs(ref[step] - got[step]) < 2e-3 * max(1.0, abs(ref[step])), (fmt, step, ref[step], got[step])
+        single, dist = exported(tmp_path / fmt / "single" / "export"), exported(tmp_path / fmt / "dist" / "export")
+        assert single.keys() == dist.keys() == states[fmt].keys()  # the export is again a complete HuggingFace checkpoint
+        for name in single:
+            torch.testing.assert_close(dist[name], single[name], rtol=2e-3, atol=2e-4, msg=lambda m, name=name: f"{fmt} {name}: {m}")  # noqa: B023
