@@ -42,12 +42,14 @@ def _build(moe: bool):
     if moe == "deepseek":
         from d9d_b200.module.model.deepseek_v2 import (DeepseekV2ForCausalLM as Cls, DeepseekV2ForCausalLMParameters,
                                                        DeepseekV2LayerParameters, DeepseekV2Parameters)
+        from d9d_b200.module.model.deepseek_v3 import deepseek_v3_router
 
         params = DeepseekV2ForCausalLMParameters(model=DeepseekV2Parameters(
             layer=DeepseekV2LayerParameters(hidden_size=32, rms_norm_eps=1e-6, num_attention_heads=4, qk_nope_head_dim=8,
                                             qk_rope_head_dim=4, v_head_dim=8, kv_lora_rank=16, q_lora_rank=12, intermediate_size=48,
                                             first_k_dense_replace=1, moe_intermediate_size=16, num_experts=4, experts_top_k=2,
-                                            num_shared_experts=1),
+                                            num_shared_experts=1, router_renormalize_probabilities=True,
+                                            router=deepseek_v3_router(n_group=2, topk_group=1, routed_scaling_factor=2.5)),
             num_hidden_layers=2, rope_base=10000, max_position_ids=64, split_vocab_size={"regular": 100, "special": 28},
             split_vocab_order=["regular", "special"]))
     elif moe == "qwen3_5_moe":
@@ -147,7 +149,8 @@ def test_moe_model_matches_single_process(mesh_names):
 
 
 def test_deepseek_v2_model_matches_single_process():
-    """Latent attention under context parallelism, dense first layer + MoE layers with a shared expert under FSDP x EP."""
+    """Latent attention under context parallelism, dense first layer + MoE layers (DeepSeek-V3 routing: sigmoid scores, selection
+    bias, group-limited top-k) with a shared expert under FSDP x EP."""
     run_distributed(_worker, 4, ("dps2_cps2_ep2",), "deepseek")
 
 
