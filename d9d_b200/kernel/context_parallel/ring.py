@@ -66,17 +66,28 @@ def _expand_heads(t: torch.Tensor, groups: int) -> torch.Tensor:
     return t if groups == 1 else t.repeat_interleave(groups, dim=2)
 
 
+_QUERY_CHUNK = 2048  # queries scored at a time against one K/V block: bounds the fp32 score tile to [B, H, 2048, S_block]
+
+
+def _query_chunks(length: int) -> list[slice]:
+    return [slice(lo, min(lo + _QUERY_CHUNK, length)) for lo in range(0, length, _QUERY_CHUNK)]
+
+
 def _block_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, mask: torch.Tensor | None
                    ) -> tuple[torch.Tensor, torch.Tensor]:
     """``(out [B,Sq,H,Dv] fp32, lse [B,H,Sq] fp32)`` of attention against one K/V block."""
     groups = q.shape[2] // k.shape[2]
-    scores = torch.einsum("bqhd,bkhd->bhqk", q.float(), _expand_heads(k, groups).float()) * scale
-    if mask is not None:
-        scores = scores.masked_fill(~mask, _NEG_INF)
-    lse = torch.logsumexp(scores, dim=-1)
-    probs = torch.exp(scores - lse.unsqueeze(-1).nan_to_num(neginf=0.0))  # rows without visible keys: exp(-inf) = 0
-    out = torch.einsum("bhqk,bkhd->bqhd", probs, _expand_heads(v, groups).float())
-    return out, lse
+    kf, vf = _expand_heads(k, groups).float(), _expand_heads(v, groups).float()
+    outs, lses = [], []
+    for rows in _query_chunks(q.shape[1]):
+        scores = torch.einsum("bqhd,bkhd->bhqk", q[:, rows].float(), kf) * scale
+        if mask is not None:
+            scores = scores.masked_fill(~mask[rows], _NEG_INF)
+        lse = torch.logsumexp(scores, dim=-1)
+        probs = torch.exp(scores - lse.unsqueeze(-1).nan_to_num(neginf=0.0))  # rows without visible keys: exp(-inf) = 0
+        outs.append(torch.einsum("bhqk,bkhd->bqhd", probs, vf))
+        lses.append(lse)
+    return torch.cat(outs, dim=1), torch.cat(lses, dim=2)
 
 
 def _merge(out: torch.Tensor | None, lse: torch.Tensor | None, out_b: torch.Tensor, lse_b: torch.Tensor
@@ -96,16 +107,20 @@ def _block_backward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, grad_out:
     """Gradients of one block given the *global* ``lse`` and ``delta = rowsum(dO * O)``: ``(dq, dk, dv)`` in fp32."""
     groups = q.shape[2] // k.shape[2]
     kf, vf = _expand_heads(k, groups).float(), _expand_heads(v, groups).float()
-    qf, gf = q.float(), grad_out.float()
-    scores = torch.einsum("bqhd,bkhd->bhqk", qf, kf) * scale
-    if mask is not None:
-        scores = scores.masked_fill(~mask, _NEG_INF)
-    probs = torch.exp(scores - lse.unsqueeze(-1).nan_to_num(neginf=0.0))
-    dv = torch.einsum("bhqk,bqhd->bkhd", probs, gf)
-    dprobs = torch.einsum("bqhd,bkhd->bhqk", gf, vf)
-    dscores = probs * (dprobs - delta.unsqueeze(-1)) * scale
-    dq = torch.einsum("bhqk,bkhd->bqhd", dscores, kf)
-    dk = torch.einsum("bhqk,bqhd->bkhd", dscores, qf)
+    dk, dv = torch.zeros_like(kf), torch.zeros_like(vf)
+    dqs = []
+    for rows in _query_chunks(q.shape[1]):
+        qf, gf = q[:, rows].float(), grad_out[:, rows].float()
+        scores = torch.einsum("bqhd,bkhd->bhqk", qf, kf) * scale
+        if mask is not None:
+            scores = scores.masked_fill(~mask[rows], _NEG_INF)
+        probs = torch.exp(scores - lse[:, :, rows].unsqueeze(-1).nan_to_num(neginf=0.0))
+        dv += torch.einsum("bhqk,bqhd->bkhd", probs, gf)
+        dprobs = torch.einsum("bqhd,bkhd->bhqk", gf, vf)
+        dscores = probs * (dprobs - delta[:, :, rows].unsqueeze(-1)) * scale
+        dqs.append(torch.einsum("bhqk,bkhd->bqhd", dscores, kf))
+        dk += torch.einsum("bhqk,bqhd->bkhd", dscores, qf)
+    dq = torch.cat(dqs, dim=1)
     if groups > 1:
         b, sk, _, d = dk.shape
         dk = dk.view(b, sk, k.shape[2], groups, d).sum(3)
