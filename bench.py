@@ -7,7 +7,7 @@ Synthetic token data, random-init weights.  Weak scaling: every GPU processes ``
 ``8 x seq_len`` tokens per optimizer step (data-parallel replicas, summed gradients).
 
     python bench.py --gpus N --steps K --warmup W            # own implementation
-    python bench.py --impl reference ...                     # unmodified reference (unavailable offline)
+    python bench.py --impl reference ...                     # unmodified reference from baseline/_ref (baseline/ref_bench.py)
 
 Prints ONE JSON line (rank 0).  Timed region = K optimizer steps bracketed by barrier + cuda synchronize, device
 events, max over ranks.  ``e2e`` repeats the measurement through the public training API with every step's inputs
@@ -105,15 +105,34 @@ class ClockSampler:
 
 
 def reference_arm(args) -> None:
-    # The reference is a pure-Python package whose build backend (poetry-core) is not installable offline and whose
-    # model imports hard-require the grouped_gemm / flash_attn.cute (FA4) / cut_cross_entropy wheels.
-    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref", "d9d")
-    reason = ("reference not installable offline: build backend poetry-core missing from the wheelhouse and its model "
-              "imports require grouped_gemm, flash_attn.cute (FA4) and cut_cross_entropy wheels that are not in this image")
-    if os.path.isdir(ref):
-        reason = "baseline/_ref present but its optional native wheels (grouped_gemm, flash_attn.cute, cut_cross_entropy) are missing"
-    if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": reason}))
+    """Runs the UNMODIFIED reference (``baseline/_ref``, see ``baseline/ref_bench.py``) on the same workload."""
+    import importlib.util
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    rank0 = int(os.environ.get("RANK", "0")) == 0
+
+    def unavailable(why: str) -> None:
+        if rank0:
+            print(json.dumps({"impl": "reference", "unavailable": why}))
+
+    def load(name: str):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(here, "baseline", f"{name}.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    if not os.path.isdir(os.path.join(here, "baseline", "_ref", "d9d")):
+        if not (int(os.environ.get("LOCAL_RANK", "0")) == 0 and load("install_reference").install()):
+            return unavailable("baseline/_ref is missing and /root/reference is not present on this machine to install it from")
+    try:
+        result = load("ref_bench").run(args, FLAGSHIP, ClockSampler)
+    except Exception as exc:  # noqa: BLE001 - the contract is: print the reason, exit 0
+        import traceback
+
+        traceback.print_exc()
+        return unavailable(f"reference failed to run: {type(exc).__name__}: {str(exc)[:300]}".replace("\n", " "))
+    if rank0:
+        print(json.dumps(result))
 
 
 def flagship_params(args):
