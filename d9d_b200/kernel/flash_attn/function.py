@@ -3,8 +3,8 @@
 sinks (with analytic ``dsink``), optional LSE.
 
 Backends:
-* ``attention_reference``: exact fp32 math (CPU, and features the fast path does not cover yet),
-* CUDA fast path: fused flash kernel (no [S,S] materialisation).
+* ``attention_reference``: exact fp32 math (CPU tensors; the oracle of the numerics tests),
+* CUDA: the native tcgen05 flash-attention forward / backward kernels (``native.py``), every option in-kernel.
 """
 
 from __future__ import annotations
@@ -68,16 +68,25 @@ def attention_reference(
     return out, lse
 
 
-def _fast_path_ok(q, k, causal, window_size, learnable_sink, softcap) -> bool:
-    if not q.is_cuda or q.dtype not in (torch.bfloat16, torch.float16):
-        return False
+_REFERENCE_SCORE_LIMIT = 1 << 22  # the fp32 oracle materialises [B,H,Sq,Sk]: test sizes only on a GPU
+
+
+def _library_path_ok(q: torch.Tensor, k: torch.Tensor, causal, window_size, learnable_sink, softcap) -> bool:
+    """Shapes / dtypes outside the native kernels (e.g. latent attention with different qk / v head sizes, fp16): plain or
+    causal attention goes to PyTorch SDPA (library flash kernels)."""
     if learnable_sink is not None or (softcap and softcap > 0):
         return False
     if window_size[0] is not None or window_size[1] is not None:
         return False
-    if causal and q.shape[1] != k.shape[1]:
-        return False
-    return True
+    return not (causal and q.shape[1] != k.shape[1])
+
+
+def _sdpa(q, k, v, softmax_scale, causal):
+    import torch.nn.functional as F
+
+    qh, kh, vh = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    out = F.scaled_dot_product_attention(qh, kh, vh, is_causal=causal, scale=softmax_scale, enable_gqa=qh.shape[1] != kh.shape[1])
+    return out.transpose(1, 2)
 
 
 def flash_attn_func(
@@ -94,16 +103,25 @@ def flash_attn_func(
     deterministic: bool = False,
     return_lse: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor | None]:
-    """Returns ``(output [B,S,H,Dv], lse [B,H,S] or None)``."""
-    del num_splits, pack_gqa, deterministic
-    if _fast_path_ok(q, k, causal, window_size, learnable_sink, softcap):
-        from .native import flash_attention, flash_attention_forward, native_forward_supported
+    """Returns ``(output [B,S,H,Dv], lse [B,H,S] or None)``.
 
-        needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
-        if return_lse and not needs_grad and native_forward_supported(q, k, v):
-            return flash_attention_forward(q, k, v, softmax_scale, causal)
-        if not return_lse:
-            return flash_attention(q, k, v, softmax_scale, causal), None
+    CUDA bf16 tensors with head size 64 / 128 run the native tcgen05 kernels (forward and backward, every option);
+    other CUDA inputs use SDPA for plain / causal attention and raise for options it cannot express - the fp32 oracle
+    (which materialises the score matrix) is only taken on CPU or for tiny problems.
+    """
+    del num_splits, pack_gqa, deterministic  # the native backward is atomic-free: always deterministic
+    if q.is_cuda:
+        from .native import flash_attention, native_supported
+
+        if native_supported(q, k, v):
+            out, lse = flash_attention(q, k, v, softmax_scale, causal, window_size, learnable_sink, softcap)
+            return out, (lse if return_lse else None)
+        if not return_lse and _library_path_ok(q, k, causal, window_size, learnable_sink, softcap):
+            return _sdpa(q, k, v, softmax_scale, causal), None
+        if q.shape[0] * q.shape[2] * q.shape[1] * k.shape[1] > _REFERENCE_SCORE_LIMIT:
+            raise NotImplementedError(
+                f"attention with dtype {q.dtype}, head sizes {q.shape[-1]}/{v.shape[-1]} and these options has no fused CUDA "
+                "path (native kernels: bf16, head size 64 or 128, equal qk / v head sizes)")
     out, lse = attention_reference(q, k, v, softmax_scale, causal, window_size, learnable_sink, softcap)
     return out, (lse if return_lse else None)
 
@@ -129,12 +147,25 @@ def flash_attn_varlen_func(
     deterministic: bool = False,
     return_lse: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor | None]:
-    """Packed variable-length attention: q ``[total_q, H, D]``, k/v ``[total_k, Hk, D]`` with ``cu_seqlens``."""
-    del max_seqlen_q, max_seqlen_k, num_splits, pack_gqa, deterministic
+    """Packed variable-length attention: q ``[total_q, H, D]``, k/v ``[total_k, Hk, D]`` with ``cu_seqlens``; the LSE is
+    ``[H, total_q]``.  On CUDA the sequence boundaries are resolved inside the kernels (no host synchronisation when
+    ``max_seqlen_q`` / ``max_seqlen_k`` are given)."""
+    del num_splits, pack_gqa, deterministic
     if page_table is not None or seqused_q is not None or seqused_k is not None:
         raise NotImplementedError("paged KV / seqused are not supported")
     if cu_seqlens_q is None or cu_seqlens_k is None:
         raise ValueError("cu_seqlens_q and cu_seqlens_k are required")
+    if q.is_cuda:
+        from .native import flash_attention, native_supported
+
+        if native_supported(q, k, v):
+            if max_seqlen_q is None:
+                max_seqlen_q = int((cu_seqlens_q[1:] - cu_seqlens_q[:-1]).max())
+            if max_seqlen_k is None:
+                max_seqlen_k = int((cu_seqlens_k[1:] - cu_seqlens_k[:-1]).max())
+            out, lse = flash_attention(q, k, v, softmax_scale, causal, window_size, learnable_sink, softcap, cu_seqlens_q,
+                                       cu_seqlens_k, max_seqlen_q, max_seqlen_k)
+            return out, (lse if return_lse else None)
     bq, bk = cu_seqlens_q.tolist(), cu_seqlens_k.tolist()
     outs, lses = [], []
     for i in range(len(bq) - 1):

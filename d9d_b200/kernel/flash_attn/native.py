@@ -1,11 +1,12 @@
-"""CUDA fast path for attention.
+"""CUDA path for attention: the hand-written tcgen05 flash-attention kernels (``ops/csrc/flash_attn.cu``).
 
-* forward-only work (inference, evaluation, ``torch.no_grad``): the hand-written tcgen05 flash-attention forward
-  (``ops/csrc/flash_attn_fwd.cu``: TMA-fed Q/K/V tiles, S and O accumulators in TMEM, online softmax in registers,
-  P·V straight from shared memory, GQA and causal masking, LSE output);
-* training: PyTorch SDPA (cuDNN flash kernels, library code) — the matching backward kernel is still to be written.
+Forward: two 128-row query tiles per CTA ping-ponged over one K/V ring, S and O accumulators in TMEM, P kept in tensor
+memory as the A operand of the second GEMM, lazy online-softmax rescaling, LSE out.  Backward: delta pre-pass, a dK/dV
+kernel (K,V resident, Q/dO streamed over the heads of the GQA group) and a dQ kernel (Q,dO resident, K/V streamed); no
+atomics.  Causal / sliding window (left, right) / soft-cap / attention sinks / packed variable-length batches are all
+handled inside the kernels.  There is no library (cuDNN / SDPA) call on this path.
 
-``D9D_NATIVE_ATTENTION=0`` forces the SDPA path everywhere.
+``D9D_FA_VARIANT=1`` stages P through shared memory instead of TMEM (debug / comparison).
 """
 
 from __future__ import annotations
@@ -14,29 +15,63 @@ import math
 import os
 
 import torch
-import torch.nn.functional as F
 
 from .._native import native_ops
 
 
-def native_forward_supported(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> bool:
+def native_supported(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> bool:
     return (q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
-            and q.dim() == 4 and q.shape[-1] in (64, 128) and v.shape[-1] == q.shape[-1] and q.shape[2] % k.shape[2] == 0
-            and os.environ.get("D9D_NATIVE_ATTENTION", "1") != "0")
+            and q.shape[-1] in (64, 128) and v.shape[-1] == q.shape[-1] and k.shape[-1] == q.shape[-1]
+            and q.shape[-2] % k.shape[-2] == 0)
 
 
-def flash_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: float | None, causal: bool
-                            ) -> tuple[torch.Tensor, torch.Tensor]:
-    """Forward only: ``(out [B,S,H,D], lse [B,H,S] fp32)`` from the native kernel."""
-    scale = softmax_scale if softmax_scale is not None else 1.0 / math.sqrt(q.shape[-1])
-    return native_ops().flash_attn_fwd(q.contiguous(), k.contiguous(), v.contiguous(), float(scale), bool(causal))
+def _window(causal: bool, window_size: tuple[int | None, int | None]) -> tuple[int, int]:
+    left, right = window_size
+    wl = left if left is not None and left >= 0 else -1
+    wr = 0 if causal else (right if right is not None and right >= 0 else -1)
+    return wl, wr
 
 
-def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: float | None, causal: bool) -> torch.Tensor:
-    """q: [B,S,H,D]; k/v: [B,S,Hk,D] -> [B,S,H,D]."""
-    needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
-    if not needs_grad and native_forward_supported(q, k, v):
-        return flash_attention_forward(q, k, v, softmax_scale, causal)[0]
-    qh, kh, vh = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
-    out = F.scaled_dot_product_attention(qh, kh, vh, is_causal=causal, scale=softmax_scale, enable_gqa=qh.shape[1] != kh.shape[1])
-    return out.transpose(1, 2)
+class _NativeFlashAttention(torch.autograd.Function):
+    """(q, k, v[, sink]) -> (out, lse); q/k/v are [B,S,H,D] or packed [total,H,D] with ``cu_seqlens``."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, sink, scale, wl, wr, softcap, cu_q, cu_k, max_q, max_k):
+        ops = native_ops()
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        sink32 = sink.detach().float().contiguous() if sink is not None else None
+        variant = int(os.environ.get("D9D_FA_VARIANT", "0"))
+        out, lse = ops.flash_attn_fwd(q, k, v, scale, wl, wr, softcap, sink32, cu_q, cu_k, max_q, max_k, variant)
+        ctx.save_for_backward(q, k, v, out, lse, sink, cu_q, cu_k)
+        ctx.cfg = (scale, wl, wr, softcap, max_q, max_k)
+        return out, lse
+
+    @staticmethod
+    def backward(ctx, dout, dlse):
+        q, k, v, out, lse, sink, cu_q, cu_k = ctx.saved_tensors
+        scale, wl, wr, softcap, max_q, max_k = ctx.cfg
+        if dout is None:
+            dout = torch.zeros_like(out)
+        dlse32 = dlse.float().contiguous() if dlse is not None else None
+        dq, dk, dv, delta = native_ops().flash_attn_bwd(dout.contiguous(), q, k, v, out, lse, scale, wl, wr, softcap, cu_q, cu_k,
+                                                        max_q, max_k, dlse32)
+        dsink = None
+        if sink is not None and ctx.needs_input_grad[3]:
+            # out_i = sum_j e^{a_ij} v_j / (L_i + e^s):  d/ds = -sum_{b,i} e^{s_h - lse} * (dout . out - dlse)
+            sink_col = sink.float()[:, None] if lse.dim() == 2 else sink.float()[None, :, None]
+            dsink = -(torch.exp(sink_col - lse) * delta).sum(dim=1 if lse.dim() == 2 else (0, 2)).to(sink.dtype)
+        return dq, dk, dv, dsink, None, None, None, None, None, None, None, None
+
+
+def flash_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: float | None, causal: bool,
+                    window_size: tuple[int | None, int | None] = (None, None), learnable_sink: torch.Tensor | None = None,
+                    softcap: float = 0.0, cu_seqlens_q: torch.Tensor | None = None, cu_seqlens_k: torch.Tensor | None = None,
+                    max_seqlen_q: int = 0, max_seqlen_k: int = 0) -> tuple[torch.Tensor, torch.Tensor]:
+    """``(out, lse)``; fixed-length: q ``[B,S,H,D]``, lse ``[B,H,S]``; packed: q ``[total,H,D]``, lse ``[H,total]``."""
+    scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(q.shape[-1])
+    wl, wr = _window(causal, window_size)
+    if cu_seqlens_q is not None:
+        cu_seqlens_q = cu_seqlens_q.to(device=q.device, dtype=torch.int32).contiguous()
+        cu_seqlens_k = cu_seqlens_k.to(device=q.device, dtype=torch.int32).contiguous()
+    return _NativeFlashAttention.apply(q, k, v, learnable_sink, scale, wl, wr, float(softcap or 0.0), cu_seqlens_q, cu_seqlens_k,
+                                       int(max_seqlen_q), int(max_seqlen_k))

@@ -337,20 +337,88 @@ void scale_inplace_(Tensor x, const Tensor& scale) {
 
 }  // namespace
 
-// ------------------------------------------------------------------ flash attention forward
-std::tuple<Tensor, Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, bool causal) {
+// ------------------------------------------------------------------ flash attention forward / backward
+// q [B, Sq, Hq, D] (or packed [total_q, Hq, D] with cu_seqlens), k / v likewise.  window_left / window_right: -1 = unbounded.
+static d9d::FlashAttnArgs fa_args(const Tensor& q, const Tensor& k, const Tensor& v, double scale, int64_t window_left,
+                                  int64_t window_right, double softcap, const c10::optional<Tensor>& sink,
+                                  const c10::optional<Tensor>& cu_q, const c10::optional<Tensor>& cu_k, int64_t max_q, int64_t max_k) {
   CHECK_CUDA_CONTIG(q); CHECK_CUDA_CONTIG(k); CHECK_CUDA_CONTIG(v);
-  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "flash_attn_fwd: [B, S, H, D] tensors expected");
-  TORCH_CHECK(q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16);
-  TORCH_CHECK(k.sizes() == v.sizes() && q.size(0) == k.size(0) && q.size(3) == k.size(3));
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16,
+              "flash_attn: bf16 tensors expected");
+  TORCH_CHECK(k.sizes() == v.sizes(), "flash_attn: k and v must have the same shape");
+  d9d::FlashAttnArgs a{};
+  a.q = q.data_ptr(); a.k = k.data_ptr(); a.v = v.data_ptr();
+  const bool varlen = cu_q.has_value();
+  TORCH_CHECK(varlen == cu_k.has_value(), "flash_attn: cu_seqlens_q and cu_seqlens_k go together");
+  if (varlen) {
+    TORCH_CHECK(q.dim() == 3 && k.dim() == 3, "flash_attn (varlen): [total, H, D] tensors expected");
+    TORCH_CHECK(cu_q->is_cuda() && cu_k->is_cuda() && cu_q->scalar_type() == at::kInt && cu_k->scalar_type() == at::kInt &&
+                cu_q->is_contiguous() && cu_k->is_contiguous() && cu_q->numel() == cu_k->numel() && cu_q->numel() >= 2,
+                "flash_attn (varlen): cu_seqlens must be int32 CUDA tensors of length B + 1");
+    a.B = static_cast<int>(cu_q->numel() - 1);
+    a.Sq = static_cast<int>(max_q); a.Sk = static_cast<int>(max_k);
+    a.total_q = q.size(0); a.total_k = k.size(0);
+    a.Hq = static_cast<int>(q.size(1)); a.Hk = static_cast<int>(k.size(1)); a.D = static_cast<int>(q.size(2));
+    TORCH_CHECK(k.size(2) == a.D);
+    a.cu_q = cu_q->data_ptr<int>(); a.cu_k = cu_k->data_ptr<int>();
+  } else {
+    TORCH_CHECK(q.dim() == 4 && k.dim() == 4, "flash_attn: [B, S, H, D] tensors expected");
+    TORCH_CHECK(q.size(0) == k.size(0) && q.size(3) == k.size(3));
+    a.B = static_cast<int>(q.size(0)); a.Sq = static_cast<int>(q.size(1)); a.Sk = static_cast<int>(k.size(1));
+    a.Hq = static_cast<int>(q.size(2)); a.Hk = static_cast<int>(k.size(2)); a.D = static_cast<int>(q.size(3));
+    a.total_q = static_cast<long long>(a.B) * a.Sq; a.total_k = static_cast<long long>(a.B) * a.Sk;
+  }
+  a.window_left = static_cast<int>(window_left); a.window_right = static_cast<int>(window_right);
+  a.scale = static_cast<float>(scale); a.softcap = static_cast<float>(softcap);
+  if (sink.has_value()) {
+    TORCH_CHECK(sink->is_cuda() && sink->scalar_type() == at::kFloat && sink->is_contiguous() && sink->numel() == a.Hq,
+                "flash_attn: sink must be a contiguous fp32 [Hq] CUDA tensor");
+    a.sink = sink->data_ptr<float>();
+  }
+  return a;
+}
+
+static Tensor fa_stats_like(const d9d::FlashAttnArgs& a, const Tensor& q) {
+  return a.cu_q != nullptr ? at::empty({a.Hq, a.total_q}, q.options().dtype(at::kFloat))
+                           : at::empty({a.B, a.Hq, a.Sq}, q.options().dtype(at::kFloat));
+}
+
+std::tuple<Tensor, Tensor> flash_attn_fwd(const Tensor& q, const Tensor& k, const Tensor& v, double scale, int64_t window_left,
+                                          int64_t window_right, double softcap, const c10::optional<Tensor>& sink,
+                                          const c10::optional<Tensor>& cu_q, const c10::optional<Tensor>& cu_k, int64_t max_q,
+                                          int64_t max_k, int64_t variant) {
   c10::cuda::CUDAGuard guard(q.device());
-  const int B = static_cast<int>(q.size(0)), Sq = static_cast<int>(q.size(1)), Hq = static_cast<int>(q.size(2)), D = static_cast<int>(q.size(3));
-  const int Sk = static_cast<int>(k.size(1)), Hk = static_cast<int>(k.size(2));
+  d9d::FlashAttnArgs a = fa_args(q, k, v, scale, window_left, window_right, softcap, sink, cu_q, cu_k, max_q, max_k);
   Tensor out = at::empty_like(q);
-  Tensor lse = at::empty({B, Hq, Sq}, q.options().dtype(at::kFloat));
-  d9d::flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), B, Sq, Sk, Hq, Hk, D,
-                      static_cast<float>(scale), causal, cur_stream());
+  Tensor lse = fa_stats_like(a, q);
+  a.out = out.data_ptr();
+  a.lse = lse.data_ptr<float>();
+  d9d::flash_attn_fwd(a, static_cast<int>(variant), cur_stream());
   return {out, lse};
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor> flash_attn_bwd(const Tensor& dout, const Tensor& q, const Tensor& k, const Tensor& v,
+                                                          const Tensor& out, const Tensor& lse, double scale, int64_t window_left,
+                                                          int64_t window_right, double softcap, const c10::optional<Tensor>& cu_q,
+                                                          const c10::optional<Tensor>& cu_k, int64_t max_q, int64_t max_k,
+                                                          const c10::optional<Tensor>& dlse) {
+  c10::cuda::CUDAGuard guard(q.device());
+  CHECK_CUDA_CONTIG(dout); CHECK_CUDA_CONTIG(out); CHECK_CUDA_CONTIG(lse);
+  TORCH_CHECK(dout.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16 && lse.scalar_type() == at::kFloat);
+  TORCH_CHECK(dout.sizes() == q.sizes() && out.sizes() == q.sizes(), "flash_attn_bwd: dout / out must match q");
+  d9d::FlashAttnArgs a = fa_args(q, k, v, scale, window_left, window_right, softcap, c10::nullopt, cu_q, cu_k, max_q, max_k);
+  Tensor delta = fa_stats_like(a, q);
+  TORCH_CHECK(lse.numel() == delta.numel(), "flash_attn_bwd: lse has the wrong shape");
+  Tensor dq = at::empty_like(q), dk = at::empty_like(k), dv = at::empty_like(v);
+  a.out = out.data_ptr();
+  a.dout = dout.data_ptr();
+  a.lse = lse.data_ptr<float>();
+  a.delta = delta.data_ptr<float>();
+  a.dq = dq.data_ptr(); a.dk = dk.data_ptr(); a.dv = dv.data_ptr();
+  d9d::flash_attn_bwd_delta(a, cur_stream());
+  if (dlse.has_value()) delta.sub_(dlse->reshape(delta.sizes()));  // d(lse)/dS = P folds into the row statistic
+  d9d::flash_attn_bwd(a, cur_stream());
+  return {dq, dk, dv, delta};
 }
 
 // ------------------------------------------------------------------ fused q/k RMSNorm + RoPE
@@ -605,7 +673,8 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_permute(Tensor x, Tensor? probs, Tensor row_map, Tensor counts, Tensor seg_offsets, int capacity) -> (Tensor, Tensor)");
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
-  m.def("flash_attn_fwd(Tensor q, Tensor k, Tensor v, float scale, bool causal) -> (Tensor, Tensor)");
+  m.def("flash_attn_fwd(Tensor q, Tensor k, Tensor v, float scale, int window_left, int window_right, float softcap, Tensor? sink, Tensor? cu_q, Tensor? cu_k, int max_q, int max_k, int variant) -> (Tensor, Tensor)");
+  m.def("flash_attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, float scale, int window_left, int window_right, float softcap, Tensor? cu_q, Tensor? cu_k, int max_q, int max_k, Tensor? dlse) -> (Tensor, Tensor, Tensor, Tensor)");
   m.def("qk_norm_rope_fwd(Tensor q, Tensor k, Tensor wq, Tensor wk, Tensor cos_t, Tensor sin_t, float eps, bool zero_centered, "
         "int style) -> (Tensor, Tensor, Tensor)");
   m.def("qk_norm_rope_bwd(Tensor dq_out, Tensor dk_out, Tensor q, Tensor k, Tensor wq, Tensor wk, Tensor cos_t, Tensor sin_t, "
@@ -648,6 +717,7 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("moe_gather", &moe_gather);
   m.impl("sumsq_accumulate_", &sumsq_accumulate_);
   m.impl("flash_attn_fwd", &flash_attn_fwd);
+  m.impl("flash_attn_bwd", &flash_attn_bwd);
   m.impl("qk_norm_rope_fwd", &qk_norm_rope_fwd);
   m.impl("qk_norm_rope_bwd", &qk_norm_rope_bwd);
   m.impl("router_topk_fwd", &router_topk_fwd);

@@ -125,10 +125,32 @@ void sumsq_accumulate(const void* x, long long n, int dtype, float* out, cudaStr
 // x *= *scale (device scalar)
 void scale_inplace(void* x, long long n, int dtype, const float* scale, cudaStream_t stream);
 
-// ------------------------------------------------------------------ flash attention (forward) -------------
-// q [B, Sq, Hq, D], k / v [B, Sk, Hk, D], out [B, Sq, Hq, D] bf16 (contiguous); lse [B, Hq, Sq] fp32 or null
-void flash_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Sk, int Hq, int Hk,
-                    int D, float scale, bool causal, cudaStream_t stream);
+// ------------------------------------------------------------------ flash attention (forward / backward) --
+// q / out / dout / dq [total_q, Hq, D], k / v / dk / dv [total_k, Hk, D] bf16 contiguous, where total = B * S for
+// fixed-length batches (cu_q == cu_k == nullptr) or the packed token count (cu_q / cu_k: [B + 1] int32 device arrays, Sq /
+// Sk = maximum sequence lengths).  lse / delta: fp32 [B, Hq, Sq] (packed: [Hq, total_q]).
+// window: key k is visible to query q iff q + (Sk - Sq) - window_left <= k <= q + (Sk - Sq) + window_right (-1 = unbounded;
+// causal = window_right 0).  softcap 0 = off.  sink: per-head logit joining the softmax denominator (or nullptr).
+struct FlashAttnArgs {
+  const void *q, *k, *v;
+  void* out;            // forward: written; backward: read
+  float* lse;           // forward: written; backward: read
+  const void* dout;     // backward
+  float* delta;         // backward scratch (written)
+  void *dq, *dk, *dv;   // backward outputs
+  const float* sink;
+  const int *cu_q, *cu_k;
+  int B, Sq, Sk, Hq, Hk, D;
+  long long total_q, total_k;
+  int window_left, window_right;
+  float scale, softcap;
+};
+// variant 0: P kept in tensor memory (A operand of the PV GEMM read from TMEM); 1: P staged through shared memory
+void flash_attn_fwd(const FlashAttnArgs& a, int variant, cudaStream_t stream);
+// backward = delta pre-pass (delta[b,h,q] = sum_d dO*O, written to a.delta) followed by the dK/dV and dQ kernels (which read
+// a.delta; the caller may subtract d(lse) from it in between)
+void flash_attn_bwd_delta(const FlashAttnArgs& a, cudaStream_t stream);
+void flash_attn_bwd(const FlashAttnArgs& a, cudaStream_t stream);
 
 // ------------------------------------------------------------------ fused q/k RMSNorm + RoPE -------------
 // q [T, Hq, D] (row stride ldq), k [T, Hk, D] (row stride ldk), cos/sin [T, rope_dim] fp32 (already gathered per token)
