@@ -43,7 +43,7 @@ for (B, S, Hq, Hk, D, causal) in shapes:
     flops = 4.0 * B * Hq * S * S * D * (0.5 if causal else 1.0)
     wr = 0 if causal else -1
     row = {"B": B, "S": S, "Hq": Hq, "Hk": Hk, "D": D, "causal": causal}
-    for variant, name in ((0, "native_fwd_ptmem"), (1, "native_fwd_psmem")):
+    for variant, name in ((0, "native_fwd"),):
         try:
             t = timeit(lambda: ops.flash_attn_fwd(q, k, v, D ** -0.5, -1, wr, 0.0, None, None, None, 0, 0, variant))
             row[name + "_ms"], row[name + "_tflops"] = t, flops / t / 1e9

@@ -18,7 +18,7 @@ def main() -> None:
     from d9d_b200.kernel.flash_attn import flash_attn_func
 
     _ops.load()
-    for variant in ([int(sys.argv[1])] if len(sys.argv) > 1 else [0, 1]):
+    for variant in ([int(sys.argv[1])] if len(sys.argv) > 1 else [0]):
         os.environ["D9D_FA_VARIANT"] = str(variant)
         for case in CASES:
             B, Sq, Sk, Hq, Hk, D, causal, window, use_sink, softcap = case

@@ -6,13 +6,11 @@ kernel (K,V resident, Q/dO streamed over the heads of the GQA group) and a dQ ke
 atomics.  Causal / sliding window (left, right) / soft-cap / attention sinks / packed variable-length batches are all
 handled inside the kernels.  There is no library (cuDNN / SDPA) call on this path.
 
-``D9D_FA_VARIANT=1`` stages P through shared memory instead of TMEM (debug / comparison).
 """
 
 from __future__ import annotations
 
 import math
-import os
 
 import torch
 
@@ -40,8 +38,7 @@ class _NativeFlashAttention(torch.autograd.Function):
         ops = native_ops()
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         sink32 = sink.detach().float().contiguous() if sink is not None else None
-        variant = int(os.environ.get("D9D_FA_VARIANT", "0"))
-        out, lse = ops.flash_attn_fwd(q, k, v, scale, wl, wr, softcap, sink32, cu_q, cu_k, max_q, max_k, variant)
+        out, lse = ops.flash_attn_fwd(q, k, v, scale, wl, wr, softcap, sink32, cu_q, cu_k, max_q, max_k, 0)
         ctx.save_for_backward(q, k, v, out, lse, sink, cu_q, cu_k)
         ctx.cfg = (scale, wl, wr, softcap, max_q, max_k)
         return out, lse

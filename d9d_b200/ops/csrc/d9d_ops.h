@@ -145,7 +145,7 @@ struct FlashAttnArgs {
   int window_left, window_right;
   float scale, softcap;
 };
-// variant 0: P kept in tensor memory (A operand of the PV GEMM read from TMEM); 1: P staged through shared memory
+// variant: reserved (P is kept in tensor memory: the A operand of the PV GEMM is read from TMEM)
 void flash_attn_fwd(const FlashAttnArgs& a, int variant, cudaStream_t stream);
 // backward = delta pre-pass (delta[b,h,q] = sum_d dO*O, written to a.delta) followed by the dK/dV and dQ kernels (which read
 // a.delta; the caller may subtract d(lse) from it in between)

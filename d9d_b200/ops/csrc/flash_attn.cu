@@ -8,23 +8,24 @@
 // no transposes, TMA 3-D maps (d, h, row) with 128B swizzle.  LSE / delta are fp32 [B, H, S] (packed: [H, total]).
 //
 // Forward (flash_attn_fwd_kernel): one CTA owns TWO consecutive 128-row query tiles of one (batch, head).
-//   warps 0-3 / 4-7  softmax warpgroup of query tile 0 / 1 (thread = query row): S row TMEM -> registers, online softmax
-//                    with lazy rescaling (O is only rescaled when the running max grows by more than 2^8), P written back
-//                    as bf16 INTO THE S COLUMNS OF TMEM and consumed from there by the second GEMM (A operand from
-//                    tensor memory) - or staged through swizzled shared memory in the P_SMEM variant
+//   warps 0-3 / 4-7  softmax warpgroup of query tile 0 / 1 (thread = query row): S row TMEM -> registers (the S columns are
+//                    handed back to the tensor core at once), online softmax with lazy rescaling (O is only rescaled when
+//                    the running max grows by more than 2^8), P (bf16) into 128B-swizzled shared memory
 //   warp 8           TMA producer: Q0, Q1 once, then K_j, V_j tiles through one ring
-//   warp 9           MMA issuer, ping-pong order  PV0(j) | S0(j+1) | PV1(j) | S1(j+1): while one warpgroup evaluates
-//                    exponentials the tensor core works for the other query tile
+//   warp 9           MMA issuer: S_w(j+1) = Q_w K_{j+1}^T is issued as soon as S_w(j) has been pulled into registers, so the
+//                    next score tile is computed while the exponentials of the current one are evaluated; O_w += P_w V_j
+//                    follows when P_w(j) is complete and runs under the softmax of j+1
 //   TMEM: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D)
 //
 // Backward = delta pre-pass + two tcgen05 kernels built from one template (no atomics, deterministic):
 //   DKV: CTA owns a 128-key tile of one kv head, keeps K,V resident, streams 64-row Q/dO half-tiles of every query
-//        head of the group:  S^T = K Q^T, dP^T = V dO^T (thread = key row)  ->  P^T, dS^T (bf16, smem)  ->
-//        dV += P^T dO, dK += dS^T Q   accumulated in TMEM over the whole loop.
+//        head of the group:  S^T = K Q^T, dP^T = V dO^T (two threads per key row)  ->  P^T, dS^T as bf16 written back INTO
+//        THE SAME TMEM COLUMNS  ->  dV += P^T dO, dK += dS^T Q with the A operand read from tensor memory, accumulated in
+//        TMEM over the whole loop.
 //   DQ : CTA owns a 128-row query tile of one head, keeps Q,dO resident, streams 64-key K/V half-tiles:
-//        S = Q K^T, dP = dO V^T (thread = query row) -> dS -> dQ += dS K.
-//   Two softmax warpgroups alternate half-tiles (S/dP double-buffered in TMEM), so MMAs of half-tile t+1 overlap the
-//   exponentials of half-tile t.   TMEM: S[u] u*64, dP[u] 128+u*64, acc1 [256,256+D), acc2 [256+D,256+2D).
+//        S = Q K^T, dP = dO V^T (two threads per query row) -> dS (TMEM) -> dQ += dS K.
+//   Two groups of 8 softmax warps alternate half-tiles (S/dP double-buffered in TMEM), so the MMAs of half-tile t+1 overlap
+//   the exponentials of half-tile t.   TMEM: S[u] u*64, dP[u] 128+u*64, acc1 [256,256+D), acc2 [256+D,256+2D).
 //
 // Reference parity: d9d/kernel/flash_attn/function.py:72-178 (fwd/bwd, sink gradient), :181-305 (varlen).
 #include <stdexcept>
@@ -76,19 +77,11 @@ __device__ __forceinline__ SeqInfo resolve_seq(const FaParams& p, int b) {
   return s;
 }
 
-// K-major operand made of 64-element boxes [rows x 128 B] (box stride rows*128), 128B swizzle; kk = UMMA_K step (16 elems)
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int rows, int kk) {
-  return make_smem_desc_sw128(base + (kk >> 2) * (rows * 128) + (kk & 3) * 32, 16, 1024);
+__device__ __forceinline__ float4 lds_f4(const float* smem_ptr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(smem_ptr)));
+  return v;
 }
-// MN-major B operand: tile [krows][N] stored as N/64 boxes [krows x 128 B]; kk steps over 16 rows of the K dimension
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int krows, int kk) {
-  return make_smem_desc_sw128(base + kk * (16 * 128), krows * 128, 1024);
-}
-
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
 
 // one bf16 row chunk (8 elements, 16 B) into a [rows x 128 B] 128B-swizzled box
 __device__ __forceinline__ void st_swizzled_16B(uint8_t* box, int row, int chunk, uint4 v) {
@@ -98,34 +91,70 @@ __device__ __forceinline__ void st_swizzled_16B(uint8_t* box, int row, int chunk
 // ======================================================================================================
 // forward
 // ======================================================================================================
-constexpr int FWD_THREADS = 384;  // warps 10-11 idle: they complete the third warpgroup so setmaxnreg can rebalance registers
+constexpr int FWD_THREADS = 384;  // warps 0-3 / 4-7: softmax of query tile 0 / 1, 8: TMA producer, 9: MMA issuer, 10-11: idle
+                                  // (they complete the third warpgroup so that setmaxnreg can move registers to the softmax warps)
 
-template <int D, bool P_TMEM>
+// Shared-memory descriptors are built once per operand (low word) and advanced by adding (byte offset >> 4): two integer
+// adds per tcgen05.mma instead of re-deriving the full 64-bit descriptor.
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+      : "memory");
+}
+// offset (in 16-byte units) of UMMA_K step kk inside a K-major operand made of [rows x 128 B] boxes / an MN-major one
+__device__ __forceinline__ constexpr uint32_t koff_kmajor(int rows, int kk) { return ((kk >> 2) * (rows * 128) + (kk & 3) * 32) >> 4; }
+__device__ __forceinline__ constexpr uint32_t koff_mnmajor(int kk) { return (kk * 16 * 128) >> 4; }
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
+
+template <int D>
 struct FwdCfg {
   static constexpr int TILE_BYTES = 128 * D * 2;
-  static constexpr int NSLOT = P_TMEM ? 4 : 3;
-  static constexpr int P_BYTES = P_TMEM ? 0 : 2 * 128 * 128 * 2;
+  static constexpr int NSLOT = 3;                       // K_j, V_j, K_{j+1}, ... through one ring
+  static constexpr int P_BYTES = 2 * 128 * 128 * 2;     // P of both query tiles (bf16, 128B-swizzled K-major)
   static constexpr int SMEM_BYTES = 2 * TILE_BYTES + NSLOT * TILE_BYTES + P_BYTES + 1024 + 256;
 };
 
-template <int D, bool P_TMEM>
+// Schedule.  S_w(j+1) is issued as soon as the softmax warps of tile w have pulled S_w(j) into registers (s_free), so the
+// next score tile is computed WHILE the exponentials of the current one are evaluated and a warpgroup goes from one
+// softmax straight into the next; P travels through shared memory (the S columns of TMEM are free again right away),
+// PV_w(j) is issued when P_w(j) is complete and runs under the softmax of j+1 (o_done orders it before the next P write /
+// O rescale).
+template <int D>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const __grid_constant__ CUtensorMap tmap_v, const FaParams p) {
-  using C = FwdCfg<D, P_TMEM>;
+  using C = FwdCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                                // [2][TILE]
-  uint8_t* smem_ring = smem_q + 2 * C::TILE_BYTES;       // [NSLOT][TILE]
-  uint8_t* smem_p = smem_ring + C::NSLOT * C::TILE_BYTES;  // [2][128x128 bf16] (P_SMEM variant only)
+  uint8_t* smem_q = smem;                                  // [2][TILE]
+  uint8_t* smem_ring = smem_q + 2 * C::TILE_BYTES;         // [NSLOT][TILE]
+  uint8_t* smem_p = smem_ring + C::NSLOT * C::TILE_BYTES;  // [2][128x128 bf16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + C::P_BYTES);
   uint64_t* bar_q = bars;            // 1
-  uint64_t* ring_full = bars + 1;    // [4]
-  uint64_t* ring_empty = bars + 5;   // [4]
-  uint64_t* s_full = bars + 9;       // [2]
-  uint64_t* p_ready = bars + 11;     // [2]
-  uint64_t* o_final = bars + 13;     // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* ring_full = bars + 1;    // [3]
+  uint64_t* ring_empty = bars + 4;   // [3]
+  uint64_t* s_full = bars + 7;       // [2]  S_w complete (tcgen05.commit)
+  uint64_t* s_free = bars + 9;       // [2]  S_w pulled into registers by its 4 softmax warps
+  uint64_t* p_ready = bars + 11;     // [2]  P_w written to shared memory
+  uint64_t* o_done = bars + 13;      // [2]  PV_w complete (tcgen05.commit)
+  uint64_t* o_final = bars + 15;     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int h = blockIdx.y, b = blockIdx.z;
@@ -157,8 +186,10 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_final[i], 1); }
+    for (int i = 0; i < C::NSLOT; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); mbar_init(&p_ready[i], 4); mbar_init(&o_done[i], 1); mbar_init(&o_final[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<512>(tmem_ptr_smem);
@@ -166,95 +197,102 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  // register rebalancing: the producer / MMA warpgroup keeps 56 registers, the two softmax warpgroups get 224
+
   if (warp >= 8) {
     setmaxnreg_dec<56>();
     if (warp == 8) {
-    // ================= TMA producer =================
-    if (elect_one()) {
-      const int nq = (q0 + 128 < sq.Sq) ? 2 : 1;
-      mbar_arrive_expect_tx(bar_q, nq * C::TILE_BYTES);
-      for (int w = 0; w < nq; ++w)
-#pragma unroll
-        for (int dc = 0; dc < D / 64; ++dc)
-          tma_load_3d(smem_q + w * C::TILE_BYTES + dc * (128 * 128), &tmap_q, bar_q, dc * 64, h, sq.q_start + q0 + w * 128);
-      int n = 0;
-      for (int j = jbeg; j < jend; ++j) {
-#pragma unroll
-        for (int kv = 0; kv < 2; ++kv, ++n) {
-          const int slot = n % C::NSLOT;
-          mbar_wait(&ring_empty[slot], ((n / C::NSLOT) & 1) ^ 1);
-          mbar_arrive_expect_tx(&ring_full[slot], C::TILE_BYTES);
+      // ================= TMA producer =================
+      if (elect_one()) {
+        const int nq = (q0 + 128 < sq.Sq) ? 2 : 1;
+        mbar_arrive_expect_tx(bar_q, nq * C::TILE_BYTES);
+        for (int w = 0; w < nq; ++w)
 #pragma unroll
           for (int dc = 0; dc < D / 64; ++dc)
-            tma_load_3d(smem_ring + slot * C::TILE_BYTES + dc * (128 * 128), kv == 0 ? &tmap_k : &tmap_v, &ring_full[slot],
-                        dc * 64, hk, sq.k_start + j * 128);
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, D, false, true);
-    auto act = [&](int w, int j) { return j >= jlo[w] && j < jhi[w]; };
-    auto ring_wait = [&](int n) { mbar_wait(&ring_full[n % C::NSLOT], (n / C::NSLOT) & 1); tc_fence_after(); };
-    auto issue_s = [&](int w, int j) {  // S_w = Q_w K_j^T
-      if (elect_one()) {
-        const uint32_t qa = smem_u32(smem_q + w * C::TILE_BYTES);
-        const uint32_t ka = smem_u32(smem_ring + ((2 * (j - jbeg)) % C::NSLOT) * C::TILE_BYTES);
+            tma_load_3d(smem_q + w * C::TILE_BYTES + dc * (128 * 128), &tmap_q, bar_q, dc * 64, h, sq.q_start + q0 + w * 128);
+        int n = 0;
+        for (int j = jbeg; j < jend; ++j) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tmem_base + w * 128, desc_kmajor(qa, 128, kk), desc_kmajor(ka, 128, kk), idesc_s, kk != 0);
-        umma_commit(&s_full[w]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int w, int j, int it) {  // O_w += P_w V_j
-      mbar_wait(&p_ready[w], it & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t va = smem_u32(smem_ring + ((2 * (j - jbeg) + 1) % C::NSLOT) * C::TILE_BYTES);
-        const uint32_t tmem_o = tmem_base + 256 + w * D;
+          for (int kv = 0; kv < 2; ++kv, ++n) {
+            const int slot = n % C::NSLOT;
+            mbar_wait(&ring_empty[slot], ((n / C::NSLOT) & 1) ^ 1);
+            mbar_arrive_expect_tx(&ring_full[slot], C::TILE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 128 / 16; ++kk) {
-          if constexpr (P_TMEM) {
-            umma_f16_ts(tmem_o, tmem_base + w * 128 + kk * 8, desc_mnmajor(va, 128, kk), idesc_o, (it | kk) != 0);
-          } else {
-            umma_f16(tmem_o, desc_kmajor(smem_u32(smem_p + w * (128 * 128 * 2)), 128, kk), desc_mnmajor(va, 128, kk), idesc_o,
-                     (it | kk) != 0);
+            for (int dc = 0; dc < D / 64; ++dc)
+              tma_load_3d(smem_ring + slot * C::TILE_BYTES + dc * (128 * 128), kv == 0 ? &tmap_k : &tmap_v, &ring_full[slot],
+                          dc * 64, hk, sq.k_start + j * 128);
           }
         }
-        if (j == jhi[w] - 1) umma_commit(&o_final[w]);
       }
-      __syncwarp();
-    };
-    auto release = [&](int n) {
-      if (elect_one()) umma_commit(&ring_empty[n % C::NSLOT]);
-      __syncwarp();
-    };
-    if (jend > jbeg) {
-      mbar_wait(bar_q, 0);
-      ring_wait(0);
-      if (act(0, jbeg)) issue_s(0, jbeg);
-      if (act(1, jbeg)) issue_s(1, jbeg);
-      release(0);
-      int it0 = 0, it1 = 0;
-      for (int j = jbeg; j < jend; ++j) {
-        const int n = 2 * (j - jbeg);
-        ring_wait(n + 1);  // V_j
-        if (act(0, j)) issue_pv(0, j, it0++);
-        if (j + 1 < jend) {
-          ring_wait(n + 2);  // K_{j+1}
-          if (act(0, j + 1)) issue_s(0, j + 1);
+    } else if (warp == 9) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, D, false, true);
+      auto act = [&](int w, int j) { return j >= jlo[w] && j < jhi[w]; };
+      auto ring_wait = [&](int n) { mbar_wait(&ring_full[n % C::NSLOT], (n / C::NSLOT) & 1); tc_fence_after(); };
+      auto release = [&](int n) {
+        if (elect_one()) umma_commit(&ring_empty[n % C::NSLOT]);
+        __syncwarp();
+      };
+      auto issue_s = [&](int w, int n) {  // S_w = Q_w K^T, K tile in ring slot n % NSLOT
+        if (elect_one()) {
+          const uint32_t qa = desc_lo(smem_u32(smem_q + w * C::TILE_BYTES), 16);
+          const uint32_t ka = desc_lo(smem_u32(smem_ring + (n % C::NSLOT) * C::TILE_BYTES), 16);
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk)
+            umma_lo(tmem_base + w * 128, qa + koff_kmajor(128, kk), ka + koff_kmajor(128, kk), idesc_s, kk != 0);
+          umma_commit(&s_full[w]);
         }
-        if (act(1, j)) issue_pv(1, j, it1++);
-        release(n + 1);
-        if (j + 1 < jend) {
-          if (act(1, j + 1)) issue_s(1, j + 1);
-          release(n + 2);
+        __syncwarp();
+      };
+      auto issue_pv = [&](int w, int n, int it, bool last) {  // O_w += P_w V, V tile in ring slot n % NSLOT
+        if (elect_one()) {
+          const uint32_t pa = desc_lo(smem_u32(smem_p + w * (128 * 128 * 2)), 16);
+          const uint32_t va = desc_lo(smem_u32(smem_ring + (n % C::NSLOT) * C::TILE_BYTES), 128 * 128);
+#pragma unroll
+          for (int kk = 0; kk < 128 / 16; ++kk)
+            umma_lo(tmem_base + 256 + w * D, pa + koff_kmajor(128, kk), va + koff_mnmajor(kk), idesc_o, (it | kk) != 0);
+          umma_commit(&o_done[w]);
+          if (last) umma_commit(&o_final[w]);
+        }
+        __syncwarp();
+      };
+      if (jend > jbeg) {
+        mbar_wait(bar_q, 0);
+        ring_wait(0);
+        if (act(0, jbeg)) issue_s(0, 0);
+        if (act(1, jbeg)) issue_s(1, 0);
+        release(0);
+        int it0 = 0, it1 = 0;
+        for (int j = jbeg; j < jend; ++j) {
+          const int n = 2 * (j - jbeg);
+          if (j + 1 < jend) {
+            ring_wait(n + 2);  // K_{j+1}
+            if (act(0, j + 1)) {
+              if (act(0, j)) { mbar_wait(&s_free[0], it0 & 1); tc_fence_after(); }
+              issue_s(0, n + 2);
+            }
+            if (act(1, j + 1)) {
+              if (act(1, j)) { mbar_wait(&s_free[1], it1 & 1); tc_fence_after(); }
+              issue_s(1, n + 2);
+            }
+            release(n + 2);
+          }
+          ring_wait(n + 1);  // V_j
+          if (act(0, j)) {
+            mbar_wait(&p_ready[0], it0 & 1);
+            tc_fence_after();
+            issue_pv(0, n + 1, it0, j == jhi[0] - 1);
+            ++it0;
+          }
+          if (act(1, j)) {
+            mbar_wait(&p_ready[1], it1 & 1);
+            tc_fence_after();
+            issue_pv(1, n + 1, it1, j == jhi[1] - 1);
+            ++it1;
+          }
+          release(n + 1);
         }
       }
-    }
     }
   } else {
     setmaxnreg_inc<224>();
@@ -273,8 +311,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const float cap_in = capped ? p.scale / p.softcap : 0.f;
     float m_used = -INFINITY, l = 0.f;
     for (int it = 0; it < n_it; ++it) {
-      const int j = jlo[w] + it;
-      const int k0 = j * 128;
+      const int k0 = (jlo[w] + it) * 128;
       mbar_wait(&s_full[w], it & 1);
       tc_fence_after();
       uint32_t s[128];
@@ -284,16 +321,24 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         tmem_ld_32x32b_x32(tmem_s + c * 32, chunk);
       }
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[w]);  // the tensor core may overwrite S_w with the next score tile
       if (capped) {
 #pragma unroll
         for (int i = 0; i < 128; ++i) s[i] = __float_as_uint(p.softcap * tanhf(__uint_as_float(s[i]) * cap_in));
       }
-      // boundary tiles only: out-of-window / out-of-sequence keys -> -inf (warp-uniform branch)
-      const bool edge = (k0 < k_lo) || (k0 + 127 > k_hi);
-      if (__any_sync(0xffffffffu, edge)) {
+      // boundary tiles only: out-of-window / out-of-sequence keys -> -inf (warp-uniform branches)
+      const int hi_rel = k_hi - k0, lo_rel = k_lo - k0;
+      if (__any_sync(0xffffffffu, hi_rel < 127)) {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
-          if (k0 + i < k_lo || k0 + i > k_hi) s[i] = __float_as_uint(-INFINITY);
+          if (i > hi_rel) s[i] = __float_as_uint(-INFINITY);
+      }
+      if (__any_sync(0xffffffffu, lo_rel > 0)) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i < lo_rel) s[i] = __float_as_uint(-INFINITY);
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -311,44 +356,40 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         l *= alpha;
         m_used = m_new;
       }
-      if (it > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        // PV(it-1) has completed: S(it) was issued after it and tcgen05 operations complete in order
+      if (it > 0) {
+        // PV_w(it-1) reads P_w from shared memory and accumulates into O_w: it must be complete before either is touched
+        mbar_wait(&o_done[w], (it - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < D / 16; ++c) {  // 16 columns at a time: the S row stays live in registers
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(tmem_o + c * 16, o);
+            tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(tmem_o + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(tmem_o + c * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x16(tmem_o + c * 16, o);
+          }
+          tmem_st_wait();
         }
       }
       const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used;
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t packed[16];
+      for (int c = 0; c < 16; ++c) {  // 8 keys = one 16-byte chunk of the swizzled P row
+        uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(fmaf(__uint_as_float(s[c * 32 + i]), scale_eff, neg_m));
-          const float p1 = exp2f(fmaf(__uint_as_float(s[c * 32 + i + 1]), scale_eff, neg_m));
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = exp2f(fmaf(__uint_as_float(s[c * 8 + 2 * e]), scale_eff, neg_m));
+          const float p1 = exp2f(fmaf(__uint_as_float(s[c * 8 + 2 * e + 1]), scale_eff, neg_m));
           sum0 += p0;
           sum1 += p1;
-          packed[i >> 1] = pack_bf16x2(p0, p1);
+          pk[e] = pack_bf16x2(p0, p1);
         }
-        if constexpr (P_TMEM) {
-          tmem_st_32x32b_x16(tmem_s + c * 16, packed);
-        } else {
-          uint8_t* box = smem_p + w * (128 * 128 * 2) + (c >> 1) * (128 * 128);
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            st_swizzled_16B(box, row, (c & 1) * 4 + q4,
-                            make_uint4(packed[4 * q4], packed[4 * q4 + 1], packed[4 * q4 + 2], packed[4 * q4 + 3]));
-        }
+        st_swizzled_16B(smem_p + w * (128 * 128 * 2) + (c >> 3) * (128 * 128), row, c & 7, make_uint4(pk[0], pk[1], pk[2], pk[3]));
       }
       l += sum0 + sum1;
-      tmem_st_wait();
-      if constexpr (!P_TMEM) fence_proxy_async_smem();
+      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[w]);
@@ -400,19 +441,33 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 // ======================================================================================================
 // backward
 // ======================================================================================================
-constexpr int BWD_THREADS = 384;
-constexpr int BWD_NST = 3;
+constexpr int BWD_THREADS = 576;  // 16 softmax warps + TMA producer + MMA issuer
+constexpr int BWD_NST = 4;        // streamed half-tile ring depth
+
+__device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+      : "memory");
+}
 
 template <int D, bool DKV>
 struct BwdCfg {
   static constexpr int RES_BYTES = 128 * D * 2;       // one resident tile
   static constexpr int STR_BYTES = 64 * D * 2;        // one streamed half-tile
-  static constexpr int PD_BYTES = 128 * 64 * 2;       // one P^T / dS^T buffer
-  static constexpr int N_PD = DKV ? 4 : 2;
   static constexpr int VEC_BYTES = DKV ? BWD_NST * 2 * 64 * 4 : 0;
-  static constexpr int SMEM_BYTES = 2 * RES_BYTES + BWD_NST * 2 * STR_BYTES + N_PD * PD_BYTES + VEC_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = 2 * RES_BYTES + BWD_NST * 2 * STR_BYTES + VEC_BYTES + 1024 + 256;
 };
 
+// P^T / dS^T (DKV) resp. dS (DQ) never touch shared memory: each softmax thread writes its bf16 values back into the TMEM
+// columns its fp32 S / dP values came from, and the accumulating GEMMs read their A operand from tensor memory.
+//   packed column of streamed index c (0..63) inside the 64-column buffer:  (c / 32) * 32 + (c % 32) / 2
 template <int D, bool DKV>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_constant__ CUtensorMap tmap_r2,
@@ -424,15 +479,13 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
   uint8_t* smem_r1 = smem;
   uint8_t* smem_r2 = smem_r1 + C::RES_BYTES;
   uint8_t* smem_s = smem_r2 + C::RES_BYTES;                      // [NST][s1 | s2]
-  uint8_t* smem_pd = smem_s + BWD_NST * 2 * C::STR_BYTES;        // DKV: [u][P^T | dS^T]; DQ: [u][dS]
-  float* smem_vec = reinterpret_cast<float*>(smem_pd + C::N_PD * C::PD_BYTES);  // DKV: [NST][lse2(64) | delta(64)]
+  float* smem_vec = reinterpret_cast<float*>(smem_s + BWD_NST * 2 * C::STR_BYTES);  // DKV: [NST][lse2(64) | delta(64)]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_vec) + C::VEC_BYTES);
   uint64_t* r_full = bars;          // 1
-  uint64_t* st_full = bars + 1;     // [3]
-  uint64_t* st_empty = bars + 4;    // [3]
-  uint64_t* sp_full = bars + 7;     // [2]
-  uint64_t* pd_ready = bars + 9;    // [2]
-  uint64_t* pd_free = bars + 11;    // [2]
+  uint64_t* st_full = bars + 1;     // [NST]
+  uint64_t* st_empty = bars + 5;    // [NST]
+  uint64_t* sp_full = bars + 9;     // [2]  S / dP of buffer u complete
+  uint64_t* pd_ready = bars + 11;   // [2]  bf16 P^T / dS^T of buffer u written back to TMEM
   uint64_t* acc_done = bars + 13;   // 1
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
@@ -460,26 +513,25 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
   const int nc = chi - clo;
   const int T = DKV ? g * nc : nc;  // streamed half-tiles processed by this CTA
 
-  if (warp == 8 && elect_one()) {
+  if (warp == 16 && elect_one()) {
     tma_prefetch_desc(&tmap_r1);
     tma_prefetch_desc(&tmap_r2);
     tma_prefetch_desc(&tmap_s1);
     tma_prefetch_desc(&tmap_s2);
     mbar_init(r_full, 1);
     for (int i = 0; i < BWD_NST; ++i) { mbar_init(&st_full[i], DKV ? 2 : 1); mbar_init(&st_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sp_full[i], 1); mbar_init(&pd_ready[i], 4); mbar_init(&pd_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sp_full[i], 1); mbar_init(&pd_ready[i], 8); }
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_ptr_smem);
+  if (warp == 17) tmem_alloc<512>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const float scale_log2 = p.scale * kLog2e;
-  if (warp >= 8) {
-    setmaxnreg_dec<56>();
-    if (warp == 8) {
+
+  if (warp == 16) {
     // ================= producer: TMA tiles (+ lse / delta vectors in DKV mode) =================
     if (T > 0) {
       if (elect_one()) {
@@ -529,47 +581,46 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
         __syncwarp();
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc_sp = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
-    auto issue_sp = [&](int t) {
+    auto issue_sp = [&](int t) {  // S[u] = R1 s1^T, dP[u] = R2 s2^T
       const int u = t & 1, st = t % BWD_NST;
       mbar_wait(&st_full[st], (t / BWD_NST) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a1 = smem_u32(smem_r1), a2 = smem_u32(smem_r2);
-        const uint32_t b1 = smem_u32(smem_s + st * 2 * C::STR_BYTES), b2 = b1 + C::STR_BYTES;
+        const uint32_t a1 = desc_lo(smem_u32(smem_r1), 16), a2 = desc_lo(smem_u32(smem_r2), 16);
+        const uint32_t b1 = desc_lo(smem_u32(smem_s + st * 2 * C::STR_BYTES), 16);
+        const uint32_t b2 = desc_lo(smem_u32(smem_s + st * 2 * C::STR_BYTES + C::STR_BYTES), 16);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tmem_base + u * 64, desc_kmajor(a1, 128, kk), desc_kmajor(b1, 64, kk), idesc_sp, kk != 0);
+          umma_lo(tmem_base + u * 64, a1 + koff_kmajor(128, kk), b1 + koff_kmajor(64, kk), idesc_sp, kk != 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tmem_base + 128 + u * 64, desc_kmajor(a2, 128, kk), desc_kmajor(b2, 64, kk), idesc_sp, kk != 0);
+          umma_lo(tmem_base + 128 + u * 64, a2 + koff_kmajor(128, kk), b2 + koff_kmajor(64, kk), idesc_sp, kk != 0);
         umma_commit(&sp_full[u]);
       }
       __syncwarp();
     };
-    auto issue_acc = [&](int t) {
+    auto issue_acc = [&](int t) {  // A operands (bf16 P^T / dS^T) straight from the TMEM columns of buffer u
       const int u = t & 1, st = t % BWD_NST;
       mbar_wait(&pd_ready[u], (t >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t b1 = smem_u32(smem_s + st * 2 * C::STR_BYTES), b2 = b1 + C::STR_BYTES;
-        const uint32_t pd = smem_u32(smem_pd + u * (C::N_PD / 2) * C::PD_BYTES);
-        if constexpr (DKV) {
+        const uint32_t b1 = desc_lo(smem_u32(smem_s + st * 2 * C::STR_BYTES), 64 * 128);
+        const uint32_t b2 = desc_lo(smem_u32(smem_s + st * 2 * C::STR_BYTES + C::STR_BYTES), 64 * 128);
+        const uint32_t tp = tmem_base + u * 64, tds = tmem_base + 128 + u * 64;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO
-            umma_f16(tmem_base + 256, desc_kmajor(pd, 128, kk), desc_mnmajor(b2, 64, kk), idesc_acc, (t | kk) != 0);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q
-            umma_f16(tmem_base + 256 + D, desc_kmajor(pd + C::PD_BYTES, 128, kk), desc_mnmajor(b1, 64, kk), idesc_acc, (t | kk) != 0);
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // dQ += dS K
-            umma_f16(tmem_base + 256, desc_kmajor(pd, 128, kk), desc_mnmajor(b1, 64, kk), idesc_acc, (t | kk) != 0);
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t aoff = (kk >> 1) * 32 + (kk & 1) * 8;  // packed bf16 columns of streamed rows [16 kk, 16 kk + 16)
+          if constexpr (DKV) {
+            umma_ts_lo(tmem_base + 256, tp + aoff, b2 + koff_mnmajor(kk), idesc_acc, (t | kk) != 0);       // dV += P^T dO
+            umma_ts_lo(tmem_base + 256 + D, tds + aoff, b1 + koff_mnmajor(kk), idesc_acc, (t | kk) != 0);  // dK += dS^T Q
+          } else {
+            umma_ts_lo(tmem_base + 256, tds + aoff, b1 + koff_mnmajor(kk), idesc_acc, (t | kk) != 0);      // dQ += dS K
+          }
         }
-        umma_commit(&pd_free[u]);
         umma_commit(&st_empty[st]);
         if (t == T - 1) umma_commit(acc_done);
       }
@@ -580,18 +631,19 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
       issue_sp(0);
       if (T > 1) issue_sp(1);
       for (int t = 0; t < T; ++t) {
-        issue_acc(t);
-        if (t + 2 < T) issue_sp(t + 2);
+        issue_acc(t);                     // reads buffer u = t & 1 ...
+        if (t + 2 < T) issue_sp(t + 2);   // ... which the next S / dP of that buffer overwrites: tcgen05 ops complete in order
       }
     }
-    }
   } else {
-    setmaxnreg_inc<224>();
-    // ================= softmax warpgroups (thread = resident row) =================
-    const int u = warp >> 2;
+    // ================= softmax warps: two threads per resident row, 32 streamed columns each =================
+    const int u = warp >> 3;                 // S / dP buffer of this group of 8 warps
+    const int hf = (warp >> 2) & 1;          // column half [hf*32, hf*32+32) of the 64-wide half-tile
     const int row = (warp & 3) * 32 + lane;
     const int ri = r0 + row;  // sequence-local key (DKV) / query (DQ) index
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + u * 64 + hf * 32;
+    const uint32_t tmem_dp = tmem_s + 128;
     const bool capped = p.softcap != 0.f;
     const float cap_in = capped ? p.scale / p.softcap : 0.f;
     float my_lse2 = INFINITY, my_delta = 0.f;
@@ -606,36 +658,40 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
     int i = 0;
     for (int t = u; t < T; t += 2, ++i) {
       const int st = t % BWD_NST;
-      const int c0 = (clo + (DKV ? t % nc : t)) * 64;
+      const int c0 = (clo + (DKV ? t % nc : t)) * 64 + hf * 32;  // first streamed row of this thread's columns
       mbar_wait(&sp_full[u], i & 1);
       tc_fence_after();
-      uint32_t s[64], dp[64];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t (&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
-        uint32_t (&c2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dp[c * 32]);
-        tmem_ld_32x32b_x32(tmem_base + lane_base + u * 64 + c * 32, c1);
-        tmem_ld_32x32b_x32(tmem_base + lane_base + 128 + u * 64 + c * 32, c2);
-      }
+      uint32_t s[32], dp[32];
+      tmem_ld_32x32b_x32(tmem_s, s);
+      tmem_ld_32x32b_x32(tmem_dp, dp);
       tmem_ld_wait();
-      // visible streamed columns [vlo, vhi] (tile-local) of this row
+      // visible streamed columns [vlo, vhi] (relative to c0) of this row
       int vlo, vhi;
       if constexpr (DKV) {  // row = key ri, column = query c0 + c
         vlo = p.wr < 0 ? 0 : ri - sq.off - p.wr - c0;
-        vhi = p.wl < 0 ? 63 : ri - sq.off + p.wl - c0;
+        vhi = p.wl < 0 ? 31 : ri - sq.off + p.wl - c0;
       } else {              // row = query ri, column = key c0 + c
         vlo = p.wl < 0 ? 0 : ri + sq.off - p.wl - c0;
         vhi = min(sq.Sk - 1, p.wr < 0 ? sq.Sk - 1 : ri + sq.off + p.wr) - c0;
       }
-      const bool edge = __any_sync(0xffffffffu, vlo > 0 || vhi < 63);
-      const float* vec = smem_vec + st * 128;
+      const bool edge = __any_sync(0xffffffffu, vlo > 0 || vhi < 31);
+      const float* vec = smem_vec + st * 128 + hf * 32;
       if constexpr (DKV) mbar_wait(&st_full[st], (t / BWD_NST) & 1);  // acquire the producer's lse / delta stores
-      uint32_t pk[32], dk[32];
+      uint32_t pk[16], dk[16];
 #pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        float pv[2], dsv[2];
+      for (int c = 0; c < 32; c += 4) {
+        float l2[4], dl[4];
+        if constexpr (DKV) {
+          const float4 a = lds_f4(vec + c), d4 = lds_f4(vec + 64 + c);
+          l2[0] = a.x; l2[1] = a.y; l2[2] = a.z; l2[3] = a.w;
+          dl[0] = d4.x; dl[1] = d4.y; dl[2] = d4.z; dl[3] = d4.w;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+          for (int e = 0; e < 4; ++e) { l2[e] = my_lse2; dl[e] = my_delta; }
+        }
+        float pv[4], dsv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
           float x = __uint_as_float(s[c + e]), tcap = 0.f;
           if (capped) {
             tcap = tanhf(x * cap_in);
@@ -643,49 +699,50 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
           } else {
             x *= scale_log2;
           }
-          const float l2 = DKV ? vec[c + e] : my_lse2;
-          const float dl = DKV ? vec[64 + c + e] : my_delta;
-          float pe = exp2f(x - l2);
-          if (edge && (c + e < vlo || c + e > vhi)) pe = 0.f;
-          float de = pe * (__uint_as_float(dp[c + e]) - dl);
-          if (capped) de *= (1.f - tcap * tcap);
-          pv[e] = pe;
-          dsv[e] = de;
+          pv[e] = exp2f(x - l2[e]);
+          dsv[e] = pv[e] * (__uint_as_float(dp[c + e]) - dl[e]);
+          if (capped) dsv[e] *= (1.f - tcap * tcap);
         }
         pk[c >> 1] = pack_bf16x2(pv[0], pv[1]);
+        pk[(c >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
         dk[c >> 1] = pack_bf16x2(dsv[0], dsv[1]);
+        dk[(c >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
       }
-      if (i > 0) mbar_wait(&pd_free[u], (i - 1) & 1);
-      uint8_t* pd = smem_pd + u * (C::N_PD / 2) * C::PD_BYTES;
+      if (edge) {  // boundary half-tiles only (warp-uniform): zero the columns outside the window / causal range
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        if constexpr (DKV) {
-          st_swizzled_16B(pd, row, q4, make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]));
-          st_swizzled_16B(pd + C::PD_BYTES, row, q4, make_uint4(dk[4 * q4], dk[4 * q4 + 1], dk[4 * q4 + 2], dk[4 * q4 + 3]));
-        } else {
-          st_swizzled_16B(pd, row, q4, make_uint4(dk[4 * q4], dk[4 * q4 + 1], dk[4 * q4 + 2], dk[4 * q4 + 3]));
+        for (int c = 0; c < 32; c += 2) {
+          const bool k0v = (c >= vlo) && (c <= vhi), k1v = (c + 1 >= vlo) && (c + 1 <= vhi);
+          const uint32_t keep = (k0v ? 0x0000ffffu : 0u) | (k1v ? 0xffff0000u : 0u);
+          pk[c >> 1] &= keep;
+          dk[c >> 1] &= keep;
         }
       }
-      fence_proxy_async_smem();
+      // bf16 results back into the first 16 of this thread's own 32 fp32 columns (nobody else reads or writes them)
+      if constexpr (DKV) tmem_st_32x32b_x16(tmem_s, pk);
+      tmem_st_32x32b_x16(tmem_dp, dk);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pd_ready[u]);
     }
-    // ---- epilogue: accumulators -> bf16 -> global
+    // ---- epilogue: accumulators -> bf16 -> global.  DKV: group 0 stores dV, group 1 stores dK (scaled); DQ: group 0 stores
+    // dQ (scaled).  The two threads of a row take one half of the D columns each.
     if (T > 0) {
       mbar_wait(acc_done, 0);
       tc_fence_after();
     }
     const bool row_ok = ri < (DKV ? sq.Sk : sq.Sq);
-    if constexpr (DKV) {
-      // warpgroup 0 stores dV, warpgroup 1 stores dK (scaled)
-      __nv_bfloat16* dst = (u == 0 ? p.dv : p.dk) + (static_cast<long long>(sq.k_start + ri) * p.Hk + head) * D;
-      const float mul = (u == 0) ? 1.f : p.scale;
+    if (DKV || u == 0) {
+      __nv_bfloat16* dst;
+      if constexpr (DKV) dst = (u == 0 ? p.dv : p.dk) + (static_cast<long long>(sq.k_start + ri) * p.Hk + head) * D + hf * (D / 2);
+      else dst = p.dq + (static_cast<long long>(sq.q_start + ri) * p.Hq + head) * D + hf * (D / 2);
+      const float mul = (DKV && u == 0) ? 1.f : p.scale;
+      const uint32_t tacc = tmem_base + lane_base + 256 + (DKV ? u * D : 0) + hf * (D / 2);
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < D / 64; ++c) {
         uint32_t o[32];
         if (T > 0) {
-          tmem_ld_32x32b_x32(tmem_base + lane_base + 256 + u * D + c * 32, o);
+          tmem_ld_32x32b_x32(tacc + c * 32, o);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -703,64 +760,37 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
           }
         }
       }
-    } else {
-      // both warpgroups store dQ: warpgroup u takes columns [u*D/2, (u+1)*D/2)
-      __nv_bfloat16* dst = p.dq + (static_cast<long long>(sq.q_start + ri) * p.Hq + head) * D + u * (D / 2);
-#pragma unroll
-      for (int c = 0; c < D / 64; ++c) {
-        uint32_t o[32];
-        if (T > 0) {
-          tmem_ld_32x32b_x32(tmem_base + lane_base + 256 + u * (D / 2) + c * 32, o);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[e] = 0;
-        }
-        if (row_ok) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint4 w4;
-            w4.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * p.scale, __uint_as_float(o[v * 8 + 1]) * p.scale);
-            w4.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * p.scale, __uint_as_float(o[v * 8 + 3]) * p.scale);
-            w4.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * p.scale, __uint_as_float(o[v * 8 + 5]) * p.scale);
-            w4.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * p.scale, __uint_as_float(o[v * 8 + 7]) * p.scale);
-            *reinterpret_cast<uint4*>(dst + c * 32 + v * 8) = w4;
-          }
-        }
-      }
     }
     tc_fence_before();
   }
 
   __syncthreads();
   tc_fence_after();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == 17) tmem_dealloc<512>(tmem_base);
 }
 
-// delta[b, h, q] = sum_d dO[q, h, d] * O[q, h, d]   (one warp per (row, head))
+// delta[b, h, q] = sum_d dO[q, h, d] * O[q, h, d]   (D/8 lanes per (row, head), 16-byte loads)
 template <int D>
 __global__ void flash_attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                         float* __restrict__ delta, const int* __restrict__ cu_q, int B, int Sq, int Hq,
                                         long long total_rows, long long lse_bs, long long lse_hs) {
-  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (gw >= total_rows * Hq) return;
-  const int lane = threadIdx.x & 31;
-  const long long r = gw / Hq;
-  const int h = static_cast<int>(gw % Hq);
-  const __nv_bfloat16* po = o + gw * D;
-  const __nv_bfloat16* pd = dout + gw * D;
+  constexpr int LANES = D / 8;  // lanes cooperating on one (row, head)
+  const long long gt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long item = gt / LANES;
+  const int sub = static_cast<int>(gt % LANES);
+  const bool ok = item < total_rows * Hq;
   float acc = 0.f;
-  if constexpr (D == 128) {
-    const uint2 a = *reinterpret_cast<const uint2*>(po + lane * 4), c = *reinterpret_cast<const uint2*>(pd + lane * 4);
-    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), c0 = unpack_bf16x2(c.x), c1 = unpack_bf16x2(c.y);
-    acc = a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y;
-  } else {
-    const uint32_t a = *reinterpret_cast<const uint32_t*>(po + lane * 2), c = *reinterpret_cast<const uint32_t*>(pd + lane * 2);
-    const float2 a0 = unpack_bf16x2(a), c0 = unpack_bf16x2(c);
-    acc = a0.x * c0.x + a0.y * c0.y;
+  if (ok) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + item * D + sub * 8), c = *reinterpret_cast<const uint4*>(dout + item * D + sub * 8);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+    const float2 c0 = unpack_bf16x2(c.x), c1 = unpack_bf16x2(c.y), c2 = unpack_bf16x2(c.z), c3 = unpack_bf16x2(c.w);
+    acc = a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y + a2.x * c2.x + a2.y * c2.y + a3.x * c3.x + a3.y * c3.y;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
+#pragma unroll
+  for (int off = LANES / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (ok && sub == 0) {
+    const long long r = item / Hq;
+    const int h = static_cast<int>(item % Hq);
     long long idx;
     if (cu_q != nullptr) {
       idx = static_cast<long long>(h) * lse_hs + r;  // packed: [H, total]
@@ -799,10 +829,10 @@ FaParams make_params(const FlashAttnArgs& a) {
   return p;
 }
 
-template <int D, bool P_TMEM>
+template <int D>
 void launch_fwd(const FlashAttnArgs& a, cudaStream_t stream) {
-  using C = FwdCfg<D, P_TMEM>;
-  auto kern = flash_attn_fwd_kernel<D, P_TMEM>;
+  using C = FwdCfg<D>;
+  auto kern = flash_attn_fwd_kernel<D>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -819,8 +849,8 @@ void launch_fwd(const FlashAttnArgs& a, cudaStream_t stream) {
 
 template <int D>
 void launch_delta(const FlashAttnArgs& a, cudaStream_t stream) {
-  const long long warps = a.total_q * a.Hq;
-  flash_attn_delta_kernel<D><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+  const long long threads = a.total_q * a.Hq * (D / 8);
+  flash_attn_delta_kernel<D><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(a.out), static_cast<const __nv_bfloat16*>(a.dout), a.delta, a.cu_q, a.B, a.Sq, a.Hq,
       a.total_q, static_cast<long long>(a.Hq) * a.Sq, a.cu_q != nullptr ? a.total_q : a.Sq);
 }
@@ -872,12 +902,9 @@ void check_args(const FlashAttnArgs& a) {
 void flash_attn_fwd(const FlashAttnArgs& a, int variant, cudaStream_t stream) {
   if (a.B == 0 || a.Sq == 0 || a.Hq == 0 || a.total_q == 0) return;
   check_args(a);
-  const bool p_tmem = variant != 1;
-  if (a.D == 64) {
-    if (p_tmem) launch_fwd<64, true>(a, stream); else launch_fwd<64, false>(a, stream);
-  } else {
-    if (p_tmem) launch_fwd<128, true>(a, stream); else launch_fwd<128, false>(a, stream);
-  }
+  (void)variant;
+  if (a.D == 64) launch_fwd<64>(a, stream);
+  else launch_fwd<128>(a, stream);
 }
 
 void flash_attn_bwd_delta(const FlashAttnArgs& a, cudaStream_t stream) {
