@@ -55,6 +55,13 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dp-impl", default="nvlink", choices=["nvlink", "nccl"],
                     help="multi-GPU gradient path of the device-timed arm: own NVLink peer-memory kernels or NCCL all-reduce")
+    ap.add_argument("--layout", default="dp", choices=["dp", "ep"],
+                    help="dp: every GPU holds the whole model (headline, comparable with the reference arm); ep: experts sharded "
+                         "over all GPUs (expert parallel = N, NVLink dispatch / combine), dense parameters replicated")
+    ap.add_argument("--model", default="example", choices=["example", "30b-a3b"],
+                    help="example: the reference's example/qwen3_moe/pretrain.json model; 30b-a3b: Qwen3-30B-A3B shape (needs --layout ep on 8 GPUs)")
+    ap.add_argument("--ep-capacity-factor", type=float, default=2.0,
+                    help="receive capacity of an expert-parallel rank as a multiple of its fair share (0 = worst case)")
     return ap.parse_args()
 
 
@@ -135,10 +142,78 @@ def reference_arm(args) -> None:
         print(json.dumps(result))
 
 
+QWEN3_30B_A3B = {**FLAGSHIP, "hidden_size": 2048, "intermediate_size": 768, "num_attention_heads": 32, "num_key_value_heads": 4,
+                 "num_hidden_layers": 48}
+
+
+def model_spec(args) -> dict:
+    return QWEN3_30B_A3B if getattr(args, "model", "example") == "30b-a3b" else FLAGSHIP
+
+
+def model_name(args) -> str:
+    m = model_spec(args)
+    tag = "Qwen3-30B-A3B shape" if m is QWEN3_30B_A3B else "qwen3_moe example/pretrain.json"
+    return (f"{tag} ({args.layers}L h{m['hidden_size']} {m['num_attention_heads']}q/{m['num_key_value_heads']}kv x{m['head_dim']} "
+            f"E{m['num_experts']} top{m['experts_top_k']} ffn{m['intermediate_size']} vocab{sum(m['split_vocab_size'].values())})")
+
+
+def expert_parallel_arm(args) -> None:
+    """Experts sharded over all N GPUs (EP = N, NVLink peer-memory dispatch / combine), dense parameters replicated and
+    reduced by the bucketed gradient synchroniser; everything runs through the public Trainer API, device-timed with CUDA
+    events inside the run, so ``value`` and ``e2e`` are the same measurement."""
+    import contextlib
+    import tempfile
+
+    import torch
+    import torch.distributed as dist
+
+    from d9d_b200 import ops
+    from d9d_b200.bench_support import TrainerEndToEnd
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    os.environ["D9D_EP_CAPACITY_FACTOR"] = str(args.ep_capacity_factor)
+    torch.cuda.set_device(local_rank)
+    ops.load()
+    vocab = sum(model_spec(args)["split_vocab_size"].values())
+    sampler = ClockSampler(local_rank)
+    with tempfile.TemporaryDirectory() as workdir, contextlib.redirect_stdout(sys.stderr):
+        runner = TrainerEndToEnd(args, world, flagship_params(args), vocab, workdir, layout="ep")
+        if rank == 0:
+            sampler.start()
+        res = runner.run()
+    clocks = sampler.stop() if rank == 0 else None
+    tokens = args.accum * args.microbatch * args.seq_len * world
+    value = tokens / (res["ms_per_step"] / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Qwen3-MoE pretrain tokens/sec (max over ranks)", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights", "impl": "own",
+            "config": {"model": model_name(args), "global_batch": args.accum * args.microbatch * world, "microbatch": args.microbatch,
+                       "seq_len": args.seq_len,
+                       "parallelism": f"ep{world} x dp{world} (experts sharded {world}-way over NVLink peer-memory dispatch/combine, "
+                                      f"capacity factor {args.ep_capacity_factor}; dense params replicated, NCCL bucketed all-reduce)",
+                       "optimizer": "stochastic_adamw bf16 states, fp32 grads, clip 5.0",
+                       "l2": "working set exceeds the 126 MB L2"},
+            "clocks": clocks,
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": res["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": res["d2h_bytes_per_step"], "ms_per_step": res["ms_per_step"], "final_loss": res["final_loss"],
+                    "ep_overflow": res.get("ep_overflow"),
+                    "api": "d9d_b200.loop.run.TrainingConfigurator(...).configure().train(); pinned-memory StatefulDataLoader"},
+            "gpu_launches": res["launches"], "final_loss": res["final_loss"]}))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def flagship_params(args):
     from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLMParameters, Qwen3MoELayerParameters, Qwen3MoEParameters
 
-    layer = Qwen3MoELayerParameters(**{k: FLAGSHIP[k] for k in (
+    spec = model_spec(args)
+    layer = Qwen3MoELayerParameters(**{k: spec[k] for k in (
         "hidden_size", "intermediate_size", "num_experts", "experts_top_k", "num_attention_heads",
         "num_key_value_heads", "rms_norm_eps", "head_dim")})
     return Qwen3MoEForCausalLMParameters(model=Qwen3MoEParameters(
@@ -163,8 +238,13 @@ def build_model(args, device):
 
 def main():
     args = parse_args()
+    if args.model == "30b-a3b" and args.layers == FLAGSHIP["num_hidden_layers"]:
+        args.layers = QWEN3_30B_A3B["num_hidden_layers"]
     if args.impl == "reference":
         reference_arm(args)
+        return
+    if args.layout == "ep":
+        expert_parallel_arm(args)
         return
 
     import torch
@@ -183,7 +263,7 @@ def main():
     ops.load()
 
     runner = TrainStepRunner(args, device, world, build_model)
-    vocab = sum(FLAGSHIP["split_vocab_size"].values())
+    vocab = sum(model_spec(args)["split_vocab_size"].values())
     tokens_per_step_per_gpu = args.accum * args.microbatch * args.seq_len
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=device)
 
@@ -259,7 +339,7 @@ def main():
             "data": "synthetic tokens, random-init weights",
             "impl": "own",
             "config": {
-                "model": f"qwen3_moe example/pretrain.json ({args.layers}L h768 16q/4kv x128 E128 top8 ffn576 vocab151669)",
+                "model": model_name(args),
                 "global_batch": args.accum * args.microbatch * world,
                 "microbatch": args.microbatch,
                 "seq_len": args.seq_len,

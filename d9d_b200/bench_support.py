@@ -8,6 +8,8 @@ folded into the fused stochastic-rounding AdamW launch.  No host synchronisation
 
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -160,7 +162,7 @@ class TrainerEndToEnd:
     events recorded from ``EVENT_TRAIN_STEP_PRE`` / ``EVENT_TRAIN_STEP_POST`` subscribers.
     """
 
-    def __init__(self, args, world: int, model_params, vocab: int, workdir: str):
+    def __init__(self, args, world: int, model_params, vocab: int, workdir: str, layout: str = "dp"):
         from d9d_b200.core.dist_context import DeviceMeshParameters
         from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
         from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
@@ -180,16 +182,19 @@ class TrainerEndToEnd:
         global_batch = args.accum * args.microbatch * world
         lr_cfg = PiecewiseConfig.model_validate({"name": "piecewise", "scheduler": {"initial_multiplier": 1.0, "phases": [
             {"mode": "rest", "target_multiplier": 1.0, "curve": {"type": "linear"}}]}})
+        self.layout = layout
+        nvlink_dp = layout == "dp" and world > 1 and getattr(args, "dp_impl", "nvlink") == "nvlink"
+        mesh = (DeviceMeshParameters(data_parallel_replicate=world, expert_parallel=world) if layout == "ep"
+                else DeviceMeshParameters(data_parallel_replicate=world))
         self.trainer = TrainingConfigurator(
-            mesh=DeviceMeshParameters(data_parallel_replicate=world),
+            mesh=mesh,
             parameters=TrainerConfig.model_validate(trainer_config_for_bench(args, world, self.total_steps, workdir)),
             task_provider=lambda ctx: CausalLMTask(),
             model_provider=Qwen3MoEModelProvider(Qwen3MoEModelProviderConfig(model=model_params)),
             data_provider=SyntheticDataProvider(SyntheticDataConfig(
                 num_samples=global_batch * self.total_steps, seq_len=args.seq_len, vocab_size=vocab, seed=5)),
             optimizer_provider=AutoOptimizerProvider(
-                NvlinkShardedAdamWOptimizerConfig(lr=2.5e-4, state_dtype="bfloat16")
-                if world > 1 and getattr(args, "dp_impl", "nvlink") == "nvlink"
+                NvlinkShardedAdamWOptimizerConfig(lr=2.5e-4, state_dtype="bfloat16") if nvlink_dp
                 else StochasticAdamWOptimizerConfig(lr=2.5e-4, state_dtype="bfloat16")),
             lr_scheduler_provider=AutoLRSchedulerProvider(lr_cfg),
         ).configure()
@@ -201,7 +206,16 @@ class TrainerEndToEnd:
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = {}
 
+        prof_path = os.environ.get("D9D_BENCH_PROFILE")  # attribution only: per-kernel totals of the LAST step (rank 0)
+        prof_box: dict = {}
+
         def pre(ctx) -> None:
+            if prof_path and state.dist_context.is_main_process and ctx.stepper.current_step == self.total_steps - 1:
+                from torch.profiler import ProfilerActivity, profile
+
+                torch.cuda.synchronize()
+                prof_box["p"] = profile(activities=[ProfilerActivity.CUDA])
+                prof_box["p"].__enter__()
             if ctx.stepper.current_step == args.warmup:
                 state.dist_context.wait_world()
                 launches["before"] = native_launch_count()
@@ -210,6 +224,20 @@ class TrainerEndToEnd:
         def post(ctx) -> None:
             if ctx.stepper.current_step == self.total_steps - 1:
                 end.record()
+                if "p" in prof_box:
+                    torch.cuda.synchronize()
+                    prof_box["p"].__exit__(None, None, None)
+                    totals: dict[str, list] = {}
+                    for ev in prof_box["p"].events():
+                        if ev.device_type == torch.autograd.DeviceType.CUDA:
+                            t = totals.setdefault(ev.name, [0, 0.0])
+                            t[0] += 1
+                            t[1] += ev.device_time
+                    rows = sorted(totals.items(), key=lambda kv: -kv[1][1])
+                    with open(prof_path, "w") as f:
+                        import json as _json
+
+                        _json.dump([{"name": k[:160], "calls": v[0], "total_us": v[1]} for k, v in rows], f, indent=1)
                 state.dist_context.wait_world()
                 launches["after"] = native_launch_count()
 
@@ -222,5 +250,11 @@ class TrainerEndToEnd:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         # bytes moved per optimizer step and rank: input_ids + labels + position_ids (int64) up, one fp32 loss down
         h2d = args.accum * 3 * args.microbatch * args.seq_len * 8
+        overflow = None
+        if self.layout == "ep":
+            from d9d_b200.module.block.moe.communications.nvlink import NvlinkExpertParallelCommunicationHandler as H
+
+            overflow = any(h.overflowed for h in H.instances)
         return {"ms_per_step": ms.item() / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "final_loss": state.logger.last_loss, "launches": launches.get("after", 0) - launches.get("before", 0)}
+                "final_loss": state.logger.last_loss, "launches": launches.get("after", 0) - launches.get("before", 0),
+                "ep_overflow": overflow}

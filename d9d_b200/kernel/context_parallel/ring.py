@@ -27,7 +27,7 @@ def _exchange(tensors: list[torch.Tensor], group: dist.ProcessGroup) -> tuple[li
     """Start sending ``tensors`` to the next rank of the ring and receiving the previous rank's into fresh buffers."""
     world, rank = group.size(), group.rank()
     nxt, prv = (rank + 1) % world, (rank - 1) % world
-    received = [torch.empty_like(t) for t in tensors]
+    received = [torch.empty_like(t, memory_format=torch.contiguous_format) for t in tensors]  # irecv needs dense buffers
     ops = [dist.P2POp(dist.isend, t.contiguous(), group=group, group_peer=nxt) for t in tensors]
     ops += [dist.P2POp(dist.irecv, r, group=group, group_peer=prv) for r in received]
     return received, dist.batch_isend_irecv(ops)

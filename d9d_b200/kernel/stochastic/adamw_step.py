@@ -28,6 +28,11 @@ def _validate(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
         raise ValueError("Exp_avg_sq state must be contiguous since it is an in-place kernel.")
     if m.dtype != v.dtype:
         raise ValueError("States have different dtypes.")
+    # the kernel distinguishes bf16 from "everything else = fp32": any other dtype would be reinterpreted silently
+    if g.dtype not in (torch.bfloat16, torch.float32):
+        raise ValueError(f"Grads must be BFloat16 or Float32 for this kernel, got {g.dtype}.")
+    if m.dtype not in (torch.bfloat16, torch.float32):
+        raise ValueError(f"Optimizer states must be BFloat16 or Float32 for this kernel, got {m.dtype}.")
 
 
 class AdamWLaunchPlan:

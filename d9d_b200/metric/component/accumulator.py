@@ -66,23 +66,32 @@ class MetricAccumulator(Stateful):
         self._local = self._local.to(device)
         self._synchronized = self._synchronized.to(device)
 
+    @staticmethod
+    def _rank_key() -> str:
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        return f"local.rank{rank}"
+
     def state_dict(self) -> dict[str, Any]:
-        """Checkpoint view.  The keys are rank independent (the reference's key tree) and a distributed checkpoint stores ONE
-        copy of such tensors, so what is stored is the *global* accumulation: ``local`` holds the reduction of every rank's
-        local value.  Collective - every rank has to call it (``torch.distributed.checkpoint`` does, on save and on load)."""
-        total = self._local.clone()
-        if dist.is_available() and dist.is_initialized():
-            dist.all_reduce(total, op=_TORCH_OP[self._reduce_op])
-        return {"local": total, "synchronized": self._synchronized.clone(), "is_synchronized": self._is_synchronized}
+        """Checkpoint view.  No collective runs in here (``state_dict`` may be called by a subset of the ranks, or a different
+        number of times per rank): every rank stores ITS OWN partial value under a rank-qualified key - the same convention
+        as the data-loader and task states - so a resumed job continues each rank's accumulation exactly."""
+        return {self._rank_key(): self._local.clone(), "synchronized": self._synchronized.clone(), "is_synchronized": self._is_synchronized}
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
-        """Inverse of :meth:`state_dict`: the stored global value becomes the local value of rank 0 (every rank for max / min,
-        which are idempotent) and the other ranks restart from the identity, so the next ``sync`` reproduces the total."""
-        total = state_dict["local"].detach().clone().to(self._local.device)
-        distributed = dist.is_available() and dist.is_initialized()
-        if distributed and self._reduce_op == MetricReduceOp.sum and dist.get_rank() != 0:
-            total = self._initial.clone()
-        self._local = total
+        """Restores this rank's partial value.  Checkpoints written by the earlier format (one rank-independent ``local``
+        key holding the global reduction) are still understood: the total goes to rank 0, the other ranks restart from the
+        identity (max / min are idempotent, every rank takes the value)."""
+        key = self._rank_key()
+        if key in state_dict:
+            local = state_dict[key].detach().clone().to(self._local.device)
+        elif "local" in state_dict:
+            local = state_dict["local"].detach().clone().to(self._local.device)
+            distributed = dist.is_available() and dist.is_initialized()
+            if distributed and self._reduce_op == MetricReduceOp.sum and dist.get_rank() != 0:
+                local = self._initial.clone()
+        else:
+            raise KeyError(f"metric accumulator state has no entry for this rank ({key}); it was saved by a different world size")
+        self._local = local
         self._synchronized = state_dict["synchronized"].detach().clone().to(self._synchronized.device)
         self._is_synchronized = bool(state_dict["is_synchronized"])
 

@@ -300,6 +300,20 @@ std::tuple<Tensor, Tensor> moe_permute(const Tensor& x, const c10::optional<Tens
   return {xp, pp};
 }
 
+// zero the pad rows [seg[e] + counts[e], seg[e+1]) of an aligned expert-sorted buffer (and of its per-row fp32 side array)
+void moe_zero_pad(Tensor xp, const c10::optional<Tensor>& pp, const Tensor& counts, const Tensor& seg_offsets) {
+  TORCH_CHECK(xp.is_cuda() && xp.dim() == 2 && xp.scalar_type() == at::kBFloat16 && xp.stride(1) == 1 && xp.stride(0) == xp.size(1));
+  TORCH_CHECK(counts.scalar_type() == at::kInt && seg_offsets.scalar_type() == at::kInt && counts.is_contiguous() && seg_offsets.is_contiguous());
+  c10::cuda::CUDAGuard guard(xp.device());
+  float* p = nullptr;
+  if (pp.has_value()) {
+    TORCH_CHECK(pp->scalar_type() == at::kFloat && pp->is_contiguous());
+    p = pp->data_ptr<float>();
+  }
+  d9d::moe_zero_pad(xp.data_ptr(), p, counts.data_ptr<int>(), seg_offsets.data_ptr<int>(), static_cast<int>(counts.numel()),
+                    static_cast<int>(xp.size(1)), cur_stream());
+}
+
 // y[T,H] = sum_j yp[row_map[t,j]];   with dpp: also dprobs[T,k] = dpp[row_map[t,j]]
 std::tuple<Tensor, Tensor> moe_gather(const Tensor& yp, const c10::optional<Tensor>& dpp, const Tensor& row_map,
                                       int64_t T, int64_t k) {
@@ -673,6 +687,7 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("moe_permute(Tensor x, Tensor? probs, Tensor row_map, Tensor counts, Tensor seg_offsets, int capacity) -> (Tensor, Tensor)");
   m.def("moe_gather(Tensor yp, Tensor? dpp, Tensor row_map, int T, int k) -> (Tensor, Tensor)");
   m.def("sumsq_accumulate_(Tensor x, Tensor(a!) out) -> ()");
+  m.def("moe_zero_pad(Tensor(a!) xp, Tensor? pp, Tensor counts, Tensor seg_offsets) -> ()");
   m.def("flash_attn_fwd(Tensor q, Tensor k, Tensor v, float scale, int window_left, int window_right, float softcap, Tensor? sink, Tensor? cu_q, Tensor? cu_k, int max_q, int max_k, int variant) -> (Tensor, Tensor)");
   m.def("flash_attn_bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor lse, float scale, int window_left, int window_right, float softcap, Tensor? cu_q, Tensor? cu_k, int max_q, int max_k, Tensor? dlse) -> (Tensor, Tensor, Tensor, Tensor)");
   m.def("qk_norm_rope_fwd(Tensor q, Tensor k, Tensor wq, Tensor wk, Tensor cos_t, Tensor sin_t, float eps, bool zero_centered, "
@@ -716,6 +731,7 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("moe_permute", &moe_permute);
   m.impl("moe_gather", &moe_gather);
   m.impl("sumsq_accumulate_", &sumsq_accumulate_);
+  m.impl("moe_zero_pad", &moe_zero_pad);
   m.impl("flash_attn_fwd", &flash_attn_fwd);
   m.impl("flash_attn_bwd", &flash_attn_bwd);
   m.impl("qk_norm_rope_fwd", &qk_norm_rope_fwd);
