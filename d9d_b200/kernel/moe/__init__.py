@@ -9,6 +9,7 @@ Compatibility surface (``compat.py``): ``fused_indices_to_multihot``, ``moe_perm
 """
 
 from .compat import fused_indices_to_multihot, moe_permute_with_probs, moe_unpermute_mask
+from .experts import grouped_swiglu
 from .layout import MoELayout, build_moe_layout, grouped_linear, moe_permute, moe_unpermute
 
 __all__ = [
@@ -16,6 +17,7 @@ __all__ = [
     "build_moe_layout",
     "fused_indices_to_multihot",
     "grouped_linear",
+    "grouped_swiglu",
     "moe_permute",
     "moe_permute_with_probs",
     "moe_unpermute",

@@ -21,3 +21,8 @@ class ExpertCommunicationHandler(abc.ABC):
 
     @abc.abstractmethod
     def combine(self, hidden_states: torch.Tensor) -> torch.Tensor: ...
+
+    def expert_buffers(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        """Between ``dispatch`` and ``combine``: optional ``[>= capacity, hidden]`` buffers the expert block may write its
+        output / its input gradient into directly (memory the handler would otherwise have to copy them to)."""
+        return None, None

@@ -117,7 +117,8 @@ class _Dispatch(Function):
         plan: _Plan = ctx.plan
         ws, ops = plan.ws, native_ops()
         r, cap = ws.region, plan.layout.capacity
-        r.x[:cap].copy_(dxp)
+        if dxp.data_ptr() != r.x.data_ptr():  # the fused expert block writes its input gradient straight into the staging region
+            r.x[:cap].copy_(dxp)
         if dpp is None:
             r.p[:cap].zero_()
         else:
@@ -136,7 +137,8 @@ class _Combine(Function):
     def forward(ctx: Any, yp: torch.Tensor, plan: _Plan):
         ws, ops = plan.ws, native_ops()
         r = ws.region
-        r.x[: plan.layout.capacity].copy_(yp)
+        if yp.data_ptr() != r.x.data_ptr():  # the fused expert block writes its output straight into the staging region
+            r.x[: plan.layout.capacity].copy_(yp)
         ws.barrier()  # all expert outputs are published
         y, _ = ops.ep_pull_sum(r.arena.peer_ptrs_dev, r.off_x, r.off_p, plan.dest_rank, plan.dest_row, plan.num_tokens, plan.top_k,
                                plan.hidden, False)
@@ -271,6 +273,12 @@ class NvlinkExpertParallelCommunicationHandler(ExpertCommunicationHandler):
         xp, pp = _Dispatch.apply(hidden_states.contiguous(), topk_weights, plan)
         return xp, pp, layout
 
+    def expert_buffers(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        if self._plan is None:
+            return None, None
+        staging = self._plan.ws.region.x
+        return staging, staging
+
     def combine(self, hidden_states: torch.Tensor) -> torch.Tensor:
         if self._plan is None:
             raise ValueError("Cannot run combine before running dispatch!")
@@ -303,6 +311,9 @@ class AutoExpertParallelCommunicationHandler(ExpertCommunicationHandler):
                 and self._world <= 8 and os.environ.get("D9D_EP_NVLINK", "1") != "0")
         self._active = self._nvlink if fast else self._collective
         return self._active.dispatch(hidden_states, topk_ids, topk_weights)
+
+    def expert_buffers(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+        return self._active.expert_buffers() if self._active is not None else (None, None)
 
     def combine(self, hidden_states: torch.Tensor) -> torch.Tensor:
         if self._active is None:

@@ -58,7 +58,8 @@ class MoELayer(nn.Module, ModuleLateInit):
         self._update_tokens_per_expert(routing.selected_expert_indices)
 
         xp, pp, grouping = self._communicator.dispatch(x, routing.selected_expert_indices, routing.selected_probabilities)
-        yp = self.grouped_experts(xp, pp, grouping)
+        out_buf, dx_buf = self._communicator.expert_buffers()
+        yp = self.grouped_experts(xp, pp, grouping, out=out_buf, dx_out=dx_buf)
         y = self._communicator.combine(yp)
         if shared is not None:
             y = y + shared

@@ -54,13 +54,13 @@ void gemm(const Tensor& a, const Tensor& b, Tensor d, bool a_mn, bool b_mn, bool
 }
 
 // d[R,N] = a[R,K] · W[e(r)];  b: [E,N,K] (b_mn=false) or [E,K,N] (b_mn=true)
-void gemm_grouped_m(const Tensor& a, const Tensor& b, Tensor d, const Tensor& tile_group, bool b_mn) {
+void gemm_grouped_m(const Tensor& a, const Tensor& b, Tensor d, const Tensor& tile_group, bool b_mn, bool accumulate) {
   CHECK_CUDA_CONTIG(a); CHECK_CUDA_CONTIG(b); CHECK_CUDA_CONTIG(d); CHECK_CUDA_CONTIG(tile_group);
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && d.scalar_type() == at::kBFloat16);
   TORCH_CHECK(tile_group.scalar_type() == at::kInt && a.size(0) % 128 == 0 && tile_group.numel() == a.size(0) / 128);
   c10::cuda::CUDAGuard guard(a.device());
   d9d::GemmArgs g;
-  g.mode = 1; g.epi = 0; g.a_mn = false; g.b_mn = b_mn;
+  g.mode = 1; g.epi = accumulate ? 3 : 0; g.a_mn = false; g.b_mn = b_mn;
   g.M = static_cast<int>(a.size(0)); g.K = static_cast<int>(a.size(1));
   g.N = static_cast<int>(b_mn ? b.size(2) : b.size(1));
   TORCH_CHECK((b_mn ? b.size(1) : b.size(2)) == g.K, "gemm_grouped_m: K mismatch");
@@ -186,23 +186,30 @@ std::tuple<Tensor, Tensor> silu_mul_bwd(const Tensor& dout, const Tensor& x, con
   return {dx, dy};
 }
 
-Tensor silu_mul_probs_fwd(const Tensor& x, const Tensor& y, const Tensor& probs) {
+static const int* valid_rows_ptr(const c10::optional<Tensor>& v) {
+  if (!v.has_value()) return nullptr;
+  TORCH_CHECK(v->is_cuda() && v->scalar_type() == at::kInt && v->numel() >= 1, "valid_rows must be an int32 CUDA scalar");
+  return v->data_ptr<int>();
+}
+
+Tensor silu_mul_probs_fwd(const Tensor& x, const Tensor& y, const Tensor& probs, const c10::optional<Tensor>& valid_rows) {
   CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(y); CHECK_CUDA_CONTIG(probs);
   TORCH_CHECK(x.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 && probs.scalar_type() == at::kFloat);
   c10::cuda::CUDAGuard guard(x.device());
   Tensor out = at::empty_like(x);
   d9d::silu_mul_probs_fwd(x.data_ptr(), y.data_ptr(), probs.data_ptr<float>(), out.data_ptr(), x.size(0),
-                          static_cast<int>(x.size(1)), cur_stream());
+                          static_cast<int>(x.size(1)), valid_rows_ptr(valid_rows), cur_stream());
   return out;
 }
 
 std::tuple<Tensor, Tensor, Tensor> silu_mul_probs_bwd(const Tensor& dout, const Tensor& x, const Tensor& y,
-                                                      const Tensor& probs) {
+                                                      const Tensor& probs, const c10::optional<Tensor>& valid_rows) {
   CHECK_CUDA_CONTIG(dout); CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(y); CHECK_CUDA_CONTIG(probs);
   c10::cuda::CUDAGuard guard(x.device());
   Tensor dx = at::empty_like(x), dy = at::empty_like(y), dp = at::empty_like(probs);
   d9d::silu_mul_probs_bwd(dout.data_ptr(), x.data_ptr(), y.data_ptr(), probs.data_ptr<float>(), dx.data_ptr(),
-                          dy.data_ptr(), dp.data_ptr<float>(), x.size(0), static_cast<int>(x.size(1)), cur_stream());
+                          dy.data_ptr(), dp.data_ptr<float>(), x.size(0), static_cast<int>(x.size(1)), valid_rows_ptr(valid_rows),
+                          cur_stream());
   return {dx, dy, dp};
 }
 
@@ -668,7 +675,7 @@ void nvl_adamw_shard_(Tensor own_param, const Tensor& own_grad, Tensor exp_avg, 
 
 TORCH_LIBRARY(d9d_b200, m) {
   m.def("gemm(Tensor a, Tensor b, Tensor(a!) d, bool a_mn, bool b_mn, bool accumulate) -> ()");
-  m.def("gemm_grouped_m(Tensor a, Tensor b, Tensor(a!) d, Tensor tile_group, bool b_mn) -> ()");
+  m.def("gemm_grouped_m(Tensor a, Tensor b, Tensor(a!) d, Tensor tile_group, bool b_mn, bool accumulate=False) -> ()");
   m.def("gemm_grouped_k(Tensor a, Tensor b, Tensor(a!) d, Tensor group_offsets, bool accumulate) -> ()");
   m.def("ce_forward(Tensor h, Tensor w, Tensor target, int ignore_index) -> (Tensor, Tensor)");
   m.def("ce_dlogits(Tensor h, Tensor w, Tensor target, Tensor lse, Tensor grad, Tensor(a!) out, int ignore_index) -> ()");
@@ -676,8 +683,8 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("rms_norm_bwd(Tensor dout, Tensor x, Tensor w, Tensor inv_rms, bool zero_centered) -> (Tensor, Tensor)");
   m.def("silu_mul_fwd(Tensor x, Tensor y) -> Tensor");
   m.def("silu_mul_bwd(Tensor dout, Tensor x, Tensor y) -> (Tensor, Tensor)");
-  m.def("silu_mul_probs_fwd(Tensor x, Tensor y, Tensor probs) -> Tensor");
-  m.def("silu_mul_probs_bwd(Tensor dout, Tensor x, Tensor y, Tensor probs) -> (Tensor, Tensor, Tensor)");
+  m.def("silu_mul_probs_fwd(Tensor x, Tensor y, Tensor probs, Tensor? valid_rows=None) -> Tensor");
+  m.def("silu_mul_probs_bwd(Tensor dout, Tensor x, Tensor y, Tensor probs, Tensor? valid_rows=None) -> (Tensor, Tensor, Tensor)");
   m.def("sr_copy_(Tensor(a!) dst, Tensor src, int seed) -> ()");
   m.def(
       "adamw_sr_multi_(Tensor metas, Tensor block_map, float lr, float beta1, float beta2, float eps, float "

@@ -70,9 +70,10 @@ void silu_mul_bwd(const void* dout, const void* x, const void* y, void* dx, void
                   cudaStream_t stream);
 // MoE variant: out[r, :] = silu(x) * y * probs[r];  bwd also yields dprobs[r]
 void silu_mul_probs_fwd(const void* x, const void* y, const float* probs, void* out, long long rows, int cols,
-                        cudaStream_t stream);
+                        const int* valid_rows, cudaStream_t s);
+// valid_rows (device scalar or nullptr): rows >= *valid_rows are skipped (unused tail of a static-capacity buffer)
 void silu_mul_probs_bwd(const void* dout, const void* x, const void* y, const float* probs, void* dx, void* dy,
-                        float* dprobs, long long rows, int cols, cudaStream_t stream);
+                        float* dprobs, long long rows, int cols, const int* valid_rows, cudaStream_t s);
 
 // ------------------------------------------------------------------ stochastic rounding ----------
 void sr_copy_f32_to_bf16(const float* src, void* dst, long long n, uint64_t seed, cudaStream_t stream);

@@ -658,7 +658,8 @@ __global__ void __launch_bounds__(256) silu_mul_probs_fwd_kernel(const __nv_bflo
                                                                  const __nv_bfloat16* __restrict__ y,
                                                                  const float* __restrict__ probs,
                                                                  __nv_bfloat16* __restrict__ out, long long rows,
-                                                                 int cols) {
+                                                                 int cols, const int* __restrict__ valid_rows) {
+  if (valid_rows != nullptr) rows = min(rows, static_cast<long long>(*valid_rows));  // rows past the last expert segment are never read
   const int vec_per_row = cols >> 3;
   const long long nvec = rows * vec_per_row;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -681,7 +682,8 @@ __global__ void __launch_bounds__(256) silu_mul_probs_fwd_kernel(const __nv_bflo
 __global__ void __launch_bounds__(256) silu_mul_probs_bwd_kernel(
     const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
     const float* __restrict__ probs, __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dy,
-    float* __restrict__ dprobs, long long rows, int cols) {
+    float* __restrict__ dprobs, long long rows, int cols, const int* __restrict__ valid_rows) {
+  if (valid_rows != nullptr) rows = min(rows, static_cast<long long>(*valid_rows));
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -732,20 +734,20 @@ void silu_mul_bwd(const void* dout, const void* x, const void* y, void* dx, void
 }
 
 void silu_mul_probs_fwd(const void* x, const void* y, const float* probs, void* out, long long rows, int cols,
-                        cudaStream_t s) {
+                        const int* valid_rows, cudaStream_t s) {
   if (rows == 0) return;
   if (cols % 8) throw std::runtime_error("d9d silu_mul_probs: cols must be a multiple of 8");
-  silu_mul_probs_fwd_kernel<<<ew_grid(rows * (cols >> 3)), 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, probs, (__nv_bfloat16*)out, rows, cols);
+  silu_mul_probs_fwd_kernel<<<ew_grid(rows * (cols >> 3)), 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, probs, (__nv_bfloat16*)out, rows, cols, valid_rows);
 }
 
 void silu_mul_probs_bwd(const void* dout, const void* x, const void* y, const float* probs, void* dx, void* dy,
-                        float* dprobs, long long rows, int cols, cudaStream_t s) {
+                        float* dprobs, long long rows, int cols, const int* valid_rows, cudaStream_t s) {
   if (rows == 0) return;
   if (cols % 8) throw std::runtime_error("d9d silu_mul_probs: cols must be a multiple of 8");
   long long blocks = (rows + 7) / 8;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  silu_mul_probs_bwd_kernel<<<static_cast<int>(blocks), 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, probs, (__nv_bfloat16*)dx, (__nv_bfloat16*)dy, dprobs, rows, cols);
+  silu_mul_probs_bwd_kernel<<<static_cast<int>(blocks), 256, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, probs, (__nv_bfloat16*)dx, (__nv_bfloat16*)dy, dprobs, rows, cols, valid_rows);
 }
 
 // ================================================================= stochastic rounding ==========

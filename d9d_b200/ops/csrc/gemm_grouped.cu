@@ -12,9 +12,15 @@ void gemm_grouped(const GemmArgs& a, cudaStream_t stream) {
   if (a.mode == GROUPED_M) {
     const int bn = a.block_n ? a.block_n : pick_block_n(m_tiles, a.N);
     if (a.a_mn) throw std::runtime_error("d9d gemm: GROUPED_M requires K-major A");
-    if (a.epi != EPI_BF16) throw std::runtime_error("d9d gemm: GROUPED_M supports bf16 store only");
-    if (a.b_mn) D9D_DISPATCH_BN(GROUPED_M, false, true, EPI_BF16, bn, a, stream);
-    else        D9D_DISPATCH_BN(GROUPED_M, false, false, EPI_BF16, bn, a, stream);
+    if (a.epi == EPI_BF16_ACC) {
+      // D += X W^T (second dgrad of a pair of projections sharing the input: gate / up) - K-major B only
+      if (a.b_mn) throw std::runtime_error("d9d gemm: GROUPED_M accumulate is built for K-major B (dgrad) only");
+      D9D_DISPATCH_BN(GROUPED_M, false, false, EPI_BF16_ACC, bn, a, stream);
+    } else {
+      if (a.epi != EPI_BF16) throw std::runtime_error("d9d gemm: GROUPED_M supports bf16 store / accumulate only");
+      if (a.b_mn) D9D_DISPATCH_BN(GROUPED_M, false, true, EPI_BF16, bn, a, stream);
+      else        D9D_DISPATCH_BN(GROUPED_M, false, false, EPI_BF16, bn, a, stream);
+    }
   } else if (a.mode == GROUPED_K) {
     const int bn = a.block_n ? a.block_n : pick_block_n(m_tiles * a.num_groups, a.N);
     if (!a.a_mn || !a.b_mn) throw std::runtime_error("d9d gemm: GROUPED_K requires MN-major A and B");
