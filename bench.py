@@ -55,9 +55,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dp-impl", default="nvlink", choices=["nvlink", "nccl"],
                     help="multi-GPU gradient path of the device-timed arm: own NVLink peer-memory kernels or NCCL all-reduce")
-    ap.add_argument("--layout", default="dp", choices=["dp", "ep"],
+    ap.add_argument("--layout", default="dp", choices=["dp", "ep", "example"],
                     help="dp: every GPU holds the whole model (headline, comparable with the reference arm); ep: experts sharded "
-                         "over all GPUs (expert parallel = N, NVLink dispatch / combine), dense parameters replicated")
+                         "over all GPUs (expert parallel = N, NVLink dispatch / combine), dense parameters replicated; example: the "
+                         "reference example's PP4 x DP2 x EP2 layout with looped_bfs, 2 stages per rank (8 GPUs)")
     ap.add_argument("--model", default="example", choices=["example", "30b-a3b"],
                     help="example: the reference's example/qwen3_moe/pretrain.json model; 30b-a3b: Qwen3-30B-A3B shape (needs --layout ep on 8 GPUs)")
     ap.add_argument("--ep-capacity-factor", type=float, default=2.0,
@@ -181,7 +182,7 @@ def expert_parallel_arm(args) -> None:
     vocab = sum(model_spec(args)["split_vocab_size"].values())
     sampler = ClockSampler(local_rank)
     with tempfile.TemporaryDirectory() as workdir, contextlib.redirect_stdout(sys.stderr):
-        runner = TrainerEndToEnd(args, world, flagship_params(args), vocab, workdir, layout="ep")
+        runner = TrainerEndToEnd(args, world, flagship_params(args), vocab, workdir, layout=args.layout)
         if rank == 0:
             sampler.start()
         res = runner.run()
@@ -195,8 +196,11 @@ def expert_parallel_arm(args) -> None:
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights", "impl": "own",
             "config": {"model": model_name(args), "global_batch": args.accum * args.microbatch * world, "microbatch": args.microbatch,
                        "seq_len": args.seq_len,
-                       "parallelism": f"ep{world} x dp{world} (experts sharded {world}-way over NVLink peer-memory dispatch/combine, "
-                                      f"capacity factor {args.ep_capacity_factor}; dense params replicated, NCCL bucketed all-reduce)",
+                       "parallelism": (f"ep{world} x dp{world} (experts sharded {world}-way over NVLink peer-memory dispatch/combine, "
+                                       f"capacity factor {args.ep_capacity_factor}; dense params replicated, NCCL bucketed all-reduce)"
+                                       if args.layout == "ep" else
+                                       "pp4 x dp2 x ep2, looped_bfs 2 stages/rank (the reference example's layout), NCCL p2p between "
+                                       f"stages, NVLink EP dispatch/combine (capacity factor {args.ep_capacity_factor})"),
                        "optimizer": "stochastic_adamw bf16 states, fp32 grads, clip 5.0",
                        "l2": "working set exceeds the 126 MB L2"},
             "clocks": clocks,
@@ -243,7 +247,7 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
-    if args.layout == "ep":
+    if args.layout in ("ep", "example"):
         expert_parallel_arm(args)
         return
 

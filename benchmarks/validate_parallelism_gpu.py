@@ -22,10 +22,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 DEVICE, DTYPE = "cuda", torch.bfloat16  # ``--cpu`` (logic dry run on gloo) switches to cpu / fp32
 
 MESHES = {
+    # 2 GPUs
+    "dpr2": dict(data_parallel_replicate=2), "dps2": dict(data_parallel_shard=2), "dpr2_ep2": dict(data_parallel_replicate=2, expert_parallel=2),
     "cps2": dict(context_parallel_shard=2), "tp2": dict(tensor_parallel=2),
+    # 4 GPUs
+    "dpr4": dict(data_parallel_replicate=4), "dps4": dict(data_parallel_shard=4), "dpr2_dps2": dict(data_parallel_replicate=2, data_parallel_shard=2),
+    "dpr4_ep4": dict(data_parallel_replicate=4, expert_parallel=4), "dps4_ep2": dict(data_parallel_shard=4, expert_parallel=2),
     "cps4": dict(context_parallel_shard=4), "dpr2_tp2": dict(data_parallel_replicate=2, tensor_parallel=2),
     "dps2_tp2": dict(data_parallel_shard=2, tensor_parallel=2), "cpr2_tp2": dict(context_parallel_replicate=2, tensor_parallel=2),
     "dpr2_cps2": dict(data_parallel_replicate=2, context_parallel_shard=2),
+    # 8 GPUs: the single-stage meshes of the reference's distributed tier (test/d9d_test/modules/model/meshes.py) + TP / CP
+    "dpr8": dict(data_parallel_replicate=8), "dps8": dict(data_parallel_shard=8),
+    "dpr2_dps4": dict(data_parallel_replicate=2, data_parallel_shard=4),
+    "dpr8_ep2": dict(data_parallel_replicate=8, expert_parallel=2), "dps8_ep2": dict(data_parallel_shard=8, expert_parallel=2),
+    "dpr2_dps4_ep2": dict(data_parallel_replicate=2, data_parallel_shard=4, expert_parallel=2),
+    "dpr8_ep8": dict(data_parallel_replicate=8, expert_parallel=8),
+    "dpr2_cps2_tp2": dict(data_parallel_replicate=2, context_parallel_shard=2, tensor_parallel=2),
+    "dps4_tp2": dict(data_parallel_shard=4, tensor_parallel=2),
 }
 
 
@@ -77,7 +90,7 @@ def check_model(mesh_name: str, moe: bool) -> None:
         torch.manual_seed(5)
         if moe:
             from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLM as Cls, Qwen3MoEForCausalLMParameters as P, Qwen3MoELayerParameters as L, Qwen3MoEParameters as B
-            layer = L(hidden_size=hidden, intermediate_size=hidden // 2, num_experts=8, experts_top_k=2, num_attention_heads=8, num_key_value_heads=4, rms_norm_eps=1e-6, head_dim=hidden // 8)
+            layer = L(hidden_size=hidden, intermediate_size=hidden // 2, num_experts=16, experts_top_k=2, num_attention_heads=8, num_key_value_heads=4, rms_norm_eps=1e-6, head_dim=hidden // 8)
         else:
             from d9d_b200.module.model.qwen3_dense import Qwen3DenseForCausalLM as Cls, Qwen3DenseForCausalLMParameters as P, Qwen3DenseLayerParameters as L, Qwen3DenseParameters as B
             layer = L(hidden_size=hidden, intermediate_size=2 * hidden, num_attention_heads=8, num_key_value_heads=4, rms_norm_eps=1e-6, head_dim=hidden // 8)
@@ -123,6 +136,7 @@ def check_model(mesh_name: str, moe: bool) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--meshes", nargs="*", default=None)
+    ap.add_argument("--skip-attention", action="store_true")
     ap.add_argument("--cpu", action="store_true", help="dry run of the script's logic on gloo / cpu / fp32 with tiny shapes")
     args = ap.parse_args()
     global DEVICE, DTYPE
@@ -148,15 +162,15 @@ def main() -> None:
             bad = [f"rank {i}: {s}" for i, s in enumerate(flags) if s != "ok"]
             print(f"{label:60s} {'ok' if not bad else bad}", flush=True)
 
-    for mode in ("ulysses", "ring"):
+    for mode in (() if args.skip_attention else ("ulysses", "ring")):
         for layout in ("zigzag", "contiguous"):
             for causal in (True, False):
                 run(f"attention {mode} {layout} causal={causal} (world {world})", check_attention, mode, layout, causal)
     meshes = args.meshes if args.meshes is not None else [m for m, kw in MESHES.items() if _size(kw) == world]
     for mesh_name in meshes:
         for moe in (False, True):
-            if moe and "tp" in mesh_name and "ep" not in mesh_name and world < 2:
-                continue
+            if not moe and "ep" in mesh_name:
+                continue  # expert parallelism needs experts
             run(f"model {'moe' if moe else 'dense'} {mesh_name}", check_model, mesh_name, moe)
     dist.barrier()
     dist.destroy_process_group()

@@ -142,7 +142,8 @@ def trainer_config_for_bench(args, world: int, total_steps: int, workdir: str) -
         "batching": {"global_batch_size": args.accum * args.microbatch * world, "microbatch_size": args.microbatch},
         "data_loading": {"num_workers": 0, "pin_memory": True, "persistent_workers": False},
         "logging": {"period_steps": 10_000, "tracker": {"provider": "null"}},
-        "pipelining": {"schedule": {"schedule": "gpipe"}},
+        "pipelining": {"schedule": ({"schedule": "looped_bfs", "num_stages_per_rank": 2} if getattr(args, "layout", "dp") == "example"
+                                     else {"schedule": "gpipe"})},
         "model_stage_factory": {"source_checkpoint": None, "checkpoint_only_trainable_parameters": False},
         "determinism": {"base_seed": 1337},
         "gc": {"period_steps": 10_000},
@@ -184,8 +185,14 @@ class TrainerEndToEnd:
             {"mode": "rest", "target_multiplier": 1.0, "curve": {"type": "linear"}}]}})
         self.layout = layout
         nvlink_dp = layout == "dp" and world > 1 and getattr(args, "dp_impl", "nvlink") == "nvlink"
-        mesh = (DeviceMeshParameters(data_parallel_replicate=world, expert_parallel=world) if layout == "ep"
-                else DeviceMeshParameters(data_parallel_replicate=world))
+        if layout == "ep":
+            mesh = DeviceMeshParameters(data_parallel_replicate=world, expert_parallel=world)
+        elif layout == "example":  # the reference example's own layout (example/qwen3_moe/pretrain.json:2-10), 8 GPUs
+            if world != 8:
+                raise ValueError("--layout example is the reference's PP4 x DP2 x EP2 layout: it needs 8 GPUs")
+            mesh = DeviceMeshParameters(pipeline_parallel=4, data_parallel_replicate=2, expert_parallel=2)
+        else:
+            mesh = DeviceMeshParameters(data_parallel_replicate=world)
         self.trainer = TrainingConfigurator(
             mesh=mesh,
             parameters=TrainerConfig.model_validate(trainer_config_for_bench(args, world, self.total_steps, workdir)),
@@ -251,7 +258,7 @@ class TrainerEndToEnd:
         # bytes moved per optimizer step and rank: input_ids + labels + position_ids (int64) up, one fp32 loss down
         h2d = args.accum * 3 * args.microbatch * args.seq_len * 8
         overflow = None
-        if self.layout == "ep":
+        if self.layout in ("ep", "example"):
             from d9d_b200.module.block.moe.communications.nvlink import NvlinkExpertParallelCommunicationHandler as H
 
             overflow = any(h.overflowed for h in H.instances)

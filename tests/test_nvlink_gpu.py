@@ -98,6 +98,14 @@ def test_nvlink_sharded_adamw_matches_reference(state_dtype, max_norm, multimem,
     _spawn(_sharded_adamw_worker, 2, state_dtype, max_norm, overlap)
 
 
+@pytest.mark.parametrize("world", [4, 8])
+@pytest.mark.parametrize("multimem", ["0", "1"])
+def test_nvlink_sharded_adamw_matches_reference_on_more_gpus(world, multimem, monkeypatch):
+    _need_gpus(world)
+    monkeypatch.setenv("D9D_NVLINK_MULTIMEM", multimem)
+    _spawn(_sharded_adamw_worker, world, torch.bfloat16, 1.0, True)
+
+
 def _trainer_worker(rank, world, optimizer_name, tmp, expert_parallel=1):
     from pathlib import Path
 
@@ -229,9 +237,10 @@ def _tp_gemm_worker(rank, world):
         out.barrier()
 
 
-def test_tensor_parallel_gemms_with_fused_communication():
-    _need_gpus(2)
-    _spawn(_tp_gemm_worker, 2)
+@pytest.mark.parametrize("world", [2, 4])
+def test_tensor_parallel_gemms_with_fused_communication(world):
+    _need_gpus(world)
+    _spawn(_tp_gemm_worker, world)
 
 
 def _tp_mlp_worker(rank, world):
@@ -294,7 +303,7 @@ def _ep_worker(rank, world):
     from d9d_b200.module.block.moe import MoELayer
     from d9d_b200.module.parallelism.api import parallelize_expert_parallel
 
-    E, k, H, F = 8, 2, 256, 192
+    E, k, H, F = 16, 2, 256, 192
     torch.manual_seed(3)
     ref = MoELayer(hidden_dim=H, intermediate_dim_grouped=F, num_grouped_experts=E, top_k=k, router_renormalize_probabilities=True)
     ref.reset_parameters()
@@ -337,9 +346,13 @@ def _ep_worker(rank, world):
     close(gate.to_local() if hasattr(gate, "to_local") else gate, ref.router.gate.weight.grad, "router")
 
 
-def test_expert_parallel_over_nvlink_matches_local_experts():
-    _need_gpus(2)
-    _spawn(_ep_worker, 2)
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("capacity_factor", ["0", "4"])
+def test_expert_parallel_over_nvlink_matches_local_experts(world, capacity_factor, monkeypatch):
+    """EP = world: worst-case buffers and capacity-factor buffers (generous enough not to drop anything here)."""
+    _need_gpus(world)
+    monkeypatch.setenv("D9D_EP_CAPACITY_FACTOR", capacity_factor)
+    _spawn(_ep_worker, world)
 
 
 def test_trainer_with_expert_parallel_over_nvlink(tmp_path):

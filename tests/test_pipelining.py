@@ -189,10 +189,11 @@ def _pp_case(ctx, cfg_json, n_mb, freeze):
 
     cfg = TypeAdapter(AnyPipelineScheduleConfig).validate_json(cfg_json)
     batch = n_mb * 2
+    dev = ctx.current_device  # cpu (gloo) or this rank's GPU (NCCL p2p, tests/test_parallelism_gpu.py)
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(batch, 16, generator=g)
-    scale = torch.rand(batch, generator=g) + 0.5
-    target = torch.randn(batch, 16, generator=g)
+    x = torch.randn(batch, 16, generator=g).to(dev)
+    scale = (torch.rand(batch, generator=g) + 0.5).to(dev)
+    target = torch.randn(batch, 16, generator=g).to(dev)
     target_mb = target.chunk(n_mb)
     losses = {}
 
@@ -208,7 +209,7 @@ def _pp_case(ctx, cfg_json, n_mb, freeze):
 
     hits = {}
     is_inference = cfg.schedule == "inference"
-    info, modules = build_schedule(ctx, n_mb, cfg, lambda st: _StageModel(st, freeze_some=freeze),
+    info, modules = build_schedule(ctx, n_mb, cfg, lambda st: _StageModel(st, freeze_some=freeze).to(dev),
                                    result_fn if is_inference else loss_fn)
     for mi, mod in enumerate(modules):
         for n, p in mod.named_parameters():
@@ -227,7 +228,7 @@ def _pp_case(ctx, cfg_json, n_mb, freeze):
 
     # sequential reference on every rank
     num_stages = modules[0]._stage.num_stages
-    ref_stages = [_StageModel(PipelineStageInfo(s, num_stages), freeze_some=freeze) for s in range(num_stages)]
+    ref_stages = [_StageModel(PipelineStageInfo(s, num_stages), freeze_some=freeze).to(dev) for s in range(num_stages)]
     h = x
     for s, st in enumerate(ref_stages):
         h = st(x=h, scale=scale)["hidden"] if s == 0 else st(hidden=h, scale=scale)["hidden"]
