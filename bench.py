@@ -61,6 +61,7 @@ def parse_args():
                          "reference example's PP4 x DP2 x EP2 layout with looped_bfs, 2 stages per rank (8 GPUs)")
     ap.add_argument("--model", default="example", choices=["example", "30b-a3b"],
                     help="example: the reference's example/qwen3_moe/pretrain.json model; 30b-a3b: Qwen3-30B-A3B shape (needs --layout ep on 8 GPUs)")
+    ap.add_argument("--checkpointing", action="store_true", help="per-layer activation checkpointing (needed by the 30b-a3b shape)")
     ap.add_argument("--ep-capacity-factor", type=float, default=2.0,
                     help="receive capacity of an expert-parallel rank as a multiple of its fair share (0 = worst case)")
     return ap.parse_args()
@@ -202,6 +203,7 @@ def expert_parallel_arm(args) -> None:
                                        "pp4 x dp2 x ep2, looped_bfs 2 stages/rank (the reference example's layout), NCCL p2p between "
                                        f"stages, NVLink EP dispatch/combine (capacity factor {args.ep_capacity_factor})"),
                        "optimizer": "stochastic_adamw bf16 states, fp32 grads, clip 5.0",
+                       "activation_checkpointing": bool(args.checkpointing),
                        "l2": "working set exceeds the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": res["h2d_bytes_per_step"],

@@ -197,7 +197,7 @@ class TrainerEndToEnd:
             mesh=mesh,
             parameters=TrainerConfig.model_validate(trainer_config_for_bench(args, world, self.total_steps, workdir)),
             task_provider=lambda ctx: CausalLMTask(),
-            model_provider=Qwen3MoEModelProvider(Qwen3MoEModelProviderConfig(model=model_params)),
+            model_provider=Qwen3MoEModelProvider(Qwen3MoEModelProviderConfig(model=model_params, checkpointing=bool(getattr(args, "checkpointing", False)))),
             data_provider=SyntheticDataProvider(SyntheticDataConfig(
                 num_samples=global_batch * self.total_steps, seq_len=args.seq_len, vocab_size=vocab, seed=5)),
             optimizer_provider=AutoOptimizerProvider(

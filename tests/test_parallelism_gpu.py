@@ -16,7 +16,7 @@ import sys
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -25,7 +25,7 @@ def _gpus() -> int:
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _torchrun(world: int, script_args: list[str], timeout: int = 900) -> None:
+def _torchrun(world: int, script_args: list[str], timeout: int = 420) -> None:
     port = 29800 + (os.getpid() % 150)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), *script_args]
