@@ -37,7 +37,6 @@ MESHES = {
     "dpr8_ep2": dict(data_parallel_replicate=8, expert_parallel=2), "dps8_ep2": dict(data_parallel_shard=8, expert_parallel=2),
     "dpr2_dps4_ep2": dict(data_parallel_replicate=2, data_parallel_shard=4, expert_parallel=2),
     "dpr8_ep8": dict(data_parallel_replicate=8, expert_parallel=8),
-    "dpr2_cps2_tp2": dict(data_parallel_replicate=2, context_parallel_shard=2, tensor_parallel=2),
     "dps4_tp2": dict(data_parallel_shard=4, tensor_parallel=2),
 }
 
