@@ -56,6 +56,17 @@ class _Workspace:
         self.group = group
         self.region: _Region | None = None
         self.num_experts = 0
+        # receive buffers not in use by any layer.  Shared by all layers of the group: without activation checkpointing every
+        # layer keeps its buffer from forward to backward (the pool just grows to one per layer and microbatch in flight),
+        # with checkpointing a handful of buffers serve the whole model.
+        self.pool: list[_Region] = []
+
+    def acquire(self, rows: int, hidden: int, device: torch.device) -> "_Region":
+        for i, r in enumerate(self.pool):
+            if r.rows >= rows and r.hidden == hidden:
+                return self.pool.pop(i)
+        # collective allocation: every rank of the group runs the same schedule, so pools grow in lock-step
+        return _Region(rows, hidden, self.group, device)
 
     @classmethod
     def for_group(cls, group: dist.ProcessGroup) -> "_Workspace":
@@ -85,6 +96,19 @@ class _Workspace:
         self.region.arena.barrier()
 
 
+class _ReleaseOnDelete:
+    """Runs ``release`` when the last reference (the autograd node's context) goes away."""
+
+    def __init__(self, release: Any):
+        self._release = release
+
+    def __del__(self) -> None:
+        try:
+            self._release()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
 @dataclasses.dataclass
 class _Plan:
     ws: _Workspace
@@ -96,6 +120,7 @@ class _Plan:
     num_tokens: int
     top_k: int
     hidden: int
+    guard: Any = None
 
 
 class _Dispatch(Function):
@@ -110,6 +135,9 @@ class _Dispatch(Function):
         plan.ws.barrier()  # every peer's rows have landed
         cap = plan.layout.capacity
         ctx.plan, ctx.probs_dtype = plan, probs.dtype
+        # a graph that is dropped without a backward pass (the recomputation of non-reentrant activation checkpointing,
+        # an abandoned forward) must still hand its receive buffer back
+        plan.guard = _ReleaseOnDelete(plan.release)
         return recv.x[:cap], recv.p[:cap]
 
     @staticmethod
@@ -185,7 +213,6 @@ class NvlinkExpertParallelCommunicationHandler(ExpertCommunicationHandler):
         self._num_experts = num_experts
         self._group: dist.ProcessGroup | None = None
         self._plan: _Plan | None = None
-        self._pool: list[_Region] = []
         self._overflow: torch.Tensor | None = None
         NvlinkExpertParallelCommunicationHandler.instances.append(self)
 
@@ -198,13 +225,6 @@ class NvlinkExpertParallelCommunicationHandler(ExpertCommunicationHandler):
     def overflowed(self) -> bool:
         """True if rows were dropped because a capacity factor was too small (host synchronisation)."""
         return bool(self._overflow.item()) if self._overflow is not None else False
-
-    def _acquire(self, rows: int, hidden: int, device: torch.device) -> _Region:
-        for i, r in enumerate(self._pool):
-            if r.rows >= rows and r.hidden == hidden:
-                return self._pool.pop(i)
-        # collective allocation: every rank of the group runs the same schedule, so pools grow in lock-step
-        return _Region(rows, hidden, self._group, device)
 
     def dispatch(self, hidden_states: torch.Tensor, topk_ids: torch.Tensor, topk_weights: torch.Tensor):
         group = self._group
@@ -221,7 +241,7 @@ class NvlinkExpertParallelCommunicationHandler(ExpertCommunicationHandler):
             capacity = min(capacity, layout_capacity(int(math.ceil(tokens * factor)), top_k, local_experts))
         ws = _Workspace.for_group(group)
         ws.ensure(capacity, hidden, experts, device)
-        recv = self._acquire(capacity, hidden, device)
+        recv = ws.acquire(capacity, hidden, device)
 
         send = build_moe_layout(topk_ids, experts, align=1)  # counts / offsets / stable sorted position per pair
         for peer in range(world):
@@ -265,7 +285,7 @@ class NvlinkExpertParallelCommunicationHandler(ExpertCommunicationHandler):
         def release() -> None:
             if not released:
                 released.append(True)
-                self._pool.append(recv)
+                ws.pool.append(recv)
 
         plan = _Plan(ws=ws, recv=recv, release=release, dest_rank=dest_rank, dest_row=dest_row, layout=layout, num_tokens=tokens,
                      top_k=top_k, hidden=hidden)
