@@ -8,6 +8,7 @@ _KERNELS_PER_OP = {
     "moe_build_layout": 3,
     "moe_permute": 2,
     "ce_forward": 3,  # zero-fill of the target-logit buffer + GEMM + finalize
+    "ce_forward_ex": 3,
     "flash_attn_bwd": 3,  # delta pre-pass + dK/dV kernel + dQ kernel
 }
 

@@ -28,8 +28,12 @@ class SplitLanguageModellingHead(nn.Module, ModuleLateInit):
         parts = [self.lm_head[name].weight for name in self._split_order]
         return parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
 
+    def classifier_blocks(self) -> list[torch.Tensor]:
+        """The classifier as row blocks in vocabulary order (consumed in place by the fused linear-CE kernels)."""
+        return [self.lm_head[name].weight for name in self._split_order]
+
     def forward(self, hidden_states: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        return linear_cross_entropy(hidden_states, self.classifier_weight(), labels, ignore_index=LM_IGNORE_INDEX, reduction="none")
+        return linear_cross_entropy(hidden_states, self.classifier_blocks(), labels, ignore_index=LM_IGNORE_INDEX, reduction="none")
 
     def reset_parameters(self) -> None:
         for head in self.lm_head.values():

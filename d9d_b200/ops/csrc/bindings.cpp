@@ -92,8 +92,10 @@ void gemm_grouped_k(const Tensor& a, const Tensor& b, Tensor d, const Tensor& gr
   d9d::gemm_grouped(g, cur_stream());
 }
 
-// fused linear-CE forward: returns (nll[T] fp32, lse[T] fp32)
-std::tuple<Tensor, Tensor> ce_forward(const Tensor& h, const Tensor& w, const Tensor& target, int64_t ignore_index) {
+// fused linear-CE forward over a row slice w = C[col_offset : col_offset + V] of the classifier:
+// returns (nll[T], lse[T], tgt_logit[T]) fp32; tgt_logit is 0 where the target lies outside the slice (nll is then lse)
+std::tuple<Tensor, Tensor, Tensor> ce_forward_ex(const Tensor& h, const Tensor& w, const Tensor& target, int64_t ignore_index,
+                                                 const c10::optional<Tensor>& bias, double softcap, int64_t col_offset) {
   CHECK_CUDA_CONTIG(h); CHECK_CUDA_CONTIG(w); CHECK_CUDA_CONTIG(target);
   TORCH_CHECK(h.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && target.scalar_type() == at::kLong);
   c10::cuda::CUDAGuard guard(h.device());
@@ -108,20 +110,34 @@ std::tuple<Tensor, Tensor> ce_forward(const Tensor& h, const Tensor& w, const Te
   g.mode = 0; g.epi = 4;
   g.M = T; g.N = V; g.K = K;
   g.A = h.data_ptr(); g.B = w.data_ptr(); g.lda = K; g.ldb = K; g.ldd = V;
-  g.ce_target = target.data_ptr<int64_t>() ? reinterpret_cast<const long long*>(target.data_ptr<int64_t>()) : nullptr;
+  g.ce_target = reinterpret_cast<const long long*>(target.data_ptr<int64_t>());
   g.ce_part_max = part_max.data_ptr<float>(); g.ce_part_sum = part_sum.data_ptr<float>();
   g.ce_tgt_logit = tgt_logit.data_ptr<float>();
   g.ce_ignore_index = ignore_index;
+  g.ce_softcap = static_cast<float>(softcap);
+  g.ce_col_offset = col_offset;
+  if (bias.has_value()) {
+    CHECK_CUDA_CONTIG(*bias);
+    TORCH_CHECK(bias->scalar_type() == at::kFloat && bias->numel() == V, "ce: bias must be fp32 [V]");
+    g.ce_bias = bias->data_ptr<float>();
+  }
   d9d::gemm_ce(g, cur_stream());
   d9d::ce_finalize(part_max.data_ptr<float>(), part_sum.data_ptr<float>(), tgt_logit.data_ptr<float>(),
                    reinterpret_cast<const long long*>(target.data_ptr<int64_t>()), ignore_index, n_tiles, T,
                    lse.data_ptr<float>(), nll.data_ptr<float>(), cur_stream());
-  return {nll, lse};
+  return {nll, lse, tgt_logit};
 }
 
-// fused linear-CE backward, one token chunk: out[Tc, V] (bf16) = grad[t] * (softmax(h w^T) - onehot(target))
+// fused linear-CE forward: returns (nll[T] fp32, lse[T] fp32)
+std::tuple<Tensor, Tensor> ce_forward(const Tensor& h, const Tensor& w, const Tensor& target, int64_t ignore_index) {
+  auto r = ce_forward_ex(h, w, target, ignore_index, c10::nullopt, 0.0, 0);
+  return {std::get<0>(r), std::get<1>(r)};
+}
+
+// fused linear-CE backward, one chunk: out[T, V] (bf16) = grad[t] * d nll[t] / d logits[t, col_offset : col_offset + V]
+// (w is the matching row slice of the classifier; lse is the log-sum-exp over the WHOLE vocabulary)
 void ce_dlogits(const Tensor& h, const Tensor& w, const Tensor& target, const Tensor& lse, const Tensor& grad,
-                Tensor out, int64_t ignore_index) {
+                Tensor out, int64_t ignore_index, const c10::optional<Tensor>& bias, double softcap, int64_t col_offset) {
   CHECK_CUDA_CONTIG(h); CHECK_CUDA_CONTIG(w); CHECK_CUDA_CONTIG(target); CHECK_CUDA_CONTIG(lse);
   CHECK_CUDA_CONTIG(grad);
   TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.stride(1) == 1, "ce_dlogits: out must be row-major (row pitch may be padded)");
@@ -136,6 +152,13 @@ void ce_dlogits(const Tensor& h, const Tensor& w, const Tensor& target, const Te
   g.ce_target = reinterpret_cast<const long long*>(target.data_ptr<int64_t>());
   g.ce_lse = lse.data_ptr<float>(); g.ce_grad = grad.data_ptr<float>();
   g.ce_ignore_index = ignore_index;
+  g.ce_softcap = static_cast<float>(softcap);
+  g.ce_col_offset = col_offset;
+  if (bias.has_value()) {
+    CHECK_CUDA_CONTIG(*bias);
+    TORCH_CHECK(bias->scalar_type() == at::kFloat && bias->numel() == V, "ce: bias must be fp32 [V]");
+    g.ce_bias = bias->data_ptr<float>();
+  }
   d9d::gemm_ce(g, cur_stream());
 }
 
@@ -678,7 +701,8 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("gemm_grouped_m(Tensor a, Tensor b, Tensor(a!) d, Tensor tile_group, bool b_mn, bool accumulate=False) -> ()");
   m.def("gemm_grouped_k(Tensor a, Tensor b, Tensor(a!) d, Tensor group_offsets, bool accumulate) -> ()");
   m.def("ce_forward(Tensor h, Tensor w, Tensor target, int ignore_index) -> (Tensor, Tensor)");
-  m.def("ce_dlogits(Tensor h, Tensor w, Tensor target, Tensor lse, Tensor grad, Tensor(a!) out, int ignore_index) -> ()");
+  m.def("ce_forward_ex(Tensor h, Tensor w, Tensor target, int ignore_index, Tensor? bias=None, float softcap=0.0, int col_offset=0) -> (Tensor, Tensor, Tensor)");
+  m.def("ce_dlogits(Tensor h, Tensor w, Tensor target, Tensor lse, Tensor grad, Tensor(a!) out, int ignore_index, Tensor? bias=None, float softcap=0.0, int col_offset=0) -> ()");
   m.def("rms_norm_fwd(Tensor x, Tensor w, float eps, bool zero_centered) -> (Tensor, Tensor)");
   m.def("rms_norm_bwd(Tensor dout, Tensor x, Tensor w, Tensor inv_rms, bool zero_centered) -> (Tensor, Tensor)");
   m.def("silu_mul_fwd(Tensor x, Tensor y) -> Tensor");
@@ -724,6 +748,7 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("gemm_grouped_m", &gemm_grouped_m);
   m.impl("gemm_grouped_k", &gemm_grouped_k);
   m.impl("ce_forward", &ce_forward);
+  m.impl("ce_forward_ex", &ce_forward_ex);
   m.impl("ce_dlogits", &ce_dlogits);
   m.impl("rms_norm_fwd", &rms_norm_fwd);
   m.impl("rms_norm_bwd", &rms_norm_bwd);

@@ -44,6 +44,9 @@ struct GemmArgs {
   float* ce_part_sum = nullptr;
   float* ce_tgt_logit = nullptr;
   long long ce_ignore_index = -100;
+  float ce_softcap = 0.f;              // logits -> softcap * tanh(logits / softcap); 0 = off
+  const float* ce_bias = nullptr;      // [N] fp32 logit bias
+  long long ce_col_offset = 0;         // B is a row slice of the classifier starting at this class id
 };
 
 void gemm_dense(const GemmArgs& a, cudaStream_t stream);

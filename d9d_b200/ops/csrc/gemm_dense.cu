@@ -11,7 +11,7 @@ void gemm_dense(const GemmArgs& a, cudaStream_t stream) {
   if (!a.a_mn && !a.b_mn) {
     D9D_DISPATCH_EPI4(DENSE, false, false, a.epi, bn, a, stream);
   } else if (!a.a_mn && a.b_mn) {
-    D9D_DISPATCH_EPI2(DENSE, false, true, a.epi, bn, a, stream);
+    D9D_DISPATCH_EPI4(DENSE, false, true, a.epi, bn, a, stream);  // accumulate: chunked dE of the fused linear-CE
   } else if (a.a_mn && a.b_mn) {
     D9D_DISPATCH_EPI4(DENSE, true, true, a.epi, bn, a, stream);
   } else {

@@ -152,7 +152,8 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   p.tile_group = a.tile_group; p.group_offsets = a.group_offsets;
   p.ce_target = a.ce_target; p.ce_lse = a.ce_lse; p.ce_grad = a.ce_grad;
   p.ce_part_max = a.ce_part_max; p.ce_part_sum = a.ce_part_sum; p.ce_tgt_logit = a.ce_tgt_logit;
-  p.ce_ignore_index = a.ce_ignore_index; p.ce_softcap = 0.f;
+  p.ce_ignore_index = a.ce_ignore_index; p.ce_softcap = a.ce_softcap; p.ce_bias = a.ce_bias;
+  p.ce_col_offset = a.ce_col_offset;
 
   const long long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   long long tiles = m_tiles * n_tiles * (MODE == GROUPED_K ? a.num_groups : 1) * p.k_splits;

@@ -85,8 +85,22 @@ struct Params {
   float* ce_part_sum;          // [n_tiles, M]  (LSE)
   float* ce_tgt_logit;         // [M]           (LSE) written by the tile that owns the target column
   long long ce_ignore_index;
-  float ce_softcap;  // unused (0)
+  float ce_softcap;            // logits -> softcap * tanh(logits / softcap) (0 = off)
+  const float* ce_bias;        // [N] fp32 added to the logits (or nullptr)
+  long long ce_col_offset;     // B is a row slice of the classifier: global class id of its first row
 };
+
+// logit transform shared by the fused-CE epilogues: z = softcap(acc + bias); returns z and dz/dacc
+__device__ __forceinline__ float ce_transform(float acc, float bias, float cap, float inv_cap, float& dz) {
+  float z = acc + bias;
+  dz = 1.f;
+  if (cap > 0.f) {
+    const float th = tanhf(z * inv_cap);
+    z = cap * th;
+    dz = 1.f - th * th;
+  }
+  return z;
+}
 
 template <int BLOCK_N>
 struct Cfg {
@@ -363,7 +377,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if constexpr (EPI == EPI_CE_LSE) {
         // online softmax statistics over this tile's columns
         float run_max = -INFINITY, run_sum = 0.f;
-        const long long tgt = row_ok ? p.ce_target[row] : -1;
+        long long tgt = row_ok ? p.ce_target[row] : -1;
+        tgt = (tgt == p.ce_ignore_index) ? -1 : tgt - p.ce_col_offset;  // class id relative to this slice of the classifier
+        const bool ce_xf = (p.ce_bias != nullptr) || (p.ce_softcap > 0.f);  // warp-uniform
+        const float ce_inv_cap = p.ce_softcap > 0.f ? 1.f / p.ce_softcap : 0.f;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t r[32];
@@ -371,6 +388,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
           const int cbase = col0 + c * 32;
+          if (ce_xf) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float dz;
+              const float b = (p.ce_bias != nullptr && cbase + i < p.N) ? p.ce_bias[cbase + i] : 0.f;
+              r[i] = __float_as_uint(ce_transform(__uint_as_float(r[i]), b, p.ce_softcap, ce_inv_cap, dz));
+            }
+          }
           float cmax = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -404,12 +429,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         static_assert(BLOCK_N % CHUNK_COLS == 0, "BLOCK_N must be a multiple of the epilogue chunk");
         float lse = 0.f, g = 0.f;
         long long tgt = -1;
+        [[maybe_unused]] bool ce_xf = false;
+        [[maybe_unused]] float ce_inv_cap = 0.f;
         if constexpr (EPI == EPI_CE_DLOGITS) {
           if (row_ok) {
             tgt = p.ce_target[row];
             lse = p.ce_lse[row];
             g = (tgt == p.ce_ignore_index) ? 0.f : p.ce_grad[row];
+            tgt = (tgt == p.ce_ignore_index) ? -1 : tgt - p.ce_col_offset;
           }
+          ce_xf = (p.ce_bias != nullptr) || (p.ce_softcap > 0.f);  // warp-uniform
+          ce_inv_cap = p.ce_softcap > 0.f ? 1.f / p.ce_softcap : 0.f;
         }
         if (have_acc || !REDUCE) {
 #pragma unroll 1
@@ -433,11 +463,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                   for (int i = 0; i < 32; ++i) r[i] = 0;
                 }
                 if constexpr (EPI == EPI_CE_DLOGITS) {
+                  if (!ce_xf) {
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) {
-                    float pr = __expf(__uint_as_float(r[i]) - lse);
-                    if (cbase + h * 32 + i == tgt) pr -= 1.f;
-                    r[i] = __float_as_uint(pr * g);
+                    for (int i = 0; i < 32; ++i) {
+                      float pr = __expf(__uint_as_float(r[i]) - lse);
+                      if (cbase + h * 32 + i == tgt) pr -= 1.f;
+                      r[i] = __float_as_uint(pr * g);
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                      const int col = cbase + h * 32 + i;
+                      float dz;
+                      const float b = (p.ce_bias != nullptr && col < p.N) ? p.ce_bias[col] : 0.f;
+                      float pr = __expf(ce_transform(__uint_as_float(r[i]), b, p.ce_softcap, ce_inv_cap, dz) - lse);
+                      if (col == tgt) pr -= 1.f;
+                      r[i] = __float_as_uint(pr * g * dz);
+                    }
                   }
                 }
 #pragma unroll
@@ -479,12 +521,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (MODE == GROUPED_K) d_off += static_cast<long long>(t.group) * p.d_group_stride;
         float lse = 0.f, g = 0.f;
         long long tgt = -1;
+        [[maybe_unused]] bool ce_xf = false;
+        [[maybe_unused]] float ce_inv_cap = 0.f;
         if constexpr (EPI == EPI_CE_DLOGITS) {
           if (row_ok) {
             tgt = p.ce_target[row];
             lse = p.ce_lse[row];
             g = (tgt == p.ce_ignore_index) ? 0.f : p.ce_grad[row];
+            tgt = (tgt == p.ce_ignore_index) ? -1 : tgt - p.ce_col_offset;
           }
+          ce_xf = (p.ce_bias != nullptr) || (p.ce_softcap > 0.f);  // warp-uniform
+          ce_inv_cap = p.ce_softcap > 0.f ? 1.f / p.ce_softcap : 0.f;
         }
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -502,9 +549,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if constexpr (EPI == EPI_CE_DLOGITS) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float pr = __expf(__uint_as_float(r[i]) - lse);
+              float dz = 1.f, z = __uint_as_float(r[i]);
+              if (ce_xf) {
+                const float b = (p.ce_bias != nullptr && cbase + i < p.N) ? p.ce_bias[cbase + i] : 0.f;
+                z = ce_transform(z, b, p.ce_softcap, ce_inv_cap, dz);
+              }
+              float pr = __expf(z - lse);
               if (cbase + i == tgt) pr -= 1.f;
-              r[i] = __float_as_uint(pr * g);
+              r[i] = __float_as_uint(pr * g * dz);
             }
           }
           const bool full_chunk = (cbase + 32 <= p.N);

@@ -149,6 +149,84 @@ def test_linear_ce(ops, T, V, K):
     assert _rel_err(out, refg) < 2e-2
 
 
+@pytest.mark.parametrize("softcap,with_bias", [(0.0, False), (8.0, False), (0.0, True), (8.0, True)])
+def test_linear_ce_slice_options(ops, softcap, with_bias):
+    """Bias / tanh soft-capping / class-id offset of a classifier slice inside the CE epilogues."""
+    T, V, K, v0, v1 = 384, 1500, 128, 520, 1300
+    h = (torch.randn(T, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(V, K, device="cuda") * 0.2).bfloat16()
+    bias = torch.randn(V, device="cuda") * 0.5 if with_bias else None
+    tgt = torch.randint(0, V, (T,), device="cuda")
+    tgt[::7] = -100
+    z = h.float() @ w.float().t()
+    if with_bias:
+        z = z + bias
+    dz = torch.ones_like(z)
+    if softcap > 0:
+        th = torch.tanh(z / softcap)
+        z, dz = softcap * th, 1 - th * th
+    zs = z[:, v0:v1]
+    b = bias[v0:v1].contiguous() if with_bias else None
+    nll, lse, tl = ops.ce_forward_ex(h, w[v0:v1], tgt, -100, b, softcap, v0)
+    inside = (tgt >= v0) & (tgt < v1)
+    ref_lse = torch.logsumexp(zs, -1)
+    ref_tl = torch.where(inside, z.gather(1, tgt.clamp(0, V - 1)[:, None])[:, 0], torch.zeros_like(ref_lse))
+    assert torch.allclose(lse, ref_lse, atol=3e-3, rtol=3e-3)
+    assert torch.allclose(tl, ref_tl, atol=3e-3, rtol=3e-3)
+    assert torch.allclose(nll, torch.where(tgt == -100, torch.zeros_like(lse), ref_lse - ref_tl), atol=5e-3, rtol=5e-3)
+    full_lse = torch.logsumexp(z, -1)
+    g = torch.rand(T, device="cuda")
+    out = torch.empty(T, (v1 - v0 + 127) // 128 * 128, device="cuda", dtype=torch.bfloat16)[:, : v1 - v0]
+    ops.ce_dlogits(h, w[v0:v1], tgt, full_lse, g, out, -100, b, softcap, v0)
+    p = torch.exp(zs - full_lse[:, None])
+    rows = torch.nonzero(inside)[:, 0]
+    p[rows, tgt[rows] - v0] -= 1
+    ref = p * (g * (tgt != -100))[:, None] * dz[:, v0:v1]
+    assert _rel_err(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("sizes", [(4000,), (3000, 24), (1000, 520, 8)])
+@pytest.mark.parametrize("budget", [1 << 30, 512 * 1024 * 2])
+@pytest.mark.parametrize("fused_wgrad", [False, True])
+def test_linear_cross_entropy_split_blocks_autograd(monkeypatch, sizes, budget, fused_wgrad):
+    """The public function over split classifier blocks with the vocabulary-chunked backward vs fp32 autograd."""
+    from d9d_b200.kernel import _native
+    from d9d_b200.kernel.cce import main as cce
+
+    monkeypatch.setattr(cce, "_CHUNK_BYTES", budget)
+    T, K = 512, 256
+    e = (torch.randn(T, K, device="cuda") * 0.5).bfloat16().requires_grad_()
+    ws = [(torch.randn(s, K, device="cuda") * 0.1).bfloat16().requires_grad_() for s in sizes]
+    tgt = torch.randint(0, sum(sizes), (T,), device="cuda")
+    tgt[::9] = -100
+    tgt[3] = sum(sizes) - 1
+    if fused_wgrad:
+        for w in ws:
+            w.grad = torch.full(w.shape, 0.5, device="cuda", dtype=torch.float32)
+            setattr(w, _native.FUSED_WGRAD_ATTR, True)
+    loss = cce.linear_cross_entropy(e, ws, tgt, reduction="sum")
+    loss.backward()
+    e2 = e.detach().float().requires_grad_()
+    w2 = [w.detach().float().requires_grad_() for w in ws]
+    nll, _ = cce.linear_cross_entropy_reference(e2, torch.cat(w2), tgt)
+    nll.sum().backward()
+    assert abs(loss.item() - nll.sum().item()) < 2e-3 * abs(nll.sum().item())
+    assert _rel_err(e.grad, e2.grad) < 2e-2
+    for w, r in zip(ws, w2):
+        assert _rel_err(w.grad.float() - (0.5 if fused_wgrad else 0.0), r.grad) < 2e-2
+
+
+def test_gemm_dgrad_layout_fp32_accumulate(ops):
+    # d[M,N] (fp32) += a[M,K] @ b[K,N]: the accumulate epilogue of the chunked linear-CE input gradient
+    M, N, K = 1024, 768, 2048
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    d0 = torch.randn(M, N, device="cuda", dtype=torch.float32)
+    d = d0.clone()
+    ops.gemm(a, b, d, False, True, True)
+    assert _rel_err(d, a.float() @ b.float() + d0) < 1e-4
+
+
 # ----------------------------------------------------------------------------- RMSNorm
 @pytest.mark.parametrize("N", [64, 128, 256, 768, 1024, 2048, 4096, 7168])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
