@@ -162,6 +162,93 @@ void ce_dlogits(const Tensor& h, const Tensor& w, const Tensor& target, const Te
   d9d::gemm_ce(g, cur_stream());
 }
 
+// ------------------------------------------------------------------ fp8 GEMM -----------------------
+// x[M,K] bf16 -> (q[M,K] e4m3, scale[M] fp32) with x ~= q * scale[:, None]
+std::tuple<Tensor, Tensor> quantize_rowwise(const Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == at::kBFloat16, "quantize_rowwise: 2-D bf16 CUDA tensor required");
+  TORCH_CHECK(x.size(1) % 16 == 0 && x.stride(0) % 8 == 0 && (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0,
+              "quantize_rowwise: K must be a multiple of 16 and rows 16-byte aligned");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t M = x.size(0), K = x.size(1);
+  Tensor q = at::empty({M, K}, x.options().dtype(at::kFloat8_e4m3fn));
+  Tensor scale = at::empty({M}, x.options().dtype(at::kFloat));
+  d9d::quantize_rowwise_e4m3(x.data_ptr(), q.data_ptr(), scale.data_ptr<float>(), M, static_cast<int>(K), x.stride(0), cur_stream());
+  return {q, scale};
+}
+
+// x[R,C] bf16 -> (qt[C,R] e4m3 (row pitch padded to 16 bytes), scale[C] fp32) with x[r,c] ~= qt[c,r] * scale[c]
+std::tuple<Tensor, Tensor> quantize_colwise_t(const Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == at::kBFloat16, "quantize_colwise_t: 2-D bf16 CUDA tensor required");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t R = x.size(0), C = x.size(1);
+  const int64_t pitch = (R + 15) / 16 * 16;
+  Tensor qt = at::zeros({C, pitch}, x.options().dtype(at::kFloat8_e4m3fn));
+  Tensor scale = at::empty({C}, x.options().dtype(at::kFloat));
+  Tensor amax = at::empty({C}, x.options().dtype(at::kFloat));
+  d9d::quantize_colwise_t_e4m3(x.data_ptr(), qt.data_ptr(), scale.data_ptr<float>(), amax.data_ptr<float>(), R, static_cast<int>(C),
+                               x.stride(0), pitch, cur_stream());
+  return {qt.narrow(1, 0, R), scale};
+}
+
+// x[M,K] bf16 -> (q[M,K] e4m3, sf uint8 [2*ceil(M/256), K/128, 512]): OCP MXFP8, one UE8M0 scale per 32 elements along K,
+// stored in the 128-row x 4-group block layout tcgen05.cp expects
+std::tuple<Tensor, Tensor> quantize_mx(const Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == at::kBFloat16, "quantize_mx: 2-D bf16 CUDA tensor required");
+  TORCH_CHECK(x.size(1) % 128 == 0 && x.stride(0) % 8 == 0 && (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15) == 0,
+              "quantize_mx: K must be a multiple of 128 and rows 16-byte aligned");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int64_t M = x.size(0), K = x.size(1);
+  Tensor q = at::empty({M, K}, x.options().dtype(at::kFloat8_e4m3fn));
+  Tensor sf = at::zeros({(M + 255) / 256 * 2, K / 128, 512}, x.options().dtype(at::kByte));
+  d9d::quantize_mx_e4m3(x.data_ptr(), q.data_ptr(), sf.data_ptr(), M, static_cast<int>(K), x.stride(0), cur_stream());
+  return {q, sf};
+}
+
+static void fill_fp8_operands(d9d::Fp8GemmArgs& g, const Tensor& a, const Tensor& b, Tensor& d) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda() && a.dim() == 2 && b.dim() == 2 && d.dim() == 2, "gemm_fp8: 2-D CUDA tensors required");
+  TORCH_CHECK(a.scalar_type() == at::kFloat8_e4m3fn && b.scalar_type() == at::kFloat8_e4m3fn, "gemm_fp8: e4m3 operands required");
+  TORCH_CHECK(d.scalar_type() == at::kBFloat16 && a.stride(1) == 1 && b.stride(1) == 1 && d.stride(1) == 1, "gemm_fp8: bf16 row-major output");
+  TORCH_CHECK(a.size(1) == b.size(1) && d.size(0) == a.size(0) && d.size(1) == b.size(0), "gemm_fp8: shape mismatch");
+  g.M = static_cast<int>(a.size(0)); g.K = static_cast<int>(a.size(1)); g.N = static_cast<int>(b.size(0));
+  g.A = a.data_ptr(); g.B = b.data_ptr(); g.D = d.data_ptr();
+  g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
+}
+
+// d[M,N] bf16 = (a[M,K] · b[N,K]^T) * scale_a[m] * scale_b[n] * scalar
+void gemm_fp8(const Tensor& a, const Tensor& b, const c10::optional<Tensor>& scale_a, const c10::optional<Tensor>& scale_b, double scalar,
+              Tensor d) {
+  c10::cuda::CUDAGuard guard(a.device());
+  d9d::Fp8GemmArgs g;
+  fill_fp8_operands(g, a, b, d);
+  if (scale_a.has_value()) {
+    CHECK_CUDA_CONTIG(*scale_a);
+    TORCH_CHECK(scale_a->scalar_type() == at::kFloat && scale_a->numel() == g.M, "gemm_fp8: scale_a must be fp32 [M]");
+    g.scale_a = scale_a->data_ptr<float>();
+  }
+  if (scale_b.has_value()) {
+    CHECK_CUDA_CONTIG(*scale_b);
+    TORCH_CHECK(scale_b->scalar_type() == at::kFloat && scale_b->numel() == g.N, "gemm_fp8: scale_b must be fp32 [N]");
+    g.scale_b = scale_b->data_ptr<float>();
+  }
+  g.scale_scalar = static_cast<float>(scalar);
+  d9d::gemm_fp8(g, cur_stream());
+}
+
+// d[M,N] bf16 = sum_k (a * 2^sfa) (b * 2^sfb): block-scaled (MXFP8) operands from quantize_mx
+void gemm_mxfp8(const Tensor& a, const Tensor& sfa, const Tensor& b, const Tensor& sfb, Tensor d) {
+  c10::cuda::CUDAGuard guard(a.device());
+  d9d::Fp8GemmArgs g;
+  fill_fp8_operands(g, a, b, d);
+  CHECK_CUDA_CONTIG(sfa); CHECK_CUDA_CONTIG(sfb);
+  TORCH_CHECK(g.K % 128 == 0, "gemm_mxfp8: K must be a multiple of 128");
+  const int64_t kb = g.K / 128;
+  TORCH_CHECK(sfa.scalar_type() == at::kByte && sfa.numel() >= (static_cast<int64_t>(g.M) + 127) / 128 * kb * 512, "gemm_mxfp8: sfa too small");
+  TORCH_CHECK(sfb.scalar_type() == at::kByte && sfb.numel() >= (static_cast<int64_t>(g.N) + 255) / 256 * 2 * kb * 512, "gemm_mxfp8: sfb too small");
+  g.block_scaled = true;
+  g.sfa = sfa.data_ptr<uint8_t>(); g.sfb = sfb.data_ptr<uint8_t>();
+  d9d::gemm_fp8(g, cur_stream());
+}
+
 // ------------------------------------------------------------------ RMSNorm ---------------------
 std::tuple<Tensor, Tensor> rms_norm_fwd(const Tensor& x, const Tensor& w, double eps, bool zero_centered) {
   CHECK_CUDA_CONTIG(x); CHECK_CUDA_CONTIG(w);
@@ -703,6 +790,11 @@ TORCH_LIBRARY(d9d_b200, m) {
   m.def("ce_forward(Tensor h, Tensor w, Tensor target, int ignore_index) -> (Tensor, Tensor)");
   m.def("ce_forward_ex(Tensor h, Tensor w, Tensor target, int ignore_index, Tensor? bias=None, float softcap=0.0, int col_offset=0) -> (Tensor, Tensor, Tensor)");
   m.def("ce_dlogits(Tensor h, Tensor w, Tensor target, Tensor lse, Tensor grad, Tensor(a!) out, int ignore_index, Tensor? bias=None, float softcap=0.0, int col_offset=0) -> ()");
+  m.def("quantize_rowwise(Tensor x) -> (Tensor, Tensor)");
+  m.def("quantize_colwise_t(Tensor x) -> (Tensor, Tensor)");
+  m.def("quantize_mx(Tensor x) -> (Tensor, Tensor)");
+  m.def("gemm_fp8(Tensor a, Tensor b, Tensor? scale_a, Tensor? scale_b, float scalar, Tensor(a!) d) -> ()");
+  m.def("gemm_mxfp8(Tensor a, Tensor sfa, Tensor b, Tensor sfb, Tensor(a!) d) -> ()");
   m.def("rms_norm_fwd(Tensor x, Tensor w, float eps, bool zero_centered) -> (Tensor, Tensor)");
   m.def("rms_norm_bwd(Tensor dout, Tensor x, Tensor w, Tensor inv_rms, bool zero_centered) -> (Tensor, Tensor)");
   m.def("silu_mul_fwd(Tensor x, Tensor y) -> Tensor");
@@ -750,6 +842,11 @@ TORCH_LIBRARY_IMPL(d9d_b200, CUDA, m) {
   m.impl("ce_forward", &ce_forward);
   m.impl("ce_forward_ex", &ce_forward_ex);
   m.impl("ce_dlogits", &ce_dlogits);
+  m.impl("quantize_rowwise", &quantize_rowwise);
+  m.impl("quantize_colwise_t", &quantize_colwise_t);
+  m.impl("quantize_mx", &quantize_mx);
+  m.impl("gemm_fp8", &gemm_fp8);
+  m.impl("gemm_mxfp8", &gemm_mxfp8);
   m.impl("rms_norm_fwd", &rms_norm_fwd);
   m.impl("rms_norm_bwd", &rms_norm_bwd);
   m.impl("silu_mul_fwd", &silu_mul_fwd);

@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #ifndef D9D_WATCHDOG
 #define D9D_WATCHDOG 1  // bounded mbarrier spins: a protocol bug traps instead of hanging the GPU
@@ -330,6 +331,74 @@ __device__ __forceinline__ uint16_t sr_bf16_bits(float x, uint32_t rnd16) {
   if ((b & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(b >> 16);
   b += (rnd16 & 0xFFFFu);
   return static_cast<uint16_t>(b >> 16);
+}
+
+}  // namespace d9d
+
+// ----------------------------------------------------------------------------------------------
+// fp8 (kind::f8f6f4) and block-scaled fp8 (kind::mxf8f6f4) MMA, scale-factor staging
+// ----------------------------------------------------------------------------------------------
+namespace d9d {
+
+// D[tmem] (+)= A[smem] * B[smem], e4m3 / e5m2 inputs (32 K-elements per instruction), fp32 accumulate.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Block-scaled variant: every 32 K-elements of a row of A / B carry one UE8M0 scale factor living in tensor memory.
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+
+// smem -> tmem copy of one scale-factor block: 32 rows x 16 bytes, replicated into the four 32-lane quadrants.
+__device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t tmem_dst, uint64_t smem_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;\n" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+}
+
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Shared-memory matrix descriptor without swizzling (K-major "interleave" layout): 8-row x 16-byte core matrices,
+// `sbo_bytes` between consecutive 8-row groups, `lbo_bytes` between core matrices along K.
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+// Instruction descriptor for kind::f8f6f4, e4m3 A/B (format code 0), fp32 accumulate, K-major operands.
+//   [4,6) c_format (1=f32) [7,10) a_format [10,13) b_format [17,23) N>>3 [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// Instruction descriptor for kind::mxf8f6f4.block_scale, e4m3 A/B, UE8M0 scales, K-major operands.
+//   [4,6) b_sf_id [7,10) a_format [10,13) b_format [17,23) N>>3 [23] scale format (1 = UE8M0) [24,29) M>>4 [29,31) a_sf_id
+__host__ __device__ constexpr uint32_t make_idesc_mxe4m3(uint32_t m, uint32_t n, uint32_t a_sf_id, uint32_t b_sf_id) {
+  return (b_sf_id << 4) | ((n >> 3) << 17) | (1u << 23) | ((m >> 4) << 24) | (a_sf_id << 29);
 }
 
 }  // namespace d9d

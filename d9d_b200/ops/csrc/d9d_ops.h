@@ -58,6 +58,28 @@ int gemm_ce_block_n();
 void ce_finalize(const float* part_max, const float* part_sum, const float* tgt_logit, const long long* target,
                  long long ignore_index, int n_tiles, int M, float* lse, float* nll, cudaStream_t stream);
 
+// ------------------------------------------------------------------ fp8 GEMM (tcgen05 kind::f8f6f4 / mxf8f6f4) --
+struct Fp8GemmArgs {
+  const void* A = nullptr;   // [M, K] e4m3, K contiguous (row pitch lda bytes)
+  const void* B = nullptr;   // [N, K] e4m3
+  void* D = nullptr;         // [M, N] bf16
+  long long lda = 0, ldb = 0, ldd = 0;
+  int M = 0, N = 0, K = 0;
+  bool block_scaled = false;          // true: MXFP8 (UE8M0 scale per 32 K-elements), false: row / column scales in the epilogue
+  const float* scale_a = nullptr;     // [M] or nullptr
+  const float* scale_b = nullptr;     // [N] or nullptr
+  float scale_scalar = 1.f;
+  const uint8_t* sfa = nullptr;       // [ceil(M/128), K/128, 512]
+  const uint8_t* sfb = nullptr;       // [2*ceil(N/256), K/128, 512]
+};
+void gemm_fp8(const Fp8GemmArgs& a, cudaStream_t stream);
+void quantize_rowwise_e4m3(const void* x, void* q, float* scale, long long M, int K, long long ldx, cudaStream_t stream);
+// qt[C, R] (row pitch ldq bytes) = e4m3(x[R, C]^T / scale[c]); amax_scratch: [C] fp32
+void quantize_colwise_t_e4m3(const void* x, void* qt, float* scale, float* amax_scratch, long long R, int C, long long ldx,
+                             long long ldq, cudaStream_t stream);
+// sf must be zero-initialised by the caller when M is not a multiple of 256 (pad blocks)
+void quantize_mx_e4m3(const void* x, void* q, void* sf, long long M, int K, long long ldx, cudaStream_t stream);
+
 // ------------------------------------------------------------------ normalisation ----------------
 // dtype codes: 0 = bf16, 1 = fp32, 2 = fp16
 void rms_norm_fwd(const void* x, const void* w, void* out, float* inv_rms, long long M, int N, float eps,
