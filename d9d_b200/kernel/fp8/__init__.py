@@ -46,12 +46,9 @@ def quantize_colwise_t_reference(x: torch.Tensor) -> tuple[torch.Tensor, torch.T
 
 def mx_scale_exponent(amax: torch.Tensor) -> torch.Tensor:
     """Smallest integer ``e`` with ``amax / 2**e <= 448`` (``-127`` for all-zero groups), clamped to [-126, 126]."""
-    v = amax.float() / E4M3_MAX
-    e = torch.ceil(torch.log2(v.clamp_min(1e-38)))
-    # guard against log2 rounding right at powers of two
-    e = torch.where(torch.exp2(e - 1) >= v, e - 1, e)
-    e = torch.where(torch.exp2(e) < v, e + 1, e)
-    e = e.clamp(-126, 126)
+    # 448 = 1.75 * 2**8: with amax = m * 2**x (1 <= m < 2) the answer is x - 8 (+1 if m > 1.75) - exact, no logarithms
+    frac, exp = torch.frexp(amax.float().clamp_min(torch.finfo(torch.float32).tiny))  # amax = frac * 2**exp, frac in [0.5, 1)
+    e = (exp - 1 - 8 + (frac * 2 > 1.75).to(exp.dtype)).clamp(-126, 126).float()
     return torch.where(amax > 0, e, torch.full_like(e, -127)).to(torch.int32)
 
 

@@ -33,7 +33,7 @@ int epi_for(const Tensor& d, bool accumulate) {
 }
 
 // d[M,N] (+)= op(a) · op(b)^T.  a: [M,K] or (a_mn) [K,M];  b: [N,K] or (b_mn) [K,N].  Row strides may be padded.
-void gemm(const Tensor& a, const Tensor& b, Tensor d, bool a_mn, bool b_mn, bool accumulate) {
+void gemm(const Tensor& a, const Tensor& b, Tensor d, bool a_mn, bool b_mn, bool accumulate, int64_t ctas) {
   TORCH_CHECK(a.is_cuda() && b.is_cuda() && d.is_cuda(), "gemm: CUDA tensors required");
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm: bf16 operands required");
   TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && d.dim() == 2, "gemm: 2-D tensors required");
@@ -50,8 +50,11 @@ void gemm(const Tensor& a, const Tensor& b, Tensor d, bool a_mn, bool b_mn, bool
   g.A = a.data_ptr(); g.B = b.data_ptr(); g.D = d.data_ptr();
   g.lda = a.stride(0); g.ldb = b.stride(0); g.ldd = d.stride(0);
   g.epi = epi_for(d, accumulate);
+  g.ctas = static_cast<int>(ctas);
   d9d::gemm_dense(g, cur_stream());
 }
+
+int64_t gemm_set_pair_mode(int64_t mode) { return d9d::gemm_set_pair_mode(static_cast<int>(mode)); }
 
 // d[R,N] = a[R,K] · W[e(r)];  b: [E,N,K] (b_mn=false) or [E,K,N] (b_mn=true)
 void gemm_grouped_m(const Tensor& a, const Tensor& b, Tensor d, const Tensor& tile_group, bool b_mn, bool accumulate) {
@@ -784,7 +787,8 @@ void nvl_adamw_shard_(Tensor own_param, const Tensor& own_grad, Tensor exp_avg, 
 }
 
 TORCH_LIBRARY(d9d_b200, m) {
-  m.def("gemm(Tensor a, Tensor b, Tensor(a!) d, bool a_mn, bool b_mn, bool accumulate) -> ()");
+  m.def("gemm(Tensor a, Tensor b, Tensor(a!) d, bool a_mn, bool b_mn, bool accumulate, int ctas=0) -> ()");
+  m.def("gemm_set_pair_mode(int mode) -> int", &gemm_set_pair_mode);
   m.def("gemm_grouped_m(Tensor a, Tensor b, Tensor(a!) d, Tensor tile_group, bool b_mn, bool accumulate=False) -> ()");
   m.def("gemm_grouped_k(Tensor a, Tensor b, Tensor(a!) d, Tensor group_offsets, bool accumulate) -> ()");
   m.def("ce_forward(Tensor h, Tensor w, Tensor target, int ignore_index) -> (Tensor, Tensor)");

@@ -25,6 +25,7 @@ struct GemmArgs {
   const int* tile_group = nullptr;     // GROUPED_M
   const int* group_offsets = nullptr;  // GROUPED_K
   int block_n = 0;                     // 0 => heuristic
+  int ctas = 0;                        // 1: one CTA per tile, 2: CTA pairs (cta_group::2, 256-row tiles), 0: process-wide policy
   int k_splits = 0;                    // dense fp32-accumulate epilogue only: 0 => heuristic, 1 => off
   // fused tensor-parallel communication (gemm::Comm); the sharded operand / output is described by its peers
   int comm = 0;
@@ -50,6 +51,12 @@ struct GemmArgs {
 };
 
 void gemm_dense(const GemmArgs& a, cudaStream_t stream);
+void gemm_dense_pair(const GemmArgs& a, cudaStream_t stream);  // CTA-pair kernels (gemm_dense_pair.cu)
+// process-wide policy for GemmArgs::ctas == 0: 0 = single-CTA kernels, 1 = CTA pairs for eligible dense / fused-CE shapes.
+// Initialised from D9D_GEMM_PAIR; returns the previous value.
+int gemm_set_pair_mode(int mode);
+int gemm_pair_mode();
+bool gemm_pair_eligible(const GemmArgs& a);
 void gemm_grouped(const GemmArgs& a, cudaStream_t stream);
 void gemm_ce(const GemmArgs& a, cudaStream_t stream);
 void gemm_comm(const GemmArgs& a, cudaStream_t stream);  // dense GEMM with a.comm != 0 (gemm_comm_*.cu)

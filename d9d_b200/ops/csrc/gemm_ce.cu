@@ -13,9 +13,16 @@ int gemm_ce_block_n() { return CE_BN; }
 void gemm_ce(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return;
   if (a.a_mn || a.b_mn) throw std::runtime_error("d9d gemm_ce: K-major operands required");
-  if (a.epi == EPI_CE_LSE) launch_one<DENSE, CE_BN, false, false, EPI_CE_LSE>(a, stream);
-  else if (a.epi == EPI_CE_DLOGITS) launch_one<DENSE, CE_BN, false, false, EPI_CE_DLOGITS>(a, stream);
-  else throw std::runtime_error("d9d gemm_ce: bad epilogue");
+  const bool pair = a.ctas == 2 || (a.ctas == 0 && gemm_pair_mode() == 1 && gemm_pair_eligible(a));
+  if (a.epi == EPI_CE_LSE) {
+    if (pair) launch_one<DENSE, CE_BN, false, false, EPI_CE_LSE, COMM_NONE, 2>(a, stream);
+    else launch_one<DENSE, CE_BN, false, false, EPI_CE_LSE>(a, stream);
+  } else if (a.epi == EPI_CE_DLOGITS) {
+    if (pair) launch_one<DENSE, CE_BN, false, false, EPI_CE_DLOGITS, COMM_NONE, 2>(a, stream);
+    else launch_one<DENSE, CE_BN, false, false, EPI_CE_DLOGITS>(a, stream);
+  } else {
+    throw std::runtime_error("d9d gemm_ce: bad epilogue");
+  }
 }
 
 __global__ void ce_finalize_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,

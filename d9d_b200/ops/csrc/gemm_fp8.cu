@@ -115,11 +115,12 @@ __global__ void quant_mx_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[j][i]));
   }
-  // smallest power of two 2^e with amax / 2^e <= 448
+  // smallest power of two 2^e with amax / 2^e <= 448 = 1.75 * 2^8: with amax = m * 2^x (1 <= m < 2) that is
+  // e = x - 8 (+1 if m > 1.75) - exact integer arithmetic on the float's bit pattern
   int e = -127;
   if (amax > 0.f) {
-    const uint32_t bits = __float_as_uint(amax * (1.f / E4M3_MAX));
-    e = static_cast<int>((bits >> 23) & 0xFF) - 127 + ((bits & 0x7FFFFF) ? 1 : 0);
+    const uint32_t bits = __float_as_uint(amax);
+    e = static_cast<int>((bits >> 23) & 0xFF) - 127 - 8 + ((bits & 0x7FFFFF) > 0x600000 ? 1 : 0);
     e = max(-126, min(126, e));
   }
   const float inv = (e == -127) ? 0.f : __uint_as_float(static_cast<uint32_t>(127 - e) << 23);

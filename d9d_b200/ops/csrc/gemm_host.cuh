@@ -73,13 +73,34 @@ inline int sm_count() {
   return n;
 }
 
-template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI, int COMM = COMM_NONE>
+// number of CTA pairs that can be resident at once (one pair per TPC)
+template <typename Kern>
+int max_active_pairs(Kern kern, int smem_bytes) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / 2 * 2));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  return n;
+}
+
+template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI, int COMM = COMM_NONE, int CTAS = 1>
 void launch_one(const GemmArgs& a, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
-  auto kern = gemm_kernel<MODE, BLOCK_N, A_MN, B_MN, EPI, COMM>;
+  using C = Cfg<BLOCK_N, CTAS>;
+  auto kern = gemm_kernel<MODE, BLOCK_N, A_MN, B_MN, EPI, COMM, CTAS>;
   static bool configured = false;
+  static int pairs = 0;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (CTAS == 2) pairs = max_active_pairs(kern, C::SMEM_BYTES);
     configured = true;
   }
   // ---- tensor maps ----
@@ -113,7 +134,7 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   } else {
     const uint64_t g = (MODE == GROUPED_M) ? a.num_groups : 1;
     if (!B_FROM_PEERS) {
-      if (!B_MN) tb = make_tmap_bf16_3d(a.B, a.K, a.N, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.N, 64, BLOCK_N);
+      if (!B_MN) tb = make_tmap_bf16_3d(a.B, a.K, a.N, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.N, 64, C::B_ROWS);
       else       tb = make_tmap_bf16_3d(a.B, a.N, a.K, g, a.ldb, a.b_group_stride ? a.b_group_stride : a.ldb * a.K, 64, BLOCK_K);
     }
     if (!A_FROM_PEERS) {
@@ -136,9 +157,9 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   p.k_splits = 1;
   if (MODE == DENSE && EPI == EPI_F32_ACC && p.tma_epilogue) {
     // split-K: reduce-adds from several CTAs land on the same tile (fp32 adds in L2; order is not deterministic)
-    const long long mn_tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N);
+    const long long mn_tiles = ((a.M + C::TILE_M - 1) / C::TILE_M) * ((a.N + BLOCK_N - 1) / BLOCK_N);
     const long long k_blocks = (a.K + BLOCK_K - 1) / BLOCK_K;
-    long long splits = a.k_splits > 0 ? a.k_splits : sm_count() / mn_tiles;
+    long long splits = a.k_splits > 0 ? a.k_splits : (sm_count() / CTAS) / mn_tiles;
     const long long max_splits = k_blocks / 8;  // keep >= 8 k-blocks (512 deep) per slice
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -155,9 +176,24 @@ void launch_one(const GemmArgs& a, cudaStream_t stream) {
   p.ce_ignore_index = a.ce_ignore_index; p.ce_softcap = a.ce_softcap; p.ce_bias = a.ce_bias;
   p.ce_col_offset = a.ce_col_offset;
 
-  const long long m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
+  const long long m_tiles = (a.M + C::TILE_M - 1) / C::TILE_M, n_tiles = (a.N + BLOCK_N - 1) / BLOCK_N;
   long long tiles = m_tiles * n_tiles * (MODE == GROUPED_K ? a.num_groups : 1) * p.k_splits;
   if (tiles <= 0) return;
+  if constexpr (CTAS == 2) {
+    // one CTA pair (cluster of 2 on one TPC) per tile
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * (tiles < pairs ? tiles : pairs)));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p, peers);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("d9d gemm: CTA-pair launch failed: ") + cudaGetErrorString(e));
+    return;
+  }
   // COMM_WAIT_A runs next to copy / flag kernels of another stream: leave `comm_spare_sms` SMs to them
   const int usable = sm_count() - ((COMM == COMM_WAIT_A) ? a.comm_spare_sms : 0);
   const int grid = static_cast<int>(tiles < usable ? tiles : usable);
@@ -194,6 +230,24 @@ inline int pick_block_n(long long m_tiles_x_groups, int N) {
       case EPI_BF16_ACC: D9D_DISPATCH_BN(MODE, AMN, BMN, EPI_BF16_ACC, bn, args, stream); break;  \
       default: throw std::runtime_error("d9d gemm: unsupported epilogue for this mode");          \
     }                                                                                             \
+  } while (0)
+
+// CTA-pair (cta_group::2) variants: 256 x {256, 128} tiles
+#define D9D_DISPATCH_PAIR_BN(AMN, BMN, EPI, bn, args, stream)                                        \
+  do {                                                                                               \
+    if ((bn) >= 256) launch_one<DENSE, 256, AMN, BMN, EPI, COMM_NONE, 2>(args, stream);              \
+    else launch_one<DENSE, 128, AMN, BMN, EPI, COMM_NONE, 2>(args, stream);                          \
+  } while (0)
+
+#define D9D_DISPATCH_PAIR_EPI4(AMN, BMN, epi, bn, args, stream)                                      \
+  do {                                                                                               \
+    switch (epi) {                                                                                   \
+      case EPI_BF16: D9D_DISPATCH_PAIR_BN(AMN, BMN, EPI_BF16, bn, args, stream); break;              \
+      case EPI_F32: D9D_DISPATCH_PAIR_BN(AMN, BMN, EPI_F32, bn, args, stream); break;                \
+      case EPI_F32_ACC: D9D_DISPATCH_PAIR_BN(AMN, BMN, EPI_F32_ACC, bn, args, stream); break;        \
+      case EPI_BF16_ACC: D9D_DISPATCH_PAIR_BN(AMN, BMN, EPI_BF16_ACC, bn, args, stream); break;      \
+      default: throw std::runtime_error("d9d gemm: unsupported epilogue for this mode");             \
+    }                                                                                                \
   } while (0)
 
 // store-only epilogues (layouts that never receive an accumulate request keep the instantiation count down)

@@ -102,14 +102,20 @@ __device__ __forceinline__ float ce_transform(float acc, float bias, float cap, 
   return z;
 }
 
-template <int BLOCK_N>
+// CTAS = 2: a CTA pair works on a 256 x BLOCK_N tile (cta_group::2): every CTA stages its own 128 rows of A and its own
+// BLOCK_N / 2 rows of B, i.e. a third less operand traffic per flop at BLOCK_N = 256 and two more stages in flight.
+template <int BLOCK_N, int CTAS = 1>
 struct Cfg {
+  static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair");
+  static_assert(CTAS == 1 || BLOCK_N % 128 == 0, "a CTA pair splits B into halves of whole 64-column swizzle atoms");
+  static constexpr int TILE_M = BLOCK_M * CTAS;
+  static constexpr int B_ROWS = BLOCK_N / CTAS;  // rows of B staged by one CTA
   static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // Operand bytes in flight decide the throughput of the mid-size GEMMs (per-SM bandwidth = bytes in flight / load latency),
   // so the 192-wide tile trades the second epilogue staging buffer for a fifth operand stage (200 KiB in flight).
-  static constexpr int EPI_BUFS = (BLOCK_N == 192) ? 1 : 2;
+  static constexpr int EPI_BUFS = (BLOCK_N == 192 && CTAS == 1) ? 1 : 2;
   static constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_BUFS * 4096;  // per epilogue warp: EPI_BUFS x (32 rows x 128 B)
   static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256 - EPI_STAGING_BYTES;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
@@ -129,20 +135,20 @@ struct TileCoord {
   bool valid;
 };
 
-template <int MODE, int BLOCK_N>
+template <int MODE, int BLOCK_N, int TILE_M = BLOCK_M>
 __device__ __forceinline__ int num_tiles(const Params& p) {
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   if (MODE == GROUPED_K) return p.num_groups * m_tiles * n_tiles;
   if (MODE == DENSE) return m_tiles * n_tiles * p.k_splits;
   return m_tiles * n_tiles;
 }
 
-template <int MODE, int BLOCK_N>
+template <int MODE, int BLOCK_N, int TILE_M = BLOCK_M>
 __device__ __forceinline__ TileCoord get_tile(const Params& p, int tile) {
   TileCoord t;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles = (p.M + TILE_M - 1) / TILE_M;
   t.valid = true;
   if (MODE == GROUPED_K) {
     const int per_group = m_tiles * n_tiles;
@@ -193,7 +199,7 @@ __device__ __forceinline__ void comm_locate(const Params& p, int idx, int& owner
   local = (blk / p.comm_world) * p.comm_block_rows + (idx - blk * p.comm_block_rows);
 }
 
-template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI, int COMM = COMM_NONE>
+template <int MODE, int BLOCK_N, bool A_MN, bool B_MN, int EPI, int COMM = COMM_NONE, int CTAS = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_d, const Params p,
@@ -203,8 +209,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   static_assert(COMM != COMM_AG_KA || A_MN, "COMM_AG_KA gathers an MN-major A along K");
   static_assert(COMM != COMM_AG_KB || B_MN, "COMM_AG_KB gathers an MN-major B along K");
   static_assert(COMM != COMM_RS_D || EPI == EPI_F32_ACC || EPI == EPI_BF16_ACC, "COMM_RS_D needs a reduce-add epilogue");
-  using C = Cfg<BLOCK_N>;
+  static_assert(CTAS == 1 || (MODE == DENSE && COMM == COMM_NONE), "CTA pairs are implemented for plain dense GEMMs");
+  using C = Cfg<BLOCK_N, CTAS>;
   constexpr int STAGES = C::STAGES;
+  constexpr int TILE_M = C::TILE_M;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -218,7 +226,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
-  const int total_tiles = num_tiles<MODE, BLOCK_N>(p);
+  const int total_tiles = num_tiles<MODE, BLOCK_N, TILE_M>(p);
+  // persistent loop: one tile per CTA (pair) at a time
+  const int pair_rank = (CTAS == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_tile = static_cast<int>(blockIdx.x) / CTAS;
+  const int tile_stride = static_cast<int>(gridDim.x) / CTAS;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
@@ -232,14 +244,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS * CTAS);  // pair: the epilogue warps of both CTAs release the leader's accumulator
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  if constexpr (CTAS == 2) {
+    if (warp == 1) tmem_alloc_pair<C::TMEM_COLS>(tmem_ptr_smem);  // executed by the same warp of both CTAs
+    tc_fence_before();
+    cluster_sync_all();  // the peer's barriers are initialised before anything is signalled across the pair
+    tc_fence_after();
+  } else {
+    if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
@@ -249,12 +268,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t phase = 0;
       // grouped modes read the tile's expert / row range from global memory: fetch it one whole tile ahead so that the
       // load latency never sits between two tiles on the critical path
-      TileCoord t_next = get_tile<MODE, BLOCK_N>(p, blockIdx.x);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord t_next = get_tile<MODE, BLOCK_N, TILE_M>(p, first_tile);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const TileCoord t = t_next;
-        if (tile + static_cast<int>(gridDim.x) < total_tiles) t_next = get_tile<MODE, BLOCK_N>(p, tile + gridDim.x);
+        if (tile + tile_stride < total_tiles) t_next = get_tile<MODE, BLOCK_N, TILE_M>(p, tile + tile_stride);
         if (!t.valid) continue;
-        const int m_idx = t.m_blk * BLOCK_M, n_idx = t.n_blk * BLOCK_N;
+        // pair: this CTA's 128 rows of the 256-row tile and its half of the B tile
+        const int m_idx = t.m_blk * TILE_M + pair_rank * BLOCK_M, n_idx = t.n_blk * BLOCK_N + pair_rank * C::B_ROWS;
         if constexpr (COMM == COMM_WAIT_A) {  // the shard holding this m-tile may still be in flight
           int owner, unused;
           comm_locate(p, m_idx, owner, unused);
@@ -277,7 +297,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         for (int kb = 0; kb < t.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if constexpr (CTAS == 2) {
+            // both CTAs' loads complete on the leader's barrier (the MMA issuer waits there)
+            if (pair_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CTAS * C::STAGE_BYTES);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          }
           const int k_idx = t.k_begin + kb * BLOCK_K;
           uint8_t* sa = smem_a + stage * C::A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * C::B_STAGE_BYTES;
@@ -292,11 +317,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int j = 0; j < BLOCK_M / 64; ++j)
               tma_load_3d(sa + j * (BLOCK_K * 128), &peers.m[owner], &full_bar[stage], m_idx + j * 64, k_local, 0);
           } else if (!A_MN) {
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], k_idx, m_idx, 0);
+            if constexpr (CTAS == 2) tma_load_3d_pair(sa, &tmap_a, &full_bar[stage], k_idx, m_idx, 0);
+            else tma_load_3d(sa, &tmap_a, &full_bar[stage], k_idx, m_idx, 0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_3d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_idx + j * 64, k_idx, 0);
+            for (int j = 0; j < BLOCK_M / 64; ++j) {
+              if constexpr (CTAS == 2) tma_load_3d_pair(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_idx + j * 64, k_idx, 0);
+              else tma_load_3d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m_idx + j * 64, k_idx, 0);
+            }
           }
           const int bg = (MODE == GROUPED_M) ? t.group : 0;
           if constexpr (COMM == COMM_AG_KB) {
@@ -306,27 +334,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_3d(sb + j * (BLOCK_K * 128), &peers.m[owner], &full_bar[stage], n_idx + j * 64, k_local, 0);
           } else if (!B_MN) {
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], k_idx, n_idx, bg);
+            if constexpr (CTAS == 2) tma_load_3d_pair(sb, &tmap_b, &full_bar[stage], k_idx, n_idx, bg);
+            else tma_load_3d(sb, &tmap_b, &full_bar[stage], k_idx, n_idx, bg);
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_3d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_idx + j * 64, k_idx, bg);
+            for (int j = 0; j < C::B_ROWS / 64; ++j) {
+              if constexpr (CTAS == 2) tma_load_3d_pair(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_idx + j * 64, k_idx, bg);
+              else tma_load_3d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n_idx + j * 64, k_idx, bg);
+            }
           }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if constexpr (CTAS == 2) {
+        // tail: every stage this CTA filled has been released again, i.e. all multicast arrivals of the leader's commits
+        // have landed here before this CTA can leave the kernel
+        for (int i = 0; i < STAGES; ++i) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // ================= MMA issuer (pair: the leader CTA issues for both) =================
+    constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    TileCoord t_next = get_tile<MODE, BLOCK_N>(p, blockIdx.x);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    TileCoord t_next = get_tile<MODE, BLOCK_N, TILE_M>(p, first_tile);
+    for (int tile = first_tile; tile < total_tiles && pair_rank == 0; tile += tile_stride) {
       const TileCoord t = t_next;
-      if (tile + static_cast<int>(gridDim.x) < total_tiles) t_next = get_tile<MODE, BLOCK_N>(p, tile + gridDim.x);
+      if (tile + tile_stride < total_tiles) t_next = get_tile<MODE, BLOCK_N, TILE_M>(p, tile + tile_stride);
       if (!t.valid) continue;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -343,14 +382,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                      : make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
                                      : make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_f16_pair(tmem_d, da, db, idesc, (kb | k) != 0);
+            else umma_f16(tmem_d, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&tmem_full[acc]);
+      if (elect_one()) {
+        if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[acc]);  // both CTAs' epilogues read their half of the accumulator
+        else umma_commit(&tmem_full[acc]);
+      }
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -361,14 +405,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t epi_chunk = 0;  // running count of staged chunks (selects the staging buffer)
-    TileCoord t_next = get_tile<MODE, BLOCK_N>(p, blockIdx.x);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    TileCoord t_next = get_tile<MODE, BLOCK_N, TILE_M>(p, first_tile);
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
       const TileCoord t = t_next;
-      if (tile + static_cast<int>(gridDim.x) < total_tiles) t_next = get_tile<MODE, BLOCK_N>(p, tile + gridDim.x);
+      if (tile + tile_stride < total_tiles) t_next = get_tile<MODE, BLOCK_N, TILE_M>(p, tile + tile_stride);
       if (!t.valid) continue;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = t.m_blk * BLOCK_M + quad * 32 + lane;
+      const int row0 = t.m_blk * TILE_M + pair_rank * BLOCK_M;  // first row of this CTA's 128-row slab
+      const int row = row0 + quad * 32 + lane;
       const int col0 = t.n_blk * BLOCK_N;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quad * 32) << 16);
@@ -504,7 +549,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              const int r0 = t.m_blk * BLOCK_M + quad * 32;
+              const int r0 = row0 + quad * 32;
               const int g0 = (MODE == GROUPED_K) ? t.group : 0;
               if constexpr (COMM == COMM_RS_D) {  // reduce-add into the shard of the peer that owns these rows
                 int owner, r_local;
@@ -622,16 +667,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_leader(&tmem_empty[acc]);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp are complete before smem is released
   }
 
   tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if constexpr (CTAS == 2) {
+    cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair may still touch its smem / barriers
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+  } else {
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
 }
 
 }  // namespace gemm
