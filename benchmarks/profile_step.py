@@ -27,6 +27,9 @@ def main() -> None:
     ap.add_argument("--trace", default=None, help="optional chrome trace path")
     args = ap.parse_args()
     args.warmup, args.steps = 2, 1
+    for name, value in (('model', 'example'), ('layout', 'dp'), ('impl', 'own'), ('checkpointing', False), ('dp_impl', 'nvlink'), ('gpus', 1)):
+        if not hasattr(args, name):
+            setattr(args, name, value)
 
     import torch
     from torch.profiler import ProfilerActivity, profile

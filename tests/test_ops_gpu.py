@@ -202,6 +202,7 @@ def test_linear_cross_entropy_split_blocks_autograd(monkeypatch, sizes, budget, 
     tgt[3] = sum(sizes) - 1
     if fused_wgrad:
         for w in ws:
+            w.grad_dtype = torch.float32
             w.grad = torch.full(w.shape, 0.5, device="cuda", dtype=torch.float32)
             setattr(w, _native.FUSED_WGRAD_ATTR, True)
     loss = cce.linear_cross_entropy(e, ws, tgt, reduction="sum")
