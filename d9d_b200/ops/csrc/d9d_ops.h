@@ -53,7 +53,7 @@ struct GemmArgs {
 void gemm_dense(const GemmArgs& a, cudaStream_t stream);
 void gemm_dense_pair(const GemmArgs& a, cudaStream_t stream);  // CTA-pair kernels (gemm_dense_pair.cu)
 // process-wide policy for GemmArgs::ctas == 0: 0 = single-CTA kernels, 1 = CTA pairs for eligible dense / fused-CE shapes.
-// Initialised from D9D_GEMM_PAIR; returns the previous value.
+// Default 1 (D9D_GEMM_PAIR=0 switches it off); returns the previous value.
 int gemm_set_pair_mode(int mode);
 int gemm_pair_mode();
 bool gemm_pair_eligible(const GemmArgs& a);

@@ -9,8 +9,10 @@ using namespace gemm;
 namespace {
 int& pair_mode_ref() {
   static int mode = [] {
+    // CTA pairs are the default for eligible shapes (measured: +7..30 % on large dense GEMMs, neutral on the MoE flagship);
+    // D9D_GEMM_PAIR=0 restores the single-CTA kernels everywhere
     const char* e = std::getenv("D9D_GEMM_PAIR");
-    return (e != nullptr && e[0] == '1') ? 1 : 0;
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
   }();
   return mode;
 }
