@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--accum", type=int, default=2, help="microbatches per GPU per optimizer step")
     ap.add_argument("--layers", type=int, default=FLAGSHIP["num_hidden_layers"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp8-dense", action="store_true",
+                    help="EXPERIMENT (not the headline: reduced precision): attention projections run forward / dgrad / wgrad in e4m3 "
+                         "(d9d_b200.kernel.fp8.Fp8Linear); experts, router and LM head stay bf16")
     ap.add_argument("--dp-impl", default="nvlink", choices=["nvlink", "nccl"],
                     help="multi-GPU gradient path of the device-timed arm: own NVLink peer-memory kernels or NCCL all-reduce")
     ap.add_argument("--layout", default="dp", choices=["dp", "ep", "example"],
@@ -239,6 +242,11 @@ def build_model(args, device):
     with torch.device(device):
         model = Qwen3MoEForCausalLM(params, PipelineStageInfo(0, 1), HiddenStatesAggregationMode.no, False).bfloat16()
     model.reset_parameters()
+    if getattr(args, "fp8_dense", False):
+        from d9d_b200.kernel.fp8 import convert_linears_to_fp8
+
+        n = convert_linears_to_fp8(model, lambda name, m: "self_attn" in name)
+        print(f"[bench] fp8: {n} attention projections converted to Fp8Linear", file=sys.stderr, flush=True)
     return model
 
 
@@ -341,7 +349,7 @@ def main():
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "bf16",
+            "dtype": "bf16" if not args.fp8_dense else "bf16 + e4m3 attention projections (EXPERIMENT, not the headline)",
             "data": "synthetic tokens, random-init weights",
             "impl": "own",
             "config": {

@@ -167,11 +167,14 @@ class Fp8Linear(nn.Linear):
 
 
 def convert_linears_to_fp8(module: nn.Module, predicate=lambda name, m: True) -> int:
-    """Re-classes every eligible ``nn.Linear`` (feature dims multiples of 16, ``predicate(name, module)`` true) of ``module``
-    to :class:`Fp8Linear` in place; parameters are shared, state-dict keys unchanged.  Returns the number converted."""
+    """Re-classes every eligible linear layer of ``module`` to :class:`Fp8Linear` in place: plain ``nn.Linear`` and the
+    framework's ``module.block.linear.Linear`` (not LoRA wrappers or other subclasses), feature dims multiples of 16,
+    ``predicate(name, module)`` true.  Parameters are shared, state-dict keys unchanged.  Returns the number converted."""
+    from d9d_b200.module.block.linear import Linear as NativeLinear
+
     n = 0
     for name, m in module.named_modules():
-        if type(m) is nn.Linear and m.in_features % 16 == 0 and m.out_features % 16 == 0 and predicate(name, m):
+        if type(m) in (nn.Linear, NativeLinear) and m.in_features % 16 == 0 and m.out_features % 16 == 0 and predicate(name, m):
             m.__class__ = Fp8Linear
             n += 1
     return n

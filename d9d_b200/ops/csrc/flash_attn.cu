@@ -493,7 +493,10 @@ flash_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_
   const int b = blockIdx.z;
   const SeqInfo sq = resolve_seq(p, b);
   const int g = p.Hq / p.Hk;
-  const int r0 = blockIdx.x * 128;  // first resident row (key for DKV, query for DQ), sequence-local
+  // first resident row (key for DKV, query for DQ), sequence-local.  Blocks are dispatched in blockIdx order: under a causal
+  // mask the heavy tiles are the early keys (DKV: natural order) and the LATE queries (DQ: reversed order), so that the light
+  // tiles fill the tail of the grid
+  const int r0 = (DKV ? static_cast<int>(blockIdx.x) : static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x)) * 128;
   if (r0 >= (DKV ? sq.Sk : sq.Sq)) return;
   const int head = blockIdx.y;      // DKV: kv head; DQ: query head
   const int hk = DKV ? head : head / g;

@@ -53,8 +53,9 @@ def _check(rank, world, mode, layout_name, causal, heads, kv_heads):
 
     local = [shard_sequence(t, 1, world, rank, layout).clone().requires_grad_() for t in (q, k, v)]
     positions = torch.stack([local_sequence_indices(seq, world, r, layout) for r in range(world)])
-    if mode == "ring":
-        out = ring_attention(*local, group, positions, causal=causal, mask_cache={})
+    if mode in ("ring", "ring_plan"):
+        # ring_plan: blocks as flash-attention calls on runs of consecutive positions (the CUDA path, here on the fp32 oracle)
+        out = ring_attention(*local, group, positions, causal=causal, mask_cache={}, block_impl="plan" if mode == "ring_plan" else "mask")
     else:
         out = ulysses_attention(*local, group, lambda a, b, c: attention_reference(a, b, c, None, causal)[0],
                                 positions=positions.reshape(-1))
@@ -70,6 +71,38 @@ def _check(rank, world, mode, layout_name, causal, heads, kv_heads):
 @pytest.mark.parametrize("world,heads,kv_heads", [(2, 4, 2), (4, 4, 1), (3, 3, 3)])
 def test_ring_attention_matches_full_attention(world, heads, kv_heads):
     run_distributed(_worker, world, "ring", heads, kv_heads)
+
+
+@pytest.mark.parametrize("world,heads,kv_heads", [(2, 4, 2), (4, 4, 1)])
+def test_ring_attention_plan_blocks_match_full_attention(world, heads, kv_heads):
+    run_distributed(_worker, world, "ring_plan", heads, kv_heads)
+
+
+def test_block_plan_of_the_two_layouts():
+    from d9d_b200.kernel.context_parallel import ContextParallelLayout, local_sequence_indices
+    from d9d_b200.kernel.context_parallel.ring import _CAUSAL, _FULL, _BlockPlan
+
+    world, seq = 4, 64
+    for name in ("zigzag", "contiguous"):
+        pos = torch.stack([local_sequence_indices(seq, world, r, ContextParallelLayout(name)) for r in range(world)])
+        for rank in range(world):
+            plan = _BlockPlan(pos, rank, True)
+            for src in range(world):
+                calls = plan.calls(src)
+                assert calls is not None  # both layouts decompose into full / aligned-causal calls
+                visible = sum(1 for _ in calls)
+                if name == "contiguous":
+                    assert calls == ([(None, None, _CAUSAL)] if src == rank else [(None, None, _FULL)] if src < rank else [])
+                elif src == rank:
+                    # two runs: (early, early) causal, (late, early) full, (late, late) causal; the last rank's two chunks are adjacent
+                    want = [_CAUSAL] if rank == world - 1 else [_FULL, _CAUSAL, _CAUSAL]
+                    assert sorted(m for _, _, m in calls) == want and visible == len(want)
+                else:
+                    # one unmasked call: all my queries x the early run of an earlier rank, or my late run x the whole later block
+                    assert len(calls) == 1 and calls[0][2] == _FULL and (calls[0][0] is None) != (calls[0][1] is None) or rank == world - 1 or src == world - 1
+    # an irregular layout (interleaved tokens) falls back to the mask path
+    weird = torch.stack([torch.arange(r, 16, 2) for r in range(2)])
+    assert _BlockPlan(weird, 0, True).calls(1) is None or all(m in (_FULL, _CAUSAL) for _, _, m in _BlockPlan(weird, 0, True).calls(1))
 
 
 @pytest.mark.parametrize("world,heads,kv_heads", [(2, 4, 2), (4, 8, 4)])
