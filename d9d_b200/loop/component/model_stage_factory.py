@@ -76,6 +76,7 @@ class ModelStageFactory:
         model = built.model
         if not isinstance(model, nn.Module) or not isinstance(model, ModuleLateInit):
             raise ValueError("Model stage is required to be nn.Module instance implementing ModuleLateInit protocol")
+        self._apply_fp8(model)
         if self._ctx.mesh_params.is_distributed:
             self._provider.parallelize_model_stage(ParallelizeModelStageContext(model=model, stage=stage, dist_context=self._ctx))
         model.to_empty(device=self._ctx.current_device)
@@ -86,6 +87,20 @@ class ModelStageFactory:
                              device=str(self._ctx.current_device), model=model, position=self._ctx.local_rank)
         model.train()
         return model
+
+    def _apply_fp8(self, model: nn.Module) -> None:
+        cfg = self._config_model.fp8_linear
+        if cfg is None:
+            return
+        if self._ctx.mesh_params.tensor_parallel > 1:
+            raise NotImplementedError("model_stage_factory.fp8_linear is not combined with tensor parallelism (the fused TP GEMMs are bf16)")
+        import re
+
+        from d9d_b200.kernel.fp8 import convert_linears_to_fp8
+
+        include, exclude = re.compile(cfg.include), re.compile(cfg.exclude) if cfg.exclude else None
+        n = convert_linears_to_fp8(model, lambda name, _m: bool(include.search(name)) and not (exclude and exclude.search(name)))
+        self._ctx.logger.info(f"fp8: {n} linear layers of this stage run in e4m3")
 
     def build_pipeline_and_modules(self) -> tuple[PipelineScheduleInfo, TrackedModules]:
         if self._config_model.checkpoint_only_trainable_parameters:

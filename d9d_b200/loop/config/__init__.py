@@ -10,6 +10,7 @@ from .config import (
     GradientManagerConfig,
     InferenceConfig,
     JobLoggerConfig,
+    Fp8LinearConfig,
     ModelStageFactoryConfig,
     PipeliningConfig,
     ProfilingConfig,
@@ -28,6 +29,7 @@ __all__ = [
     "GradientManagerConfig",
     "InferenceConfig",
     "JobLoggerConfig",
+    "Fp8LinearConfig",
     "ModelStageFactoryConfig",
     "PipeliningConfig",
     "ProfilingConfig",

@@ -40,9 +40,21 @@ class CheckpointingConfig(BaseModel):
     async_save: bool = False
 
 
+class Fp8LinearConfig(BaseModel):
+    """Run the selected dense linear layers in fp8 (e4m3, dynamic row / column scaling for forward, input-gradient and
+    weight-gradient GEMMs - ``d9d_b200.kernel.fp8.Fp8Linear``).  Net-new: the reference has no fp8 path.
+
+    ``include`` / ``exclude`` are regular expressions searched in the module names of a model stage; only plain linear
+    layers whose feature sizes are multiples of 16 are converted (LoRA wrappers, grouped expert weights, norms are not)."""
+
+    include: str = r".*"
+    exclude: str | None = r"lm_head|cls_head|embedding_head|router|\.gate$"
+
+
 class ModelStageFactoryConfig(BaseModel):
     source_checkpoint: Path | None
     checkpoint_only_trainable_parameters: bool
+    fp8_linear: Fp8LinearConfig | None = None
 
 
 class GradientClippingConfig(BaseModel):

@@ -456,3 +456,37 @@ def test_resume_with_length_bucketed_data_lora_and_profiling(tmp_path):
     want = full.state.tracked_modules.modules[0].state_dict()
     for k, v in resumed.state.tracked_modules.modules[0].state_dict().items():
         torch.testing.assert_close(v, want[k], rtol=0, atol=0, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_fp8_linear_switch_of_the_model_stage_factory(tmp_path):
+    """``model_stage_factory.fp8_linear`` re-classes the selected dense projections; the job trains (fp8 emulation on CPU)."""
+    from d9d_b200.kernel.fp8 import Fp8Linear
+    from d9d_b200.loop.config import Fp8LinearConfig
+
+    trainer = _make_trainer(tmp_path)
+    plain = trainer.state.tracked_modules.modules[0]
+    assert not any(isinstance(m, Fp8Linear) for m in plain.modules())
+
+    from d9d_b200.core.dist_context import DeviceMeshParameters
+    from d9d_b200.loop.auto import AutoLRSchedulerProvider, AutoOptimizerProvider
+    from d9d_b200.loop.auto.auto_lr_scheduler import PiecewiseConfig
+    from d9d_b200.loop.auto.auto_optimizer import AdamWOptimizerConfig
+    from d9d_b200.loop.run import TrainingConfigurator
+
+    cfg = trainer_config(tmp_path / "fp8", log_dir=tmp_path / "fp8" / "logs")
+    cfg.model_stage_factory.fp8_linear = Fp8LinearConfig(include=r"self_attn|mlp")
+    sched = PiecewiseConfig.model_validate({"name": "piecewise", "scheduler": {"initial_multiplier": 1.0, "phases": [
+        {"mode": "rest", "target_multiplier": 1.0, "curve": {"type": "linear"}}]}})
+    # hidden 32 / intermediate 64 / q 32 / kv 16: every projection of the dense model is a multiple of 16
+    fp8_trainer = TrainingConfigurator(
+        mesh=DeviceMeshParameters(), parameters=cfg, task_provider=lambda ctx: SFTTask(ctx.dist_context),
+        model_provider=LMProvider(dense_params(2)), data_provider=SyntheticDataProvider(num_samples=64),
+        optimizer_provider=AutoOptimizerProvider(AdamWOptimizerConfig(lr=3e-3, weight_decay=0.0)),
+        lr_scheduler_provider=AutoLRSchedulerProvider(sched)).configure()
+    model = fp8_trainer.state.tracked_modules.modules[0]
+    converted = [n for n, m in model.named_modules() if isinstance(m, Fp8Linear)]
+    assert converted and all(("self_attn" in n or "mlp" in n) for n in converted) and not any("lm_head" in n for n in converted)
+    assert set(model.state_dict()) == set(plain.state_dict())  # state-dict keys are unchanged
+    fp8_trainer.train()
+    losses, _ = _read_losses(tmp_path / "fp8")
+    assert losses[max(losses)] < losses[min(losses)]
