@@ -145,6 +145,7 @@ class PipelineScheduleExecutor(PipelineSchedule):
                         self._transport.post(act)
         self._transport.wait_send_all()
         for stage in self._stages.values():
+            stage.finish_step()
             stage.assert_drained()
 
 

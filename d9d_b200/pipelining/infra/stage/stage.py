@@ -1,6 +1,7 @@
 from __future__ import annotations
 
 import dataclasses
+import os
 from collections.abc import Mapping
 from typing import Any
 
@@ -31,12 +32,81 @@ class _AlreadyDone:
     """Placeholder for a weight pass whose work was done together with the input pass."""
 
 
-def _manages_parameter_lifetime(module: nn.Module) -> bool:
-    """FSDP frees the unsharded parameters and reduce-scatters their gradients from hooks around *complete* backward
-    passes; replaying part of the graph later would read freed storage and bypass the reduction."""
-    from torch.distributed.fsdp import FSDPModule
+class _FsdpSplitBackward:
+    """Split backward (input pass now, weight pass later) over FSDP2-managed stages.
 
-    return any(isinstance(m, FSDPModule) for m in module.modules())
+    FSDP frees the unsharded parameters and reduce-scatters their gradients from hooks that fire when a backward pass
+    reaches the module inputs - i.e. during the *input* pass, before any weight gradient exists, after which the deferred
+    weight pass would read freed storage.  While a stage has split backward work in flight this guard therefore switches
+    FSDP into its gradient-accumulation mode (no reshard after forward / backward, no gradient reduction, "not the last
+    backward"): parameters stay unsharded, weight gradients accumulate on the unsharded parameters.  ``release()`` - called
+    by the executor at the end of the pipeline step - restores the flags and runs FSDP's post-backward once: one
+    reduce-scatter per step, parameters resharded.  The same protocol as ``torch.distributed.pipelining`` uses
+    (``stage.py: backward_maybe_with_nosync / perform_reduce_grad``); it relies on FSDP2's private state objects, so any
+    failure to find them falls back to running the whole backward in the input slot.
+    """
+
+    def __init__(self, module: nn.Module):
+        from torch.distributed.fsdp import FSDPModule
+
+        self._modules = [m for m in module.modules() if isinstance(m, FSDPModule)]
+        self._saved: list[tuple] | None = None
+        self.supported = bool(self._modules) and os.environ.get("D9D_PP_FSDP_SPLIT", "1") != "0"
+        if self.supported:
+            try:
+                for m in self._modules:
+                    state = m._get_fsdp_state()  # noqa: SLF001
+                    _ = state._state_ctx, state._fsdp_param_group, state._root_post_backward_final_callback  # noqa: SLF001
+            except AttributeError:
+                self.supported = False
+
+    def __bool__(self) -> bool:
+        return bool(self._modules)
+
+    @property
+    def engaged(self) -> bool:
+        return self._saved is not None
+
+    def engage(self) -> None:
+        if self._saved is not None:
+            return
+        saved = []
+        for m in self._modules:
+            state = m._get_fsdp_state()  # noqa: SLF001
+            group = state._fsdp_param_group  # noqa: SLF001
+            saved.append((state, state._auto_reshard_after_forward,  # noqa: SLF001
+                          None if group is None else (group.post_forward_mesh_info, group.reshard_after_backward, group.reduce_grads,
+                                                      group.all_reduce_grads)))
+            m.set_is_last_backward(False)
+            m.set_reshard_after_backward(False, recurse=False)
+            m.set_requires_gradient_sync(False, recurse=False)
+            m.set_reshard_after_forward(False, recurse=False)
+        self._saved = saved
+
+    def unshard(self) -> None:
+        """All-gather (a no-op when already done) and register the unsharded parameters on the modules: the autograd graph of a
+        forward pass hangs off *those* tensors, and the split-backward analysis looks parameters up through the modules."""
+        for m in self._modules:
+            m.unshard()
+
+    def release(self) -> None:
+        if self._saved is None:
+            return
+        saved, self._saved = self._saved, None
+        for m, (state, auto, group_flags) in zip(self._modules, saved, strict=True):
+            state._auto_reshard_after_forward = auto  # noqa: SLF001
+            group = state._fsdp_param_group  # noqa: SLF001
+            if group is not None and group_flags is not None:
+                group.post_forward_mesh_info, group.reshard_after_backward, group.reduce_grads, group.all_reduce_grads = group_flags
+            m.set_is_last_backward(True)
+        roots = []
+        for state, _auto, _flags in saved:
+            if state._fsdp_param_group is not None:  # noqa: SLF001
+                state._fsdp_param_group.post_backward()  # noqa: SLF001  reduce-scatter of the accumulated gradients, reshard
+            if getattr(state._state_ctx, "all_states", None) and state._state_ctx.all_states[0] is state:  # noqa: SLF001
+                roots.append(state)
+        for state in roots or [saved[0][0]]:
+            state._root_post_backward_final_callback()  # noqa: SLF001  joins the reduction streams, resets FSDP's step state
 
 
 class PipelineStage:
@@ -58,6 +128,7 @@ class PipelineStage:
         self._input_grads: dict[int, dict[str, torch.Tensor | None]] = {}
         self._deferred: dict[int, DeferredWeightBackward | _DeferredFull | _AlreadyDone] = {}
         self._can_split_backward: bool | None = None
+        self._fsdp: _FsdpSplitBackward | None = None
 
     @property
     def info(self) -> PipelineStageInfo:
@@ -165,10 +236,17 @@ class PipelineStage:
         in_list = [record.inputs[k] for k in in_keys]
 
         if self._can_split_backward is None:
-            self._can_split_backward = not _manages_parameter_lifetime(self._module)
+            self._fsdp = _FsdpSplitBackward(self._module)
+            self._can_split_backward = (not self._fsdp) or self._fsdp.supported
+        if not full_backward and self._fsdp:
+            if self._can_split_backward:
+                self._fsdp.engage()  # parameters stay unsharded, gradients unreduced, until the end of this pipeline step
+                self._fsdp.unshard()
         if not full_backward and not self._can_split_backward:
-            # FSDP-sharded stage: the input slot of a zero-bubble schedule runs the whole backward (correct, merely
-            # without the bubble-filling benefit on this stage); the weight slot becomes a no-op
+            # FSDP-sharded stage without the private hooks this needs: the input slot of a zero-bubble schedule runs the whole
+            # backward (correct, merely without the bubble-filling benefit on this stage); the weight slot becomes a no-op
+            if os.environ.get("D9D_PP_FSDP_SPLIT") == "require":
+                raise RuntimeError("split backward over FSDP parameters was required but FSDP's state objects were not found")
             grads = backward_full(outs, out_grads, in_list)
             self._deferred[microbatch_index] = _AlreadyDone()
             if not self._info.is_current_stage_first:
@@ -203,7 +281,14 @@ class PipelineStage:
             backward_weight(deferred)
 
     # ------------------------------------------------------------------ housekeeping
+    def finish_step(self) -> None:
+        """End of one pipeline step: gradients of a split backward over FSDP parameters are reduced, parameters resharded."""
+        if self._fsdp is not None and self._fsdp.engaged:
+            self._fsdp.release()
+
     def reset(self) -> None:
+        if self._fsdp is not None and self._fsdp.engaged:  # a step that raised half-way: leave FSDP in a sane state
+            self._fsdp.release()
         for ch in (self._fwd_in, self._bwd_in):
             if ch is not None:
                 ch.reset()

@@ -362,13 +362,18 @@ _PIPELINE_COMBINATIONS = [
     # split backward through real decoder layers: interleaved zero-bubble 1F1B and the V-shaped zero-bubble schedule
     ({"pipeline_parallel": 2, "context_parallel_replicate": 2}, {"schedule": "1f1b", "num_stages_per_rank": 2, "zero_bubble": True}, False),
     ({"pipeline_parallel": 2, "context_parallel_replicate": 2, "expert_parallel": 2}, {"schedule": "zero_bubble_v"}, True),
+    # split backward over FSDP-sharded stages: parameters stay unsharded between the input and the weight pass, one
+    # reduce-scatter at the end of the pipeline step (D9D_PP_FSDP_SPLIT=require makes the fallback an error)
+    ({"pipeline_parallel": 2, "context_parallel_shard": 2}, {"schedule": "1f1b", "num_stages_per_rank": 1, "zero_bubble": True}, False),
+    ({"pipeline_parallel": 2, "context_parallel_shard": 2}, {"schedule": "zero_bubble_v"}, True),
 ]
 
 
 @pytest.mark.dist
-def test_pipeline_combinations_reproduce_the_single_process_run(tmp_path):
+def test_pipeline_combinations_reproduce_the_single_process_run(tmp_path, monkeypatch):
     """Pipeline schedules combined with expert parallelism / FSDP / activation recomputation on meshes whose ranks all read the
     same samples (context parallel), so the loss trajectory can be compared with the single-process job step by step."""
+    monkeypatch.setenv("D9D_PP_FSDP_SPLIT", "require")  # inherited by the spawned ranks
     layers = 4  # two stages per rank on two pipeline ranks need four layers
     jobs = []
     for moe in (False, True):
