@@ -68,6 +68,7 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         # Ownership is interleaved: the arena is cut into equal chunks and chunk c belongs to rank c % world, so every
         # rank has something to reduce as soon as *any* region of the gradients is final (backward finishes the arena
         # back to front).  A rank's moments for chunk c live in local slot c // world.
+        self._real_numel = total  # before padding to whole rows of chunks
         per_rank = -(-total // self._world)
         self._chunk = max(1024, min(int(chunk_numel), -(-per_rank // 1024) * 1024))
         row = self._chunk * self._world
@@ -272,16 +273,51 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         self.grad_arena.buffer.zero_()
 
     def state_dict(self) -> dict[str, Any]:
-        return {f"shard_{self._rank}_of_{self._world}": {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq},
-                "chunk_numel": self._chunk,
+        """Moments are stored per *global chunk* (``chunks/<chunk id>``), so a checkpoint does not depend on the number of
+        replicas it was written with as long as the chunk size is the same (it is ``chunk_numel`` for every model with more
+        than ``world * chunk_numel`` parameters): each rank saves the chunks it owns, and after a restart with another world
+        size every rank asks for the chunks it owns *now*."""
+        return {"chunks": chunk_state_views(self.exp_avg, self.exp_avg_sq, self._chunk, self._world, self._rank, self._real_numel),
+                "chunk_numel": self._chunk, "numel": self._real_numel,
                 "step": self._step_count, "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, state_dict: dict[str, Any]) -> None:
         if int(state_dict.get("chunk_numel", self._chunk)) != self._chunk:
-            raise ValueError("checkpoint was written with a different chunk size (ownership layout differs)")
-        shard = state_dict[f"shard_{self._rank}_of_{self._world}"]
-        self.exp_avg.copy_(shard["exp_avg"])
-        self.exp_avg_sq.copy_(shard["exp_avg_sq"])
+            raise ValueError(f"checkpoint was written with chunk size {state_dict.get('chunk_numel')} but this run uses {self._chunk} "
+                             "(small models derive the chunk size from the replica count): the ownership layout differs")
+        legacy = f"shard_{self._rank}_of_{self._world}"
+        if "chunks" in state_dict:
+            load_chunk_state(state_dict["chunks"], self.exp_avg, self.exp_avg_sq, self._chunk, self._world, self._rank, self._real_numel)
+        elif legacy in state_dict:  # format of the first round: one blob per (rank, world)
+            self.exp_avg.copy_(state_dict[legacy]["exp_avg"])
+            self.exp_avg_sq.copy_(state_dict[legacy]["exp_avg_sq"])
+        else:
+            raise KeyError("optimizer checkpoint has neither per-chunk moments nor a shard for this (rank, world)")
         self._step_count = int(state_dict["step"])
         for g, saved in zip(self.param_groups, state_dict["param_groups"], strict=True):
             g.update(saved)
+
+
+def owned_real_chunks(chunk: int, world: int, rank: int, real_numel: int, rows: int) -> list[tuple[int, int]]:
+    """``(global chunk id, local slot)`` of the chunks of ``rank`` that hold parameters (chunks past ``real_numel`` are padding
+    of the arena to a multiple of ``world`` chunks)."""
+    last = -(-real_numel // chunk)  # number of chunks that contain at least one real element
+    return [(row * world + rank, row) for row in range(rows) if row * world + rank < last]
+
+
+def chunk_state_views(exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, chunk: int, world: int, rank: int, real_numel: int
+                      ) -> dict[str, dict[str, torch.Tensor]]:
+    rows = exp_avg.numel() // chunk
+    return {str(c): {"exp_avg": exp_avg[slot * chunk : (slot + 1) * chunk], "exp_avg_sq": exp_avg_sq[slot * chunk : (slot + 1) * chunk]}
+            for c, slot in owned_real_chunks(chunk, world, rank, real_numel, rows)}
+
+
+def load_chunk_state(chunks: dict[str, dict[str, torch.Tensor]], exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, chunk: int, world: int,
+                     rank: int, real_numel: int) -> None:
+    rows = exp_avg.numel() // chunk
+    for c, slot in owned_real_chunks(chunk, world, rank, real_numel, rows):
+        entry = chunks.get(str(c))
+        if entry is None:
+            raise KeyError(f"optimizer checkpoint lacks the moments of chunk {c}")
+        exp_avg[slot * chunk : (slot + 1) * chunk].copy_(entry["exp_avg"])
+        exp_avg_sq[slot * chunk : (slot + 1) * chunk].copy_(entry["exp_avg_sq"])
