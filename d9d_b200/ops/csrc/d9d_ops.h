@@ -178,7 +178,8 @@ struct FlashAttnArgs {
   int window_left, window_right;
   float scale, softcap;
 };
-// variant: reserved (P is kept in tensor memory: the A operand of the PV GEMM is read from TMEM)
+// variant: reserved (the forward hands P to the PV GEMM through swizzled shared memory; the backward kernels read P^T / dS^T
+// as the A operand straight from tensor memory)
 void flash_attn_fwd(const FlashAttnArgs& a, int variant, cudaStream_t stream);
 // backward = delta pre-pass (delta[b,h,q] = sum_d dO*O, written to a.delta) followed by the dK/dV and dQ kernels (which read
 // a.delta; the caller may subtract d(lse) from it in between)
