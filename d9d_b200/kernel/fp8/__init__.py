@@ -148,40 +148,90 @@ class Fp8LinearFunction(Function):
         return dx, dw
 
 
-def fp8_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
-    """``x @ weight^T (+ bias)`` in fp8 (see :class:`Fp8LinearFunction`); shapes must satisfy ``in % 16 == 0``,
-    ``out % 16 == 0``."""
-    if x.shape[-1] % 16 or weight.shape[0] % 16:
-        raise ValueError(f"fp8_linear: feature dims must be multiples of 16 (got in={x.shape[-1]}, out={weight.shape[0]})")
+class MxFp8LinearFunction(Function):
+    """``y = x @ W^T`` with all three GEMMs in **MXFP8** (e4m3 elements, one power-of-two scale per 32 elements of the
+    reduction dimension, consumed by ``tcgen05.mma.kind::mxf8f6f4.block_scale``).
+
+    Every GEMM quantises both operands along *its own* reduction dimension, so the backward GEMMs work on transposed copies:
+
+    forward  ``y  = MX(x)[M,K]    · MX(W)[N,K]^T``          reduction over ``in``
+    dgrad    ``dx = MX(dy)[M,N]   · MX(W^T)[K,N]^T``        reduction over ``out``
+    wgrad    ``dW = MX(dy^T)[N,M] · MX(x^T)[K,M]^T``        reduction over tokens
+
+    ``in``, ``out`` and the token count must be multiples of 128 (one scale-factor block of the tensor core).
+    """
+
+    @staticmethod
+    def forward(ctx: Any, x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.x_shape = x.shape
+        return mx_mm(x2, weight).view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx: Any, grad_output: torch.Tensor):  # type: ignore[override]
+        x2, weight = ctx.saved_tensors
+        dy = grad_output.reshape(-1, grad_output.shape[-1])
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.inputs):
+            dx = mx_mm(dy, weight.t().contiguous()).view(ctx.x_shape)
+        if ctx.needs_input_grad[1] and GLOBAL_GRAD_CONTEXT.check_direction(GradDirection.weight):
+            dw = mx_mm(dy.t().contiguous(), x2.t().contiguous()).to(grad_dtype_of(weight))
+        return dx, dw
+
+
+def fp8_linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, recipe: str = "rowwise") -> torch.Tensor:
+    """``x @ weight^T (+ bias)`` in fp8.  ``recipe="rowwise"``: dynamic per-row / per-column fp32 scales
+    (:class:`Fp8LinearFunction`, feature sizes multiples of 16); ``recipe="mx"``: MXFP8 block scaling
+    (:class:`MxFp8LinearFunction`, feature sizes and token count multiples of 128)."""
+    if recipe not in ("rowwise", "mx"):
+        raise ValueError(f"unknown fp8 recipe {recipe!r}")
+    granule = 16 if recipe == "rowwise" else 128
+    tokens = x.numel() // max(x.shape[-1], 1)
+    if x.shape[-1] % granule or weight.shape[0] % granule or (recipe == "mx" and tokens % granule):
+        raise ValueError(f"fp8_linear[{recipe}]: sizes must be multiples of {granule} (got in={x.shape[-1]}, out={weight.shape[0]}, "
+                         f"tokens={tokens})")
     if on_gpu(x) and (x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16):
         raise RuntimeError("fp8_linear: bf16 activations and weights required on CUDA")
-    out = Fp8LinearFunction.apply(x, weight)
+    out = (Fp8LinearFunction if recipe == "rowwise" else MxFp8LinearFunction).apply(x, weight)
     return out if bias is None else out + bias
 
 
 class Fp8Linear(nn.Linear):
-    """Drop-in ``nn.Linear`` whose matmuls run in e4m3 (weights stay bf16 master copies)."""
+    """Drop-in ``nn.Linear`` whose matmuls run in e4m3 (weights stay bf16 master copies); ``fp8_recipe`` (class default
+    ``"rowwise"``, set per instance by :func:`convert_linears_to_fp8`) selects the scaling scheme."""
+
+    fp8_recipe: str = "rowwise"
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
-        return fp8_linear(x, self.weight, self.bias)
+        return fp8_linear(x, self.weight, self.bias, recipe=self.fp8_recipe)
 
 
-def convert_linears_to_fp8(module: nn.Module, predicate=lambda name, m: True) -> int:
+def convert_linears_to_fp8(module: nn.Module, predicate=lambda name, m: True, recipe: str = "rowwise") -> int:
     """Re-classes every eligible linear layer of ``module`` to :class:`Fp8Linear` in place: plain ``nn.Linear`` and the
-    framework's ``module.block.linear.Linear`` (not LoRA wrappers or other subclasses), feature dims multiples of 16,
-    ``predicate(name, module)`` true.  Parameters are shared, state-dict keys unchanged.  Returns the number converted."""
+    framework's ``module.block.linear.Linear`` (not LoRA wrappers or other subclasses), feature dims multiples of 16 (128 for
+    the ``"mx"`` recipe), ``predicate(name, module)`` true.  Parameters are shared, state-dict keys unchanged.  Returns the
+    number converted."""
     from d9d_b200.module.block.linear import Linear as NativeLinear
 
+    if recipe not in ("rowwise", "mx"):
+        raise ValueError(f"unknown fp8 recipe {recipe!r}")
+    granule = 16 if recipe == "rowwise" else 128
     n = 0
     for name, m in module.named_modules():
-        if type(m) in (nn.Linear, NativeLinear) and m.in_features % 16 == 0 and m.out_features % 16 == 0 and predicate(name, m):
+        if type(m) in (nn.Linear, NativeLinear) and m.in_features % granule == 0 and m.out_features % granule == 0 and predicate(name, m):
             m.__class__ = Fp8Linear
+            m.fp8_recipe = recipe
             n += 1
     return n
 
 
 __all__ = [
-    "Fp8Linear", "Fp8LinearFunction", "convert_linears_to_fp8", "dequantize_mx", "fp8_linear", "mx_mm", "mx_scale_exponent",
+    "Fp8Linear", "Fp8LinearFunction", "MxFp8LinearFunction", "convert_linears_to_fp8", "dequantize_mx", "fp8_linear", "mx_mm", "mx_scale_exponent",
     "quantize_colwise_t", "quantize_colwise_t_reference", "quantize_mx_reference", "quantize_rowwise", "quantize_rowwise_reference",
     "scaled_mm", "unpack_mx_scales",
 ]

@@ -99,7 +99,8 @@ class ModelStageFactory:
         from d9d_b200.kernel.fp8 import convert_linears_to_fp8
 
         include, exclude = re.compile(cfg.include), re.compile(cfg.exclude) if cfg.exclude else None
-        n = convert_linears_to_fp8(model, lambda name, _m: bool(include.search(name)) and not (exclude and exclude.search(name)))
+        n = convert_linears_to_fp8(model, lambda name, _m: bool(include.search(name)) and not (exclude and exclude.search(name)),
+                                   recipe=cfg.recipe)
         self._ctx.logger.info(f"fp8: {n} linear layers of this stage run in e4m3")
 
     def build_pipeline_and_modules(self) -> tuple[PipelineScheduleInfo, TrackedModules]:

@@ -1,4 +1,5 @@
 from pathlib import Path
+from typing import Literal
 
 from pydantic import BaseModel
 
@@ -49,6 +50,7 @@ class Fp8LinearConfig(BaseModel):
 
     include: str = r".*"
     exclude: str | None = r"lm_head|cls_head|embedding_head|router|\.gate$"
+    recipe: Literal["rowwise", "mx"] = "rowwise"  # "mx": MXFP8 block scaling (feature sizes and token count multiples of 128)
 
 
 class ModelStageFactoryConfig(BaseModel):

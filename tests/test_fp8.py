@@ -55,3 +55,27 @@ def test_convert_linears():
     m = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.ReLU(), torch.nn.Linear(64, 10))
     assert fp8.convert_linears_to_fp8(m) == 1 and isinstance(m[0], fp8.Fp8Linear) and type(m[2]) is torch.nn.Linear
     assert m(torch.randn(3, 32)).shape == (3, 10)
+
+
+def test_mxfp8_linear_autograd_close_to_exact():
+    torch.manual_seed(0)
+    x = torch.randn(2, 64, 128, requires_grad=True)  # 128 tokens, in = 128
+    w = (torch.randn(256, 128) * 0.1).requires_grad_()
+    y = fp8.fp8_linear(x, w, recipe="mx")
+    y.float().square().mean().backward()
+    x2, w2 = x.detach().clone().requires_grad_(), w.detach().clone().requires_grad_()
+    y2 = x2 @ w2.t()
+    y2.square().mean().backward()
+    assert ((y.float() - y2).norm() / y2.norm()) < 0.06
+    assert ((x.grad - x2.grad).norm() / x2.grad.norm()) < 0.08
+    assert ((w.grad - w2.grad).norm() / w2.grad.norm()) < 0.08
+    import pytest
+
+    with pytest.raises(ValueError):
+        fp8.fp8_linear(torch.randn(3, 128), w, recipe="mx")  # 3 tokens: not a multiple of 128
+
+
+def test_convert_linears_with_the_mx_recipe():
+    m = torch.nn.Sequential(torch.nn.Linear(128, 256), torch.nn.ReLU(), torch.nn.Linear(256, 48))
+    assert fp8.convert_linears_to_fp8(m, recipe="mx") == 1 and m[0].fp8_recipe == "mx" and type(m[2]) is torch.nn.Linear
+    assert m(torch.randn(128, 128)).shape == (128, 48)

@@ -102,3 +102,4 @@ def test_fp8_linear_function_matches_emulation():
     assert _rel(w.grad.cpu(), wc.grad) < 2e-2
     ref = x.detach().float() @ w.detach().float().t()
     assert _rel(y, ref) < 0.06
+
