@@ -1,5 +1,6 @@
 from __future__ import annotations
 
+import dataclasses
 import os
 from collections.abc import Iterable
 from typing import Any
@@ -45,14 +46,19 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
     def __init__(self, params: Iterable[nn.Parameter], group: dist.ProcessGroup, lr: float, betas: tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-2, state_dtype: torch.dtype = torch.bfloat16,
                  max_norm: float | None = None, seed: int = 0, chunk_numel: int = 1 << 24, overlap_waves: int = 8):
-        params = [p for p in params if p.requires_grad]
+        groups_in = list(params)
+        if groups_in and isinstance(groups_in[0], dict):  # torch-style parameter groups (e.g. no weight decay for norms)
+            groups_in = [{**g, "params": [p for p in g["params"] if p.requires_grad]} for g in groups_in]
+            groups_in = [g for g in groups_in if g["params"]]
+            params = [p for g in groups_in for p in g["params"]]
+        else:
+            params = [p for p in groups_in if p.requires_grad]
+            groups_in = params
         if not params:
             raise ValueError("NvlinkShardedAdamW needs at least one trainable parameter")
         if any(_local(p).dtype != torch.bfloat16 for p in params):
             raise ValueError("NvlinkShardedAdamW supports bf16 parameters only")
-        super().__init__(params, {"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay})
-        if len(self.param_groups) != 1:
-            raise ValueError("NvlinkShardedAdamW supports a single parameter group")
+        super().__init__(groups_in, {"lr": lr, "betas": betas, "eps": eps, "weight_decay": weight_decay})
         self._group = group
         self._world = group.size()
         self._rank = group.rank()
@@ -61,20 +67,18 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         self._step_count = 0
         device = _local(params[0]).device
 
-        offsets, total = [], 0
-        for p in params:
-            offsets.append(total)
-            total += (_local(p).numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         # Ownership is interleaved: the arena is cut into equal chunks and chunk c belongs to rank c % world, so every
         # rank has something to reduce as soon as *any* region of the gradients is final (backward finishes the arena
-        # back to front).  A rank's moments for chunk c live in local slot c // world.
-        self._real_numel = total  # before padding to whole rows of chunks
-        per_rank = -(-total // self._world)
-        self._chunk = max(1024, min(int(chunk_numel), -(-per_rank // 1024) * 1024))
-        row = self._chunk * self._world
-        total = -(-total // row) * row
+        # back to front).  A rank's moments for chunk c live in local slot c // world.  With several parameter groups every
+        # group starts on a whole row of chunks, so a chunk never mixes hyper-parameters.
+        params = [p for g in self.param_groups for p in g["params"]]
+        layout = plan_arena_layout([[_local(p).numel() for p in g["params"]] for g in self.param_groups], self._world, int(chunk_numel))
+        offsets, total = layout.offsets, layout.total
+        self._real_numel = layout.real_numel  # end of the last parameter (before padding to whole rows of chunks)
+        self._chunk = layout.chunk
         self._numel = total
-        self._rows = total // row  # chunks per rank
+        self._rows = layout.rows  # chunks per rank
+        self._row_group = layout.row_group  # parameter group of every row of chunks
         self._shard = self._rows * self._chunk
 
         self.param_arena = SymmetricArena(total, torch.bfloat16, device, group)
@@ -223,8 +227,6 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         if closure is not None:
             raise ValueError("closures are not supported")
         ops = native_ops()
-        group = self.param_groups[0]
-        beta1, beta2 = group["betas"]
         self._step_count += 1
         multicast = self.uses_multicast
         remaining = range(0, self._rows - self._reduced_rows)
@@ -252,14 +254,15 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
             self._scale.copy_(clip if scale is None else clip * scale)
             scale = self._scale
         self.grad_arena.barrier()  # all replicas have read my gradients: they may be overwritten / zeroed
-        lr = group["lr"]
         mc_param = self.param_arena.multicast_ptr if multicast else 0
         for row in range(self._rows):
+            group = self.param_groups[self._row_group[row]]  # a row of chunks never mixes parameter groups
+            beta1, beta2 = group["betas"]
             begin, end = self._owned_range(row)
             slot = slice(row * self._chunk, (row + 1) * self._chunk)
             ops.nvl_adamw_shard_(self.param_arena.buffer, self.grad_arena.buffer, self.exp_avg[slot], self.exp_avg_sq[slot],
                                  self.param_arena.peer_ptrs_dev, mc_param, begin, end, self._world, self._rank,
-                                 float(lr), beta1, beta2, group["eps"], group["weight_decay"],
+                                 float(group["lr"]), beta1, beta2, group["eps"], group["weight_decay"],
                                  1.0 - beta1**self._step_count, 1.0 - beta2**self._step_count,
                                  self._seed + 7919 * self._step_count, scale)
         self.grad_arena.buffer.zero_()
@@ -296,6 +299,41 @@ class NvlinkShardedAdamW(torch.optim.Optimizer):
         self._step_count = int(state_dict["step"])
         for g, saved in zip(self.param_groups, state_dict["param_groups"], strict=True):
             g.update(saved)
+
+
+@dataclasses.dataclass(frozen=True)
+class ArenaLayout:
+    offsets: list[int]      # element offset of every parameter (groups concatenated in order)
+    chunk: int              # elements per chunk
+    rows: int               # chunks per rank
+    total: int              # arena elements (= rows * world * chunk)
+    real_numel: int         # end of the last parameter
+    row_group: list[int]    # parameter group owning each row of chunks
+
+
+def plan_arena_layout(group_sizes: list[list[int]], world: int, chunk_numel: int) -> ArenaLayout:
+    """Flat arena layout: parameters 8-element aligned, the arena cut into ``rows x world`` chunks of equal size.  A single
+    group is laid out densely; with several groups each one starts on a row boundary (``world * chunk`` elements), so that
+    every chunk has one set of hyper-parameters."""
+    def aligned(n: int) -> int:
+        return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+    dense_total = sum(aligned(n) for sizes in group_sizes for n in sizes)
+    per_rank = -(-dense_total // world)
+    chunk = max(1024, min(int(chunk_numel), -(-per_rank // 1024) * 1024))
+    row = chunk * world
+    offsets: list[int] = []
+    row_group: list[int] = []
+    total = real = 0
+    for g, sizes in enumerate(group_sizes):
+        start = total
+        for n in sizes:
+            offsets.append(total)
+            real = total + n
+            total += aligned(n)
+        total = -(-total // row) * row if (len(group_sizes) > 1 or g == len(group_sizes) - 1) else total
+        row_group += [g] * ((total - start) // row)
+    return ArenaLayout(offsets=offsets, chunk=chunk, rows=total // row, total=total, real_numel=real, row_group=row_group)
 
 
 def owned_real_chunks(chunk: int, world: int, rank: int, real_numel: int, rows: int) -> list[tuple[int, int]]:
