@@ -62,3 +62,31 @@ def test_graft_entry_exposes_build_and_smoke():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert callable(mod.build) and callable(mod.smoke)
+
+
+def test_end_to_end_arm_plumbing_runs_on_cpu(tmp_path, monkeypatch):
+    """The Trainer job ``bench.py`` times for its ``e2e`` number (providers, loader, optimizer, loss logging), dry-run on CPU with
+    a tiny model: the timing itself needs CUDA events, the plumbing does not."""
+    import types
+
+    import d9d_b200.bench_support as support
+    from d9d_b200.module.model.qwen3_moe import Qwen3MoEForCausalLMParameters, Qwen3MoELayerParameters, Qwen3MoEParameters
+
+    original = support.trainer_config_for_bench
+
+    def without_pinned_memory(*a, **k):
+        cfg = original(*a, **k)
+        cfg["data_loading"]["pin_memory"] = False  # pinning needs a CUDA runtime
+        return cfg
+
+    monkeypatch.setattr(support, "trainer_config_for_bench", without_pinned_memory)
+    args = types.SimpleNamespace(warmup=1, steps=2, accum=2, microbatch=2, seq_len=32, layout="dp", dp_impl="nvlink", checkpointing=False)
+    params = Qwen3MoEForCausalLMParameters(model=Qwen3MoEParameters(
+        layer=Qwen3MoELayerParameters(hidden_size=64, intermediate_size=32, num_experts=4, experts_top_k=2, num_attention_heads=4,
+                                      num_key_value_heads=2, rms_norm_eps=1e-6, head_dim=16),
+        num_hidden_layers=2, rope_base=10000, max_position_ids=64, split_vocab_size={"regular": 200, "special": 24},
+        split_vocab_order=["regular", "special"]))
+    job = support.TrainerEndToEnd(args, 1, params, 224, str(tmp_path))
+    job.trainer.train()
+    assert job.trainer.state.stepper.current_step == 3
+    assert 0 < float(job.trainer.state.logger.last_loss) < 10
