@@ -25,11 +25,11 @@ def _gpus() -> int:
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-def _torchrun(world: int, script_args: list[str], timeout: int = 420) -> None:
+def _torchrun(world: int, script_args: list[str], timeout: int = 420, env: dict[str, str] | None = None) -> None:
     port = 29800 + (os.getpid() % 150)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), *script_args]
-    res = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=timeout)
+    res = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=timeout, env={**os.environ, **(env or {})})
     tail = (res.stdout[-6000:] + "\n" + res.stderr[-3000:])
     log_dir = os.path.join(REPO, "gpurun_out")
     os.makedirs(log_dir, exist_ok=True)
@@ -45,6 +45,16 @@ def test_model_gradients_match_single_gpu_over_meshes(world):
     if world != max(w for w in (2, 4, 8) if w <= _gpus()) and os.environ.get("D9D_TEST_ALL_WORLDS", "0") != "1":
         pytest.skip("only the largest world size the box offers runs by default (D9D_TEST_ALL_WORLDS=1 for all)")
     _torchrun(world, ["benchmarks/validate_parallelism_gpu.py"])
+
+
+def test_fsdp_collectives_over_peer_memory():
+    """FSDP / HSDP meshes with FSDP's all-gather / reduce-scatter replaced by pulls over NVLink peer memory
+    (``D9D_FSDP_COMM=peer``, ``module/parallelism/api/_peer_memory_fsdp.py``): same gradient check as the NCCL run."""
+    world = max((w for w in (2, 4, 8) if w <= _gpus()), default=0)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    meshes = {2: ["dps2"], 4: ["dps4", "dpr2_dps2"], 8: ["dps8", "dpr2_dps4"]}[world]
+    _torchrun(world, ["benchmarks/validate_parallelism_gpu.py", "--skip-attention", "--meshes", *meshes], env={"D9D_FSDP_COMM": "peer"})
 
 
 def _pp_gpu_worker(rank, world, cases):
